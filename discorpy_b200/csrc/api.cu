@@ -1,0 +1,719 @@
+// api.cu -- C ABI of libdiscorpy_b200.so (declared in include/discorpy_b200.h):
+// argument validation, launch planning (tile grid, staged-box size, TMA
+// descriptor) and kernel dispatch.  Host side only; kernels are in remap.cuh.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <mutex>
+
+#include "remap.cuh"
+#include "microbench.cuh"
+
+using namespace dcb;
+
+// ---------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+struct LastPlan {
+    int path, bw, bh, grid, smem;
+};
+static thread_local LastPlan g_last_plan = {DCB_PATH_DIRECT, 0, 0, 0, 0};
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return fail(DCB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+#define REQUIRE(cond, ...)                              \
+    do {                                                \
+        if (!(cond)) return fail(DCB_ERR_ARG, __VA_ARGS__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// driver entry point for the TMA descriptor encoder (no link-time libcuda)
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static EncodeTiledFn tma_encoder() {
+    std::call_once(g_encode_once, [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) ==
+                cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    });
+    return g_encode;
+}
+
+struct DevProps {
+    int sm_count = 0;
+    int smem_optin = 0;
+    bool ok = false;
+};
+static DevProps g_props[64];
+static std::mutex g_props_mu;
+
+static int device_props(DevProps *out) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(DCB_ERR_ARG, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_props_mu);
+    if (!g_props[dev].ok) {
+        CUDA_TRY(cudaDeviceGetAttribute(&g_props[dev].sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&g_props[dev].smem_optin,
+                                        cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        g_props[dev].ok = true;
+    }
+    *out = g_props[dev];
+    return DCB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// launch planning
+// ---------------------------------------------------------------------------
+// Upper bounds on how far the source coordinate moves per output pixel:
+//   gmain  >= |d xd / d x| , |d yd / d y|      gcross >= |d xd / d y| , |d yd / d x|
+// For the radial map xd = xc + F(r) xu: d xd/d x = F + F' xu^2 / r and
+// d xd/d y = F' xu yu / r, so |F| + |F' r| and |F' r| / 2 bound them; both are
+// sampled on a 1-D grid of r over the radii the requested rows can reach.
+static void radial_slopes(const dcb_radial &m, int W, int row0, int nrows, double *gmain,
+                          double *gcross) {
+    const double xs[2] = {0.0 - m.xc, (double)(W - 1) - m.xc};
+    const double ys[2] = {(double)row0 - m.yc, (double)(row0 + nrows - 1) - m.yc};
+    double rmax = 0.0;
+    for (double x : xs)
+        for (double y : ys) rmax = std::max(rmax, std::sqrt(x * x + y * y));
+    double gm = 0.0, gc = 0.0;
+    const int S = 512;
+    for (int i = 0; i <= S; ++i) {
+        const double r = rmax * i / S;
+        double f = 0.0, fp = 0.0;  // F and F' by Horner
+        for (int k = m.n - 1; k >= 0; --k) {
+            fp = fp * r + f;
+            f = f * r + m.a[k];
+        }
+        gm = std::max(gm, std::fabs(f) + std::fabs(fp * r));
+        gc = std::max(gc, 0.5 * std::fabs(fp * r));
+    }
+    *gmain = gm;
+    *gcross = gc;
+}
+
+static void persp_slopes(const dcb_persp &m, int H, int W, double *gmain, double *gcross) {
+    // The Jacobian of a projective map is monotone along lines where the
+    // denominator keeps its sign; sample a 9x9 grid and keep the maxima.
+    double gm = 0.0, gc = 0.0;
+    const double *c = m.c;
+    for (int iy = 0; iy <= 8; ++iy)
+        for (int ix = 0; ix <= 8; ++ix) {
+            const double x = (W - 1) * ix / 8.0, y = (H - 1) * iy / 8.0;
+            const double den = c[6] * x + c[7] * y + 1.0;
+            const double nx = c[0] * x + c[1] * y + c[2], ny = c[3] * x + c[4] * y + c[5];
+            if (den == 0.0) continue;
+            const double xx = (c[0] * den - nx * c[6]) / (den * den);
+            const double xy = (c[1] * den - nx * c[7]) / (den * den);
+            const double yx = (c[3] * den - ny * c[6]) / (den * den);
+            const double yy = (c[4] * den - ny * c[7]) / (den * den);
+            gm = std::max(gm, std::max(std::fabs(xx), std::fabs(yy)));
+            gc = std::max(gc, std::max(std::fabs(xy), std::fabs(yx)));
+        }
+    *gmain = gm;
+    *gcross = gc;
+}
+
+struct Plan {
+    RemapParams p;
+    CUtensorMap tmap;
+    int grid;
+    size_t smem;
+    int path;
+};
+
+typedef void (*TileKernel)(const RemapParams, const CUtensorMap);
+
+static int plan_and_launch(TileKernel kern, int rpt, RemapParams &p, double gmain, double gcross,
+                           int path_req, size_t src_pitch_bytes, size_t src_slice_bytes,
+                           cudaStream_t stream) {
+    DevProps props;
+    int rc = device_props(&props);
+    if (rc != DCB_OK) return rc;
+    const int TH = kWarps * rpt;
+    p.tiles_x = (p.W + kTileW - 1) / kTileW;
+    p.tiles_y = (p.nrows + TH - 1) / TH;
+    const long long tiles_xy = (long long)p.tiles_x * p.tiles_y;
+
+    // --- can this layout be described to TMA? -------------------------------
+    const bool layout_ok = ((uintptr_t)p.src % 16 == 0) && (src_pitch_bytes % 16 == 0) &&
+                           (src_slice_bytes % 16 == 0) && tma_encoder() != nullptr;
+    if (path_req == DCB_PATH_TMA && !layout_ok)
+        return fail(DCB_ERR_ARG,
+                    "DCB_PATH_TMA needs a 16-byte aligned source with pitch and slice stride "
+                    "multiples of 16 bytes (and a driver exporting cuTensorMapEncodeTiled)");
+    bool staged = layout_ok && path_req != DCB_PATH_DIRECT;
+
+    // --- staged box: bound of the tile's source footprint --------------------
+    int bw = 0, bh = 0, nstage = 0;
+    if (staged) {
+        if (!(gmain < 64.0) || !(gcross < 64.0)) gmain = gcross = 64.0;  // NaN / absurd
+        const double tw = std::min(kTileW, p.W) - 1, th = std::min(TH, p.nrows) - 1;
+        long long need_w = (long long)std::ceil(gmain * tw + gcross * th) + 3;
+        long long need_h = (long long)std::ceil(gmain * th + gcross * tw) + 3;
+        need_w = std::min<long long>(need_w, p.W);
+        need_h = std::min<long long>(need_h, p.ylast - p.yorg + 1);
+        bw = (int)((need_w + 3) / 4 * 4);
+        bh = (int)need_h;
+        // budget: at most ~24 KB per stage so that >= 4 CTAs fit per SM with a 2-deep ring
+        const int max_stage = 24 * 1024;
+        if (bw > 256 || bh > 256 || (long long)bw * bh * 4 > max_stage) {
+            // footprint bound too large (strong magnification somewhere): stage a
+            // modest box; tiles that do not fit fall back to direct gathers.
+            bw = std::min(256, (std::min(kTileW + 16, (p.W + 3) / 4 * 4)));
+            bh = std::min(std::min(TH + 8, p.ylast - p.yorg + 1), max_stage / (bw * 4));
+        }
+        nstage = (p.D > 1) ? 3 : 1;
+    }
+    p.bw = bw;
+    p.bh = bh;
+    p.nstage = nstage;
+    p.box_bytes = (unsigned)(bw * bh * 4);
+    p.stage_bytes = (p.box_bytes + 127u) / 128u * 128u;
+    size_t smem = (size_t)nstage * p.stage_bytes + kMaxStages * sizeof(uint64_t) +
+                  2 * 4 * kWarps * sizeof(int);
+
+    // --- z chunking: enough CTAs to fill the machine, long enough chunks to
+    //     amortise the fp64 coordinate evaluation --------------------------------
+    int zchunk = 1;
+    if (p.D > 1) {
+        const long long want_ctas = (long long)props.sm_count * 16;
+        long long nchunks = std::max<long long>(1, (want_ctas + tiles_xy - 1) / tiles_xy);
+        nchunks = std::min<long long>(nchunks, p.D);
+        zchunk = (int)((p.D + nchunks - 1) / nchunks);
+        zchunk = std::min(zchunk, 64);
+    }
+    p.zchunk = zchunk;
+    const long long nzc = (p.D + zchunk - 1) / zchunk;
+    const long long ntiles = tiles_xy * nzc;
+    if (ntiles > INT_MAX) return fail(DCB_ERR_UNSUPPORTED, "too many tiles (%lld)", ntiles);
+    p.ntiles = (int)ntiles;
+
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (staged) {
+        const int src_rows = p.ylast - p.yorg + 1;
+        const cuuint64_t gdim[3] = {(cuuint64_t)p.W, (cuuint64_t)src_rows, (cuuint64_t)p.D};
+        const cuuint64_t gstr[2] = {(cuuint64_t)src_pitch_bytes,
+                                    (cuuint64_t)(p.D > 1 ? src_slice_bytes
+                                                         : src_pitch_bytes * (size_t)src_rows)};
+        const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        CUresult cr = tma_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)p.src, gdim,
+                                    gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            if (path_req == DCB_PATH_TMA)
+                return fail(DCB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+            staged = false;
+            p.nstage = 0;
+            smem = kMaxStages * sizeof(uint64_t) + 2 * 4 * kWarps * sizeof(int);
+        }
+    }
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute((const void *)kern,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)kern, kThreads, smem));
+    if (occ < 1) return fail(DCB_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
+    const int grid = (int)std::min<long long>(ntiles, (long long)occ * props.sm_count);
+
+    kern<<<grid, kThreads, smem, stream>>>(p, tmap);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_last_plan = {staged ? DCB_PATH_TMA : DCB_PATH_DIRECT, bw, bh, grid, (int)smem};
+    return DCB_OK;
+}
+
+static int check_options(const dcb_options *opt, dcb_options *o) {
+    if (opt == nullptr) {
+        *o = {1, DCB_BLEND_EXACT, DCB_PATH_AUTO, 0};
+        return DCB_OK;
+    }
+    *o = *opt;
+    REQUIRE(o->order == 0 || o->order == 1,
+            "order %d not supported by the CUDA path (0 and 1 are)", o->order);
+    REQUIRE(o->blend >= 0 && o->blend <= 2, "unknown blend %d", o->blend);
+    REQUIRE(o->path >= 0 && o->path <= 2, "unknown path %d", o->path);
+    return DCB_OK;
+}
+
+template <int MAP, bool ROUND32, int RPT>
+static TileKernel pick_kernel(int order, int blend) {
+    if (order == 0) return remap_tile_kernel<MAP, 0, DCB_BLEND_EXACT, ROUND32, RPT>;
+    switch (blend) {
+        case DCB_BLEND_LERP64:
+            return remap_tile_kernel<MAP, 1, DCB_BLEND_LERP64, ROUND32, RPT>;
+        case DCB_BLEND_LERP32:
+            return remap_tile_kernel<MAP, 1, DCB_BLEND_LERP32, ROUND32, RPT>;
+        default:
+            return remap_tile_kernel<MAP, 1, DCB_BLEND_EXACT, ROUND32, RPT>;
+    }
+}
+
+static int check_image_args(const void *src, const void *dst, int H, int W, size_t src_pitch,
+                            size_t dst_pitch) {
+    REQUIRE(src != nullptr && dst != nullptr, "null image pointer");
+    REQUIRE(src != dst, "dst must not alias src");
+    REQUIRE(H >= 1 && W >= 1, "image must be at least 1x1 (got %dx%d)", H, W);
+    REQUIRE(H < (1 << 24) && W < (1 << 24), "image dimension exceeds 2^24 (fp32-exact bound)");
+    REQUIRE(src_pitch >= (size_t)W * 4 && src_pitch % 4 == 0, "bad source pitch %zu", src_pitch);
+    REQUIRE(dst_pitch >= (size_t)W * 4 && dst_pitch % 4 == 0, "bad destination pitch %zu",
+            dst_pitch);
+    return DCB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int dcb_version(void) { return DCB_VERSION_MAJOR * 1000 + DCB_VERSION_MINOR; }
+const char *dcb_last_error(void) { return g_err; }
+
+int dcb_device_count(int *count) {
+    REQUIRE(count != nullptr, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(DCB_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return DCB_OK;
+}
+
+int dcb_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(DCB_ERR_NO_DEVICE, "no CUDA device available (%s)", cudaGetErrorString(e));
+    REQUIRE(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(0));
+    int major = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10)
+        return fail(DCB_ERR_UNSUPPORTED,
+                    "libdiscorpy_b200 holds sm_100a code only; device %d is sm_%d*", device, major);
+    tma_encoder();
+    return DCB_OK;
+}
+
+int dcb_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem,
+                    size_t *free_mem, char *name, int name_len) {
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (total_mem || free_mem) {
+        int cur = 0;
+        CUDA_TRY(cudaGetDevice(&cur));
+        CUDA_TRY(cudaSetDevice(device));
+        size_t f = 0, t = 0;
+        CUDA_TRY(cudaMemGetInfo(&f, &t));
+        CUDA_TRY(cudaSetDevice(cur));
+        if (total_mem) *total_mem = t;
+        if (free_mem) *free_mem = f;
+    }
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return DCB_OK;
+}
+
+// ---- memory / streams / events ---------------------------------------------
+int dcb_malloc(void **dptr, size_t nbytes) {
+    REQUIRE(dptr != nullptr, "dptr is NULL");
+    CUDA_TRY(cudaMalloc(dptr, nbytes ? nbytes : 1));
+    return DCB_OK;
+}
+int dcb_free(void *dptr) {
+    CUDA_TRY(cudaFree(dptr));
+    return DCB_OK;
+}
+int dcb_memset(void *dptr, int value, size_t nbytes, void *stream) {
+    CUDA_TRY(cudaMemsetAsync(dptr, value, nbytes, (cudaStream_t)stream));
+    return DCB_OK;
+}
+int dcb_host_alloc(void **hptr, size_t nbytes) {
+    REQUIRE(hptr != nullptr, "hptr is NULL");
+    CUDA_TRY(cudaHostAlloc(hptr, nbytes ? nbytes : 1, cudaHostAllocPortable));
+    return DCB_OK;
+}
+int dcb_host_free(void *hptr) {
+    CUDA_TRY(cudaFreeHost(hptr));
+    return DCB_OK;
+}
+int dcb_host_register(void *hptr, size_t nbytes) {
+    CUDA_TRY(cudaHostRegister(hptr, nbytes, cudaHostRegisterPortable));
+    return DCB_OK;
+}
+int dcb_host_unregister(void *hptr) {
+    CUDA_TRY(cudaHostUnregister(hptr));
+    return DCB_OK;
+}
+int dcb_is_pinned(const void *hptr, int *pinned) {
+    REQUIRE(pinned != nullptr, "pinned is NULL");
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, hptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *pinned = 0;
+        return DCB_OK;
+    }
+    *pinned = (attr.type == cudaMemoryTypeHost) ? 1 : 0;
+    return DCB_OK;
+}
+int dcb_h2d(void *dst, const void *src, size_t n, void *stream) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return DCB_OK;
+}
+int dcb_d2h(void *dst, const void *src, size_t n, void *stream) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return DCB_OK;
+}
+int dcb_d2d(void *dst, const void *src, size_t n, void *stream) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return DCB_OK;
+}
+int dcb_h2d_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t wbytes, size_t rows,
+               void *stream) {
+    CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, wbytes, rows, cudaMemcpyHostToDevice,
+                               (cudaStream_t)stream));
+    return DCB_OK;
+}
+int dcb_d2h_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t wbytes, size_t rows,
+               void *stream) {
+    CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, wbytes, rows, cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream));
+    return DCB_OK;
+}
+int dcb_stream_create(void **stream) {
+    REQUIRE(stream != nullptr, "stream is NULL");
+    cudaStream_t s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void *)s;
+    return DCB_OK;
+}
+int dcb_stream_destroy(void *stream) {
+    CUDA_TRY(cudaStreamDestroy((cudaStream_t)stream));
+    return DCB_OK;
+}
+int dcb_stream_sync(void *stream) {
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return DCB_OK;
+}
+int dcb_device_sync(void) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    return DCB_OK;
+}
+int dcb_event_create(void **event) {
+    REQUIRE(event != nullptr, "event is NULL");
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    *event = (void *)e;
+    return DCB_OK;
+}
+int dcb_event_destroy(void *event) {
+    CUDA_TRY(cudaEventDestroy((cudaEvent_t)event));
+    return DCB_OK;
+}
+int dcb_event_record(void *event, void *stream) {
+    CUDA_TRY(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    return DCB_OK;
+}
+int dcb_event_sync(void *event) {
+    CUDA_TRY(cudaEventSynchronize((cudaEvent_t)event));
+    return DCB_OK;
+}
+int dcb_event_elapsed_ms(void *start, void *stop, float *ms) {
+    REQUIRE(ms != nullptr, "ms is NULL");
+    CUDA_TRY(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return DCB_OK;
+}
+
+// ---- hot path -----------------------------------------------------------------
+static int radial_to_dev(const dcb_radial *m, RadialDev *out) {
+    REQUIRE(m != nullptr, "radial model is NULL");
+    REQUIRE(m->n >= 1 && m->n <= DCB_MAX_TERMS, "number of polynomial terms %d not in 1..%d", m->n,
+            DCB_MAX_TERMS);
+    memset(out, 0, sizeof(*out));
+    out->xc = m->xc;
+    out->yc = m->yc;
+    out->n = m->n;
+    for (int i = 0; i < m->n; ++i) out->a[i] = m->a[i];
+    return DCB_OK;
+}
+
+int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, int W, int src_row0,
+                                  int src_rows, size_t src_pitch, size_t src_slice_stride,
+                                  size_t dst_pitch, size_t dst_slice_stride, int row0, int nrows,
+                                  int coord_round, const dcb_radial *model,
+                                  const dcb_options *opt, void *stream) {
+    dcb_options o;
+    int rc = check_options(opt, &o);
+    if (rc) return rc;
+    rc = check_image_args(src, dst, H, W, src_pitch, dst_pitch);
+    if (rc) return rc;
+    REQUIRE(D >= 1, "depth must be >= 1");
+    REQUIRE(row0 >= 0 && nrows >= 1 && row0 + nrows <= H, "rows %d..%d outside 0..%d", row0,
+            row0 + nrows - 1, H - 1);
+    REQUIRE(src_row0 >= 0 && src_rows >= 1 && src_row0 + src_rows <= H,
+            "source window rows %d..%d outside 0..%d", src_row0, src_row0 + src_rows - 1, H - 1);
+    REQUIRE(D == 1 || (src_slice_stride >= src_pitch * (size_t)src_rows && src_slice_stride % 4 == 0),
+            "bad source slice stride %zu", src_slice_stride);
+    REQUIRE(D == 1 || (dst_slice_stride >= dst_pitch * (size_t)nrows && dst_slice_stride % 4 == 0),
+            "bad destination slice stride %zu", dst_slice_stride);
+    REQUIRE(coord_round == 0 || coord_round == 1, "coord_round must be 0 or 1");
+    if (!coord_round) {
+        REQUIRE(o.order == 1, "float64-coordinate (slice) sampling is order 1 only");
+        if (o.blend == DCB_BLEND_LERP32) o.blend = DCB_BLEND_LERP64;
+    }
+    RemapParams p;
+    memset(&p, 0, sizeof(p));
+    rc = radial_to_dev(model, &p.rad);
+    if (rc) return rc;
+    p.src = src;
+    p.dst = dst;
+    p.src_pitch = (long long)(src_pitch / 4);
+    p.src_slice = (long long)(src_slice_stride / 4);
+    p.dst_pitch = (long long)(dst_pitch / 4);
+    p.dst_slice = (long long)(dst_slice_stride / 4);
+    p.H = H;
+    p.W = W;
+    p.D = D;
+    p.row0 = row0;
+    p.nrows = nrows;
+    p.yorg = src_row0;
+    p.ylast = src_row0 + src_rows - 1;
+    double gm, gc;
+    radial_slopes(*model, W, row0, nrows, &gm, &gc);
+    if (coord_round) {
+        const int rpt = 4;
+        return plan_and_launch(pick_kernel<MAP_RADIAL, true, 4>(o.order, o.blend), rpt, p, gm, gc,
+                               o.path, src_pitch, src_slice_stride, (cudaStream_t)stream);
+    }
+    return plan_and_launch(pick_kernel<MAP_RADIAL, false, 1>(1, o.blend), 1, p, gm, gc, o.path,
+                           src_pitch, src_slice_stride, (cudaStream_t)stream);
+}
+
+int dcb_unwarp_image_backward_f32(const float *src, float *dst, int H, int W, size_t src_pitch,
+                                  size_t dst_pitch, const dcb_radial *model,
+                                  const dcb_options *opt, void *stream) {
+    return dcb_unwarp_stack_backward_f32(src, dst, 1, H, W, 0, H, src_pitch, src_pitch * (size_t)H,
+                                         dst_pitch, dst_pitch * (size_t)H, 0, H, 1, model, opt,
+                                         stream);
+}
+
+int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W, size_t src_pitch,
+                                      size_t dst_pitch, const dcb_persp *model,
+                                      const dcb_options *opt, void *stream) {
+    dcb_options o;
+    int rc = check_options(opt, &o);
+    if (rc) return rc;
+    rc = check_image_args(src, dst, H, W, src_pitch, dst_pitch);
+    if (rc) return rc;
+    REQUIRE(model != nullptr, "perspective model is NULL");
+    RemapParams p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < 8; ++i) p.per.c[i] = model->c[i];
+    p.src = src;
+    p.dst = dst;
+    p.src_pitch = (long long)(src_pitch / 4);
+    p.src_slice = p.src_pitch * H;
+    p.dst_pitch = (long long)(dst_pitch / 4);
+    p.dst_slice = p.dst_pitch * H;
+    p.H = H;
+    p.W = W;
+    p.D = 1;
+    p.row0 = 0;
+    p.nrows = H;
+    p.yorg = 0;
+    p.ylast = H - 1;
+    double gm, gc;
+    persp_slopes(*model, H, W, &gm, &gc);
+    return plan_and_launch(pick_kernel<MAP_PERSP, true, 4>(o.order, o.blend), 4, p, gm, gc, o.path,
+                           src_pitch, src_pitch * (size_t)H, (cudaStream_t)stream);
+}
+
+int dcb_unwarp_image_backward_perspective_f32(const float *src, float *dst, float *scratch, int H,
+                                              int W, size_t src_pitch, size_t dst_pitch,
+                                              size_t scratch_pitch, const dcb_radial *radial,
+                                              const dcb_persp *persp, const dcb_options *opt,
+                                              void *stream) {
+    REQUIRE(scratch != nullptr && scratch != src && scratch != dst,
+            "scratch must be a third, distinct buffer");
+    int rc = dcb_unwarp_image_backward_f32(src, scratch, H, W, src_pitch, scratch_pitch, radial, opt,
+                                           stream);
+    if (rc) return rc;
+    return dcb_correct_perspective_image_f32(scratch, dst, H, W, scratch_pitch, dst_pitch, persp,
+                                             opt, stream);
+}
+
+}  // extern "C"
+
+template <class CT>
+static int launch_map_coords(const float *src, float *dst, int H, int W, long long pitch,
+                             const void *yd, const void *xd, size_t n, unsigned *oob,
+                             const dcb_options &o, cudaStream_t stream) {
+    DevProps props;
+    int rc = device_props(&props);
+    if (rc != DCB_OK) return rc;
+    const size_t want = (n + 255) / 256;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)props.sm_count * 16));
+    const CT *y = (const CT *)yd, *x = (const CT *)xd;
+    if (o.order == 0)
+        map_coords_kernel<0, DCB_BLEND_EXACT, CT><<<grid, 256, 0, stream>>>(src, dst, H, W, pitch, y,
+                                                                           x, n, oob);
+    else if (o.blend == DCB_BLEND_LERP64)
+        map_coords_kernel<1, DCB_BLEND_LERP64, CT><<<grid, 256, 0, stream>>>(src, dst, H, W, pitch,
+                                                                            y, x, n, oob);
+    else if (o.blend == DCB_BLEND_LERP32 && sizeof(CT) == 4)
+        map_coords_kernel<1, DCB_BLEND_LERP32, CT><<<grid, 256, 0, stream>>>(src, dst, H, W, pitch,
+                                                                            y, x, n, oob);
+    else
+        map_coords_kernel<1, DCB_BLEND_EXACT, CT><<<grid, 256, 0, stream>>>(src, dst, H, W, pitch, y,
+                                                                           x, n, oob);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_last_plan = {DCB_PATH_DIRECT, 0, 0, grid, 0};
+    return DCB_OK;
+}
+
+extern "C" {
+
+int dcb_map_coordinates_f32(const float *src, float *dst, int H, int W, size_t src_pitch,
+                            const void *yd, const void *xd, int coord_is_f64, size_t n_out,
+                            uint32_t *oob_count, const dcb_options *opt, void *stream) {
+    dcb_options o;
+    int rc = check_options(opt, &o);
+    if (rc) return rc;
+    REQUIRE(src != nullptr && dst != nullptr && yd != nullptr && xd != nullptr, "null pointer");
+    REQUIRE(H >= 1 && W >= 1 && H < (1 << 24) && W < (1 << 24), "bad image size %dx%d", H, W);
+    REQUIRE(src_pitch >= (size_t)W * 4 && src_pitch % 4 == 0, "bad source pitch %zu", src_pitch);
+    if (n_out == 0) return DCB_OK;
+    if (coord_is_f64)
+        return launch_map_coords<double>(src, dst, H, W, (long long)(src_pitch / 4), yd, xd, n_out,
+                                         oob_count, o, (cudaStream_t)stream);
+    return launch_map_coords<float>(src, dst, H, W, (long long)(src_pitch / 4), yd, xd, n_out,
+                                    oob_count, o, (cudaStream_t)stream);
+}
+
+int dcb_fill_synthetic_f32(float *dst, size_t n, uint64_t seed, uint64_t offset, void *stream) {
+    REQUIRE(dst != nullptr, "dst is NULL");
+    if (n == 0) return DCB_OK;
+    DevProps props;
+    int rc = device_props(&props);
+    if (rc != DCB_OK) return rc;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)props.sm_count * 32);
+    fill_synthetic_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dst, n, seed, offset);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return DCB_OK;
+}
+
+// ---- diagnostics ---------------------------------------------------------------
+int dcb_launch_count(uint64_t *count) {
+    REQUIRE(count != nullptr, "count is NULL");
+    *count = g_launches.load(std::memory_order_relaxed);
+    return DCB_OK;
+}
+int dcb_launch_count_reset(void) {
+    g_launches.store(0, std::memory_order_relaxed);
+    return DCB_OK;
+}
+int dcb_last_plan(int *path, int *box_w, int *box_h, int *grid, int *smem_bytes) {
+    if (path) *path = g_last_plan.path;
+    if (box_w) *box_w = g_last_plan.bw;
+    if (box_h) *box_h = g_last_plan.bh;
+    if (grid) *grid = g_last_plan.grid;
+    if (smem_bytes) *smem_bytes = g_last_plan.smem;
+    return DCB_OK;
+}
+
+int dcb_selftest_sqrt(size_t n, uint64_t seed, uint64_t *mismatch) {
+    REQUIRE(mismatch != nullptr, "mismatch is NULL");
+    unsigned long long *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(*d)));
+    CUDA_TRY(cudaMemset(d, 0, sizeof(*d)));
+    selftest_sqrt_kernel<<<148 * 8, 256>>>(n, seed, d);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
+    *mismatch = h;
+    return DCB_OK;
+}
+
+int dcb_microbench(int which, double *gops) {
+    REQUIRE(gops != nullptr, "gops is NULL");
+    REQUIRE(which >= 0 && which <= 5, "which must be 0..5");
+    double *sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int grid = 148 * 8, block = 256;
+    double ops_per_thread = (double)kMbIters * kMbChains;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        switch (which) {
+            case 0: microbench_kernel<0><<<grid, block>>>(sink, 1.0); break;
+            case 1: microbench_kernel<1><<<grid, block>>>(sink, 1.0); break;
+            case 2: microbench_kernel<2><<<grid, block>>>(sink, 1.0); break;
+            case 3: microbench_coords_kernel<<<grid, block>>>(sink, 2050.37, 2040.81); break;
+            case 4: microbench_kernel<4><<<grid, block>>>(sink, 1.0); break;
+            case 5: microbench_kernel<5><<<grid, block>>>(sink, 1.0); break;
+        }
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (which == 1) ops_per_thread *= 2;       // two conversions per step
+    if (which == 3) ops_per_thread = (double)kMbIters * 4;  // pixels
+    if (which == 5) ops_per_thread *= 3;       // DFMA + two conversions
+    *gops = ops_per_thread * grid * block / (best * 1e-3) / 1e9;
+    return DCB_OK;
+}
+
+}  // extern "C"

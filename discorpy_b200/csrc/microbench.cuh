@@ -1,0 +1,97 @@
+// microbench.cuh -- pipe-rate probes and the sqrt self-test (diagnostics only).
+// They size the fp64 budget of the radial kernel (DESIGN.md "fp64 budget").
+#pragma once
+#include "common.cuh"
+
+namespace dcb {
+
+constexpr int kMbIters = 2048;
+constexpr int kMbChains = 8;
+
+// which: 0 DFMA, 1 F2F f32<->f64 pair, 2 MUFU.RSQ64H, 4 FFMA, 5 DFMA + F2F mixed
+template <int WHICH>
+__global__ void __launch_bounds__(256) microbench_kernel(double *sink, double seed) {
+    double d[kMbChains];
+    float f[kMbChains];
+#pragma unroll
+    for (int c = 0; c < kMbChains; ++c) {
+        d[c] = seed + c + threadIdx.x * 1e-3;
+        f[c] = (float)d[c];
+    }
+    for (int it = 0; it < kMbIters; ++it) {
+#pragma unroll
+        for (int c = 0; c < kMbChains; ++c) {
+            if (WHICH == 0) {
+                d[c] = fma(d[c], 0.999999, 1e-7);
+            } else if (WHICH == 1) {
+                double w;
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(w) : "f"(f[c]));
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f[c]) : "d"(w));
+            } else if (WHICH == 2) {
+                asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(d[c]) : "d"(d[c]));
+            } else if (WHICH == 4) {
+                f[c] = fmaf(f[c], 0.999999f, 1e-7f);
+            } else if (WHICH == 5) {
+                d[c] = fma(d[c], 0.999999, 1e-7);
+                double w;
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(w) : "f"(f[c]));
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f[c]) : "d"(w));
+            }
+        }
+    }
+    double acc = 0;
+#pragma unroll
+    for (int c = 0; c < kMbChains; ++c) acc += d[c] + f[c];
+    if (acc == 123.456) sink[0] = acc;
+}
+
+// which == 3: the radial coordinate evaluation alone, 5 terms, 4 px per step
+__global__ void __launch_bounds__(256) microbench_coords_kernel(double *sink, double xc, double yc) {
+    const double a[5] = {1.0, -2e-5, 6e-8, -1e-10, 5e-14};
+    double xu[4], xu2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        xu[k] = (double)(threadIdx.x + 32 * k + blockIdx.x) - xc;
+        xu2[k] = xu[k] * xu[k];
+    }
+    float acc = 0.f;
+    for (int it = 0; it < kMbIters; ++it) {
+        const double yu = (double)it - yc;
+        const double yu2 = yu * yu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double r = dsqrt_pos(xu2[k] + yu2);
+            double f = a[4];
+            f = fma(f, r, a[3]);
+            f = fma(f, r, a[2]);
+            f = fma(f, r, a[1]);
+            f = fma(f, r, a[0]);
+            acc += __double2float_rn(fma(f, xu[k], xc)) + __double2float_rn(fma(f, yu, yc));
+        }
+    }
+    if (acc == 123.456f) sink[0] = acc;
+}
+
+// custom sqrt vs IEEE sqrt on pseudo-random positive inputs spanning the
+// magnitudes r^2 takes on images up to 65536^2 (and a few exact squares)
+__global__ void __launch_bounds__(256)
+    selftest_sqrt_kernel(size_t n, uint64_t seed, unsigned long long *mismatch) {
+    unsigned long long bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t h = splitmix64(seed ^ i);
+        double s;
+        if ((i & 7) == 0) {
+            const double q = (double)(h >> 44);  // exact squares
+            s = q * q;
+        } else {
+            const double m = (double)(h >> 11) * (1.0 / 9007199254740992.0);  // [0,1)
+            const int e = (int)((h & 0x3f)) - 20;                             // 2^-20 .. 2^43
+            s = ldexp(1.0 + m, e);
+        }
+        if (dsqrt_pos(s) != sqrt(s)) ++bad;
+    }
+    if (bad) atomicAdd(mismatch, bad);
+}
+
+}  // namespace dcb

@@ -1,0 +1,390 @@
+"""
+Device-side plumbing for the Python host: device selection, a small pool of
+device buffers, pinned NumPy arrays, streams and events -- all through the C
+ABI (no torch, no cuda-python).
+"""
+import ctypes
+import os
+import threading
+import weakref
+
+import numpy as np
+
+from . import _cabi
+
+_state = threading.local()
+_init_lock = threading.Lock()
+_initialised = set()
+
+
+def _default_device():
+    for key in ("DCB_DEVICE", "LOCAL_RANK"):
+        val = os.environ.get(key)
+        if val not in (None, ""):
+            try:
+                return int(val)
+            except ValueError:
+                pass
+    return 0
+
+
+def set_device(index):
+    """Bind the calling thread (and by default later threads) to a GPU."""
+    _cabi.call("dcb_init", int(index))
+    _state.device = int(index)
+    with _init_lock:
+        _initialised.add(int(index))
+    os.environ["DCB_DEVICE"] = str(int(index))
+
+
+def ensure_init():
+    """Initialise the library on first use; raise if there is no usable GPU."""
+    dev = getattr(_state, "device", None)
+    if dev is None:
+        set_device(_default_device())
+        dev = _state.device
+    return dev
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    try:
+        _cabi.call("dcb_device_count", ctypes.byref(n))
+    except _cabi.DcbError:
+        return 0
+    return n.value
+
+
+def device_info(index=None):
+    index = ensure_init() if index is None else index
+    sm, maj, mnr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    tot, free = ctypes.c_size_t(), ctypes.c_size_t()
+    name = ctypes.create_string_buffer(128)
+    _cabi.call("dcb_device_info", index, ctypes.byref(sm), ctypes.byref(maj),
+               ctypes.byref(mnr), ctypes.byref(tot), ctypes.byref(free), name,
+               128)
+    return dict(index=index, name=name.value.decode(), sm_count=sm.value,
+                cc=(maj.value, mnr.value), total_mem=tot.value,
+                free_mem=free.value)
+
+
+# --------------------------------------------------------------------------
+# device buffers
+# --------------------------------------------------------------------------
+class DeviceBuffer:
+    """Owning handle of ``nbytes`` of device memory."""
+
+    def __init__(self, nbytes):
+        ensure_init()
+        ptr = ctypes.c_void_p()
+        _cabi.call("dcb_malloc", ctypes.byref(ptr), int(nbytes))
+        self.ptr = ptr.value
+        self.nbytes = int(nbytes)
+
+    def free(self):
+        if self.ptr:
+            _cabi.load().dcb_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class _Pool:
+    """Size-bucketed free list; avoids a cudaMalloc/cudaFree per call."""
+
+    def __init__(self, factory, max_bytes):
+        self._factory = factory
+        self._free = {}
+        self._held = 0
+        self._max = max_bytes
+        self._lock = threading.Lock()
+
+    @staticmethod
+    def _bucket(nbytes):
+        nbytes = max(int(nbytes), 256)
+        if nbytes <= (1 << 20):
+            return 1 << (nbytes - 1).bit_length()
+        step = 1 << 20
+        return (nbytes + step - 1) // step * step
+
+    def take(self, nbytes):
+        b = self._bucket(nbytes)
+        with self._lock:
+            lst = self._free.get(b)
+            if lst:
+                self._held -= b
+                return lst.pop()
+        return self._factory(b)
+
+    def give(self, buf):
+        b = buf.nbytes
+        with self._lock:
+            if self._held + b <= self._max:
+                self._free.setdefault(b, []).append(buf)
+                self._held += b
+                return
+        buf.free()
+
+    def clear(self):
+        with self._lock:
+            bufs = [b for lst in self._free.values() for b in lst]
+            self._free.clear()
+            self._held = 0
+        for b in bufs:
+            b.free()
+
+
+_pool_bytes = int(os.environ.get("DCB_POOL_BYTES", str(8 << 30)))
+device_pool = _Pool(DeviceBuffer, _pool_bytes)
+
+
+class borrowed:
+    """``with borrowed(nbytes) as buf:`` -- a pooled device buffer."""
+
+    def __init__(self, nbytes):
+        self.nbytes = nbytes
+
+    def __enter__(self):
+        self.buf = device_pool.take(self.nbytes)
+        return self.buf
+
+    def __exit__(self, *exc):
+        device_pool.give(self.buf)
+        return False
+
+
+# --------------------------------------------------------------------------
+# pinned host arrays
+# --------------------------------------------------------------------------
+class _PinnedBlock:
+    def __init__(self, nbytes):
+        ensure_init()
+        ptr = ctypes.c_void_p()
+        _cabi.call("dcb_host_alloc", ctypes.byref(ptr), int(nbytes))
+        self.ptr = ptr.value
+        self.nbytes = int(nbytes)
+
+    def free(self):
+        if self.ptr:
+            _cabi.load().dcb_host_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+pinned_pool = _Pool(_PinnedBlock, int(os.environ.get("DCB_PINNED_POOL_BYTES",
+                                                     str(4 << 30))))
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """A NumPy array in page-locked host memory (full-rate async DMA).  The
+    memory goes back to a pool when the array and all its views are collected."""
+    dtype = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(int(s) for s in shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    block = pinned_pool.take(max(nbytes, 1))
+    raw = (ctypes.c_char * max(nbytes, 1)).from_address(block.ptr)
+    arr = np.frombuffer(raw, dtype=dtype, count=nbytes // dtype.itemsize)
+    arr = arr.reshape(shape)
+    weakref.finalize(raw, pinned_pool.give, block)
+    return arr
+
+
+def pinned_copy(array):
+    out = pinned_empty(np.shape(array), np.asarray(array).dtype)
+    out[...] = array
+    return out
+
+
+def is_pinned(array):
+    flag = ctypes.c_int(0)
+    _cabi.call("dcb_is_pinned", ctypes.c_void_p(array.ctypes.data),
+               ctypes.byref(flag))
+    return bool(flag.value)
+
+
+# --------------------------------------------------------------------------
+# streams / events
+# --------------------------------------------------------------------------
+class Stream:
+    def __init__(self):
+        ensure_init()
+        h = ctypes.c_void_p()
+        _cabi.call("dcb_stream_create", ctypes.byref(h))
+        self.handle = h.value
+
+    def sync(self):
+        _cabi.call("dcb_stream_sync", ctypes.c_void_p(self.handle))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _cabi.load().dcb_stream_destroy(ctypes.c_void_p(self.handle))
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Event:
+    def __init__(self):
+        ensure_init()
+        h = ctypes.c_void_p()
+        _cabi.call("dcb_event_create", ctypes.byref(h))
+        self.handle = h.value
+
+    def record(self, stream=None):
+        _cabi.call("dcb_event_record", ctypes.c_void_p(self.handle),
+                   ctypes.c_void_p(stream.handle if stream else None))
+
+    def sync(self):
+        _cabi.call("dcb_event_sync", ctypes.c_void_p(self.handle))
+
+    def elapsed_ms(self, later):
+        ms = ctypes.c_float()
+        _cabi.call("dcb_event_elapsed_ms", ctypes.c_void_p(self.handle),
+                   ctypes.c_void_p(later.handle), ctypes.byref(ms))
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _cabi.load().dcb_event_destroy(ctypes.c_void_p(self.handle))
+                self.handle = None
+        except Exception:
+            pass
+
+
+def current_stream():
+    """One non-blocking stream per host thread."""
+    s = getattr(_state, "stream", None)
+    if s is None:
+        s = _state.stream = Stream()
+    return s
+
+
+def synchronize():
+    _cabi.call("dcb_device_sync")
+
+
+def launch_count():
+    n = ctypes.c_uint64()
+    _cabi.call("dcb_launch_count", ctypes.byref(n))
+    return n.value
+
+
+def last_plan():
+    vals = [ctypes.c_int() for _ in range(5)]
+    _cabi.call("dcb_last_plan", *[ctypes.byref(v) for v in vals])
+    return dict(zip(("path", "box_w", "box_h", "grid", "smem_bytes"),
+                    [v.value for v in vals]))
+
+
+# --------------------------------------------------------------------------
+# device-resident float32 arrays
+# --------------------------------------------------------------------------
+def _pitch_for(width):
+    """Row pitch in bytes: dense when that is already a multiple of 16 (the
+    TMA requirement), otherwise padded up to one."""
+    return (int(width) * 4 + 15) // 16 * 16
+
+
+class DeviceArray:
+    """A float32 image (H, W) or stack (D, H, W) resident in HBM.
+
+    Rows are ``pitch`` bytes apart (multiple of 16), slices ``slice_stride``
+    bytes apart.  The memory comes from the buffer pool and returns to it when
+    the object is collected.
+    """
+
+    def __init__(self, shape, pitch=None):
+        shape = tuple(int(s) for s in shape)
+        if len(shape) not in (2, 3):
+            raise ValueError("DeviceArray is 2-D or 3-D")
+        self.shape = shape
+        self.dtype = np.dtype(np.float32)
+        h, w = shape[-2], shape[-1]
+        self.pitch = _pitch_for(w) if pitch is None else int(pitch)
+        self.slice_stride = self.pitch * h
+        depth = shape[0] if len(shape) == 3 else 1
+        self.nbytes = self.slice_stride * depth
+        self._buf = device_pool.take(max(self.nbytes, 16))
+        self.ptr = self._buf.ptr
+        self._fin = weakref.finalize(self, device_pool.give, self._buf)
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @classmethod
+    def from_host(cls, array, stream=None):
+        array = np.ascontiguousarray(array, dtype=np.float32)
+        out = cls(array.shape)
+        out.copy_from_host(array, stream)
+        return out
+
+    def copy_from_host(self, array, stream=None):
+        array = np.ascontiguousarray(array, dtype=np.float32)
+        if tuple(array.shape) != self.shape:
+            raise ValueError("shape mismatch %s vs %s" % (array.shape,
+                                                          self.shape))
+        stream = stream or current_stream()
+        w = self.shape[-1]
+        rows = int(np.prod(self.shape[:-1], dtype=np.int64))
+        if self.pitch == w * 4:
+            _cabi.call("dcb_h2d", ctypes.c_void_p(self.ptr),
+                       ctypes.c_void_p(array.ctypes.data), array.nbytes,
+                       ctypes.c_void_p(stream.handle))
+        else:
+            _cabi.call("dcb_h2d_2d", ctypes.c_void_p(self.ptr), self.pitch,
+                       ctypes.c_void_p(array.ctypes.data), w * 4, w * 4, rows,
+                       ctypes.c_void_p(stream.handle))
+        if not is_pinned(array):
+            stream.sync()       # pageable source: do not outlive the caller's array
+        return self
+
+    def to_host(self, out=None, stream=None):
+        stream = stream or current_stream()
+        if out is None:
+            out = pinned_empty(self.shape, np.float32)
+        w = self.shape[-1]
+        rows = int(np.prod(self.shape[:-1], dtype=np.int64))
+        if self.pitch == w * 4:
+            _cabi.call("dcb_d2h", ctypes.c_void_p(out.ctypes.data),
+                       ctypes.c_void_p(self.ptr), out.nbytes,
+                       ctypes.c_void_p(stream.handle))
+        else:
+            _cabi.call("dcb_d2h_2d", ctypes.c_void_p(out.ctypes.data), w * 4,
+                       ctypes.c_void_p(self.ptr), self.pitch, w * 4, rows,
+                       ctypes.c_void_p(stream.handle))
+        stream.sync()
+        return out
+
+    def fill_synthetic(self, seed, offset=0, stream=None):
+        """Fill with the stateless splitmix64 stream (bench inputs)."""
+        if self.pitch != self.shape[-1] * 4:
+            raise ValueError("fill_synthetic needs a dense array (W % 4 == 0)")
+        stream = stream or current_stream()
+        _cabi.call("dcb_fill_synthetic_f32", ctypes.c_void_p(self.ptr),
+                   self.nbytes // 4, int(seed), int(offset),
+                   ctypes.c_void_p(stream.handle))
+        return self
+
+
+def synthetic_host(n, seed, offset=0):
+    """NumPy restatement of dcb_fill_synthetic_f32 (spot checks in tests)."""
+    idx = (np.arange(n, dtype=np.uint64) + np.uint64(offset)) ^ np.uint64(seed)
+    with np.errstate(over="ignore"):
+        x = idx + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return ((x >> np.uint64(40)).astype(np.float32)
+            * np.float32(1.0 / 16777216.0))

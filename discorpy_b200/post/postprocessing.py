@@ -1,0 +1,554 @@
+"""
+Drop-in replacement of ``discorpy.post.postprocessing`` whose image / stack
+functions run on an NVIDIA B200 through ``libdiscorpy_b200.so``.
+
+Same public names, argument meaning and error behaviour as the reference
+module (``/root/reference/discorpy/post/postprocessing.py``, cited per
+function).  The four hot functions --
+
+- :func:`unwarp_image_backward`            (reference ``:111-148``)
+- :func:`unwarp_slice_backward`            (``:188-229``)
+- :func:`unwarp_chunk_slices_backward`     (``:255-313``)
+- :func:`correct_perspective_image`        (``:462-492``)
+
+plus ``_mapping`` (``:232-252``) and the additive
+:func:`unwarp_image_backward_perspective` -- call hand-written sm_100a kernels;
+there is NO CPU fallback for them (a missing library or GPU raises).  The
+point-list helpers (``unwarp_line_*``, residuals, ``correct_perspective_line``)
+work on a few hundred dots and stay host-side NumPy, re-implemented here so
+that ``discorpy.proc`` keeps working when this module is installed in its
+place.
+
+Every hot function also accepts a :class:`discorpy_b200.DeviceArray` instead of
+a NumPy array; it then returns a ``DeviceArray`` without synchronising, which
+is how pipelines keep data resident in HBM.
+"""
+import ctypes
+
+import numpy as np
+from scipy import optimize
+
+from .. import _cabi
+from .. import device as _dev
+from ..device import DeviceArray
+
+_MODES = ("reflect", "grid-mirror", "constant", "grid-constant", "nearest",
+          "mirror", "grid-wrap", "wrap")
+
+#: blend / path used by the hot functions; see include/discorpy_b200.h
+config = {"blend": _cabi.BLEND_EXACT, "path": _cabi.PATH_AUTO}
+
+
+# ---------------------------------------------------------------------------
+# argument policy shared by the hot functions
+# ---------------------------------------------------------------------------
+def _check_order_mode(order, mode):
+    """Mirror what ``scipy.ndimage.map_coordinates`` raises for bad arguments
+    (``scipy/ndimage/_interpolation.py:446-447``, ``_ni_support.py:59``)."""
+    if mode not in _MODES:
+        raise RuntimeError("boundary mode not supported")
+    if order is None or order < 0 or order > 5:
+        raise RuntimeError("spline order not supported")
+    if order > 1:
+        raise NotImplementedError(
+            "spline order %d is not implemented on the CUDA path yet (orders "
+            "0 and 1 are); there is no CPU fallback" % order)
+    return int(order)
+
+
+def _as_f32_image(mat):
+    """float32 images go to the GPU as they are.  Other dtypes would need the
+    reference's 'same dtype out' rule (round-half-away for integers) inside
+    the kernel and are refused loudly instead of silently going to the CPU."""
+    if mat.dtype != np.float32:
+        raise NotImplementedError(
+            "dtype %s is not implemented on the CUDA path yet (float32 is); "
+            "there is no CPU fallback" % mat.dtype)
+    return np.ascontiguousarray(mat)
+
+
+_EXACT_IN_F32 = (np.dtype(np.float32), np.dtype(np.float16), np.dtype(np.uint8),
+                 np.dtype(np.int8), np.dtype(np.uint16), np.dtype(np.int16),
+                 np.dtype(np.bool_))
+
+
+def _to_f32_exact(arr):
+    """For the functions whose output is float32 whatever the input
+    (``unwarp_slice_backward``): dtypes that embed exactly in float32 are
+    widened on the host; the result is then what the reference computes."""
+    if arr.dtype not in _EXACT_IN_F32:
+        raise NotImplementedError(
+            "dtype %s does not embed exactly in float32; not implemented on "
+            "the CUDA path (no CPU fallback)" % arr.dtype)
+    return np.ascontiguousarray(arr, dtype=np.float32)
+
+
+def _opts(order=1):
+    return _cabi.make_options(order, config["blend"], config["path"])
+
+
+def _vp(ptr):
+    return ctypes.c_void_p(ptr)
+
+
+def _radial_factor_1d(ru, list_fact):
+    """Sum_i a_i ru**i in the reference's operation order (host side, 1-D)."""
+    acc = None
+    for i, a in enumerate(list_fact):
+        term = a * ru ** i
+        acc = term if acc is None else acc + term
+    return np.zeros_like(ru) if acc is None else acc
+
+
+def _row_yd(height, width, xcenter, ycenter, list_fact, index):
+    """Clipped float64 source row coordinate of output row ``index``
+    (reference ``:214-220`` / ``:289-299``); 1-D, W values, host side."""
+    xu = np.arange(0, width) - xcenter
+    yu = index - ycenter
+    ru = np.sqrt(xu ** 2 + yu ** 2)
+    flist = _radial_factor_1d(ru, list_fact)
+    return np.clip(ycenter + flist * yu, 0, height - 1)
+
+
+# ---------------------------------------------------------------------------
+# hot functions
+# ---------------------------------------------------------------------------
+def unwarp_image_backward(mat, xcenter, ycenter, list_fact, order=1,
+                          mode="reflect"):
+    """
+    Unwarp an image using a backward model (reference ``:111-148``).
+
+    Parameters
+    ----------
+    mat : array_like or DeviceArray
+        2D float32 array.
+    xcenter, ycenter : float
+        Center of distortion.
+    list_fact : list of float
+        Polynomial coefficients of the backward model.
+    order : int, optional
+        0 (nearest) or 1 (bilinear) run on the GPU; 2..5 raise
+        ``NotImplementedError``.
+    mode : str, optional
+        Accepted for signature parity.  The coordinates are clipped to the
+        image before sampling, so for order 0/1 all eight SciPy modes give the
+        same result.
+
+    Returns
+    -------
+    array_like
+        2D array, same shape and dtype; distortion-corrected image.
+    """
+    on_device = isinstance(mat, DeviceArray)
+    if not on_device:
+        mat = np.asarray(mat)
+    (height, width) = mat.shape          # ValueError for non-2D, like :137
+    order = _check_order_mode(order, mode)
+    model = _cabi.make_radial(xcenter, ycenter, list_fact)
+    stream = _dev.current_stream()
+    src = mat if on_device else DeviceArray.from_host(_as_f32_image(mat),
+                                                      stream)
+    dst = DeviceArray((height, width))
+    opt = _opts(order)
+    _cabi.call("dcb_unwarp_image_backward_f32", _vp(src.ptr), _vp(dst.ptr),
+               height, width, src.pitch, dst.pitch, ctypes.byref(model),
+               ctypes.byref(opt), _vp(stream.handle))
+    return dst if on_device else dst.to_host(stream=stream)
+
+
+def unwarp_image_forward(mat, xcenter, ycenter, list_fact):
+    """
+    Unwarp an image using a forward model (reference ``:151-185``).  Scatter
+    with vacant pixels, "only for assessment"; host-side NumPy, not part of
+    the accelerated path.
+    """
+    mat = np.asarray(mat)
+    (height, width) = mat.shape
+    xd = np.arange(width) - xcenter
+    yd = np.arange(height) - ycenter
+    xd_mat, yd_mat = np.meshgrid(xd, yd)
+    rd_mat = np.sqrt(xd_mat ** 2 + yd_mat ** 2)
+    fact_mat = _radial_factor_1d(rd_mat, list_fact)
+    xu_mat = np.intp(np.round(np.clip(xcenter + fact_mat * xd_mat, 0,
+                                      width - 1)))
+    yu_mat = np.intp(np.round(np.clip(ycenter + fact_mat * yd_mat, 0,
+                                      height - 1)))
+    out = np.zeros_like(mat)
+    out[yu_mat, xu_mat] = mat
+    return out
+
+
+def _stack_call(src, dst, depth, height, width, src_row0, src_rows, src_pitch,
+                src_slice, row0, nrows, coord_round, model, stream):
+    opt = _opts(1)
+    _cabi.call("dcb_unwarp_stack_backward_f32", _vp(src), _vp(dst.ptr), depth,
+               height, width, src_row0, src_rows, src_pitch, src_slice,
+               dst.pitch, dst.slice_stride, row0, nrows, coord_round,
+               ctypes.byref(model), ctypes.byref(opt), _vp(stream.handle))
+
+
+def _upload_row_window(mat3d, row_lo, row_hi, stream):
+    """Rows [row_lo, row_hi) of every slice -> DeviceArray (D, rows, W)."""
+    win = _to_f32_exact(np.asarray(mat3d[:, row_lo:row_hi, :]))
+    return DeviceArray.from_host(win, stream)
+
+
+def unwarp_slice_backward(mat3D, xcenter, ycenter, list_fact, index):
+    """
+    Generate an unwarped slice [:, index, :] of a 3D dataset, i.e. one
+    unwarped sinogram of a 3D tomographic data (reference ``:188-229``).
+
+    The coordinates stay float64 (never rounded to float32) and the output is
+    always float32, as in the reference.  Only the row window the reference
+    crops to (``:221-223``) is sent to the GPU.
+
+    Returns
+    -------
+    array_like
+        2D float32 array (depth, width).
+    """
+    on_device = isinstance(mat3D, DeviceArray)
+    if len(mat3D.shape) < 3:
+        raise ValueError("Input must be a 3D data")
+    (depth, height, width) = mat3D.shape
+    yd = _row_yd(height, width, xcenter, ycenter, list_fact, index)
+    yd_min = int(np.int16(np.floor(np.amin(yd))))
+    yd_max = int(np.int16(np.ceil(np.amax(yd)))) + 1
+    if int(index) != index:
+        raise NotImplementedError("fractional slice index %r" % (index,))
+    index = int(index)
+    if not 0 <= index < height:
+        raise NotImplementedError(
+            "index %d outside the image is not supported by the CUDA path"
+            % index)
+    model = _cabi.make_radial(xcenter, ycenter, list_fact)
+    stream = _dev.current_stream()
+    dst = DeviceArray((depth, 1, width))
+    if on_device:
+        src_ptr = mat3D.ptr + yd_min * mat3D.pitch
+        _stack_call(src_ptr, dst, depth, height, width, yd_min,
+                    yd_max - yd_min, mat3D.pitch, mat3D.slice_stride, index, 1,
+                    0, model, stream)
+        dst.shape = (depth, width)
+        return dst
+    win = _upload_row_window(mat3D, yd_min, yd_max, stream)
+    _stack_call(win.ptr, dst, depth, height, width, yd_min, yd_max - yd_min,
+                win.pitch, win.slice_stride, index, 1, 0, model, stream)
+    return dst.to_host(stream=stream).reshape(depth, width)
+
+
+def _mapping(mat, xmat, ymat):
+    """
+    Apply a geometric transformation to a 2D array (reference ``:232-252``):
+    bilinear sampling of ``mat`` at the given coordinates.  Coordinates are
+    expected inside the image (every caller in the reference clips them);
+    out-of-range values raise, because clamping is not what SciPy's 'reflect'
+    does there.
+    """
+    xmat = np.asarray(xmat)
+    ymat = np.asarray(ymat)
+    out = _map_coordinates(np.asarray(mat), ymat.ravel(), xmat.ravel(), 1,
+                           "reflect")
+    return out.reshape(xmat.shape)
+
+
+def _map_coordinates(mat, yd, xd, order, mode):
+    (height, width) = mat.shape
+    src_np = _as_f32_image(mat)
+    kind = np.result_type(yd.dtype, xd.dtype)
+    ctype = np.float32 if kind == np.float32 else np.float64
+    yd = np.ascontiguousarray(yd, dtype=ctype).ravel()
+    xd = np.ascontiguousarray(xd, dtype=ctype).ravel()
+    if yd.size != xd.size:
+        raise RuntimeError("invalid shape for coordinate array")
+    n = yd.size
+    stream = _dev.current_stream()
+    src = DeviceArray.from_host(src_np, stream)
+    itemsize = np.dtype(ctype).itemsize
+    sh = _vp(stream.handle)
+    with _dev.borrowed(max(n, 1) * itemsize) as dy, \
+            _dev.borrowed(max(n, 1) * itemsize) as dx, \
+            _dev.borrowed(max(n, 1) * 4) as dout, _dev.borrowed(16) as dflag:
+        _cabi.call("dcb_h2d", _vp(dy.ptr), _vp(yd.ctypes.data), n * itemsize, sh)
+        _cabi.call("dcb_h2d", _vp(dx.ptr), _vp(xd.ctypes.data), n * itemsize, sh)
+        _cabi.call("dcb_memset", _vp(dflag.ptr), 0, 16, sh)
+        opt = _opts(order)
+        _cabi.call("dcb_map_coordinates_f32", _vp(src.ptr), _vp(dout.ptr),
+                   height, width, src.pitch, _vp(dy.ptr), _vp(dx.ptr),
+                   int(ctype is np.float64), n, _vp(dflag.ptr),
+                   ctypes.byref(opt), sh)
+        out = _dev.pinned_empty((n,), np.float32)
+        flag = np.zeros(4, dtype=np.uint32)
+        _cabi.call("dcb_d2h", _vp(out.ctypes.data), _vp(dout.ptr), n * 4, sh)
+        _cabi.call("dcb_d2h", _vp(flag.ctypes.data), _vp(dflag.ptr), 16, sh)
+        stream.sync()
+    if flag[0] != 0 and mode != "nearest":
+        raise NotImplementedError(
+            "%d coordinates lie outside the image; the CUDA path clamps them, "
+            "which equals SciPy only for mode='nearest' (got %r)"
+            % (int(flag[0]), mode))
+    return out
+
+
+def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
+                                 start_index, stop_index):
+    """
+    Generate a chunk of unwarped slices [:, start_index: stop_index, :] used
+    for tomographic data (reference ``:255-313``).  ``stop_index`` is
+    inclusive; the index checks (including the ``-1`` wart) are
+    the reference's.
+
+    Returns
+    -------
+    array_like
+        3D array (depth, stop-start+1, width), float32.
+    """
+    on_device = isinstance(mat3D, DeviceArray)
+    if len(mat3D.shape) < 3:
+        raise ValueError("Input must be a 3D data")
+    (depth, height, width) = mat3D.shape
+    index_list = np.arange(height, dtype=np.int16)
+    if stop_index == -1:
+        stop_index = height
+    if (start_index not in index_list) or (stop_index not in index_list):
+        raise ValueError("Selected index is out of the range")
+    start_index, stop_index = int(start_index), int(stop_index)
+    if stop_index < start_index:
+        raise ValueError("Selected index is out of the range")
+    yd1 = _row_yd(height, width, xcenter, ycenter, list_fact, start_index)
+    yd2 = _row_yd(height, width, xcenter, ycenter, list_fact, stop_index)
+    yd_min = int(np.int16(np.floor(np.amin(yd1))))
+    yd_max = int(np.int16(np.ceil(np.amax(yd2)))) + 1
+    if not on_device and np.asarray(mat3D[:0]).dtype != np.float32:
+        raise NotImplementedError(
+            "dtype %s is not implemented on the CUDA path yet (float32 is)"
+            % np.asarray(mat3D[:0]).dtype)
+    nrows = stop_index - start_index + 1
+    model = _cabi.make_radial(xcenter, ycenter, list_fact)
+    stream = _dev.current_stream()
+    dst = DeviceArray((depth, nrows, width))
+    if on_device:
+        src_ptr = mat3D.ptr + yd_min * mat3D.pitch
+        _stack_call(src_ptr, dst, depth, height, width, yd_min,
+                    yd_max - yd_min, mat3D.pitch, mat3D.slice_stride,
+                    start_index, nrows, 1, model, stream)
+        return dst
+    win = _upload_row_window(mat3D, yd_min, yd_max, stream)
+    _stack_call(win.ptr, dst, depth, height, width, yd_min, yd_max - yd_min,
+                win.pitch, win.slice_stride, start_index, nrows, 1, model,
+                stream)
+    return dst.to_host(stream=stream)
+
+
+def _generate_perspective_map(mat, list_coef):
+    """
+    Generate mapping indices between images (reference ``:444-459``).  Host
+    NumPy: callers use it to precompute ``map_index`` once and pass it to
+    :func:`correct_perspective_image` many times.
+    """
+    c1, c2, c3, c4, c5, c6, c7, c8 = list_coef
+    (height, width) = mat.shape
+    xu_mat, yu_mat = np.meshgrid(np.arange(width), np.arange(height))
+    den = c7 * xu_mat + c8 * yu_mat + 1.0
+    xd_mat = (c1 * xu_mat + c2 * yu_mat + c3) / den
+    yd_mat = (c4 * xu_mat + c5 * yu_mat + c6) / den
+    xd_mat = np.float32(np.clip(xd_mat, 0, width - 1))
+    yd_mat = np.float32(np.clip(yd_mat, 0, height - 1))
+    return np.reshape(yd_mat, (-1, 1)), np.reshape(xd_mat, (-1, 1))
+
+
+def correct_perspective_image(mat, list_coef, order=1, mode="reflect",
+                              map_index=None):
+    """
+    Apply perspective correction to an image (reference ``:462-492``).
+
+    Parameters
+    ----------
+    mat : array_like or DeviceArray
+        2D float32 array.
+    list_coef : list of floats
+        Coefficients of the backward-mapping matrix (eight).
+    order, mode : see :func:`unwarp_image_backward`.
+    map_index : tuple of array_like, optional
+        Precomputed ``(yd, xd)`` indices; generated on the GPU if None.
+
+    Returns
+    -------
+    array_like
+        Corrected image.
+    """
+    if len(list_coef) != 8:
+        raise ValueError("!!! Eight coefficients are required !!!")
+    on_device = isinstance(mat, DeviceArray)
+    if not on_device:
+        mat = np.asarray(mat)
+    (height, width) = mat.shape
+    order = _check_order_mode(order, mode)
+    if map_index is not None:
+        if on_device:
+            raise NotImplementedError("map_index with a DeviceArray input")
+        yd, xd = map_index
+        out = _map_coordinates(mat, np.asarray(yd), np.asarray(xd), order,
+                               mode)
+        return out.reshape((height, width))
+    model = _cabi.make_persp(list_coef)
+    stream = _dev.current_stream()
+    src = mat if on_device else DeviceArray.from_host(_as_f32_image(mat),
+                                                      stream)
+    dst = DeviceArray((height, width))
+    opt = _opts(order)
+    _cabi.call("dcb_correct_perspective_image_f32", _vp(src.ptr),
+               _vp(dst.ptr), height, width, src.pitch, dst.pitch,
+               ctypes.byref(model), ctypes.byref(opt), _vp(stream.handle))
+    return dst if on_device else dst.to_host(stream=stream)
+
+
+def unwarp_image_backward_perspective(mat, xcenter, ycenter, list_fact,
+                                      list_coef, order=1, mode="reflect"):
+    """
+    Radial unwarp followed by perspective correction in one call, the combined
+    entry BASELINE.json names.  The reference has no such function; the result
+    is defined as ``correct_perspective_image(unwarp_image_backward(mat, ...),
+    list_coef)`` (``examples/readthedocs_demo/demo_05.py:127,147``) with the
+    intermediate image rounded to float32 -- both passes run back to back on
+    the GPU, the intermediate never leaves HBM.
+    """
+    if len(list_coef) != 8:
+        raise ValueError("!!! Eight coefficients are required !!!")
+    on_device = isinstance(mat, DeviceArray)
+    if not on_device:
+        mat = np.asarray(mat)
+    (height, width) = mat.shape
+    order = _check_order_mode(order, mode)
+    radial = _cabi.make_radial(xcenter, ycenter, list_fact)
+    persp = _cabi.make_persp(list_coef)
+    stream = _dev.current_stream()
+    src = mat if on_device else DeviceArray.from_host(_as_f32_image(mat),
+                                                      stream)
+    tmp = DeviceArray((height, width))
+    dst = DeviceArray((height, width))
+    opt = _opts(order)
+    _cabi.call("dcb_unwarp_image_backward_perspective_f32", _vp(src.ptr),
+               _vp(dst.ptr), _vp(tmp.ptr), height, width, src.pitch, dst.pitch,
+               tmp.pitch, ctypes.byref(radial), ctypes.byref(persp),
+               ctypes.byref(opt), _vp(stream.handle))
+    if on_device:
+        dst._keepalive = tmp      # until the stream has consumed it
+        return dst
+    return dst.to_host(stream=stream)
+
+
+# ---------------------------------------------------------------------------
+# point-list helpers (host side; tiny inputs)
+# ---------------------------------------------------------------------------
+def unwarp_line_forward(list_lines, xcenter, ycenter, list_fact):
+    """
+    Unwarp lines of dot-centroids using a forward model (reference ``:36-64``).
+
+    Returns a list of 2D arrays of unwarped (y, x) coordinates.
+    """
+    fact = np.asarray(list_fact, dtype=np.float64)
+    expo = np.arange(len(fact), dtype=np.int16)
+    list_ulines = []
+    for line in list_lines:
+        line = np.asarray(line)
+        uline = np.zeros_like(line)
+        for j in range(len(line)):
+            xd = line[j, 1] - xcenter
+            yd = line[j, 0] - ycenter
+            rd = np.sqrt(xd * xd + yd * yd)
+            factor = np.sum(fact * np.power(rd, expo))
+            uline[j, 1] = xcenter + factor * xd
+            uline[j, 0] = ycenter + factor * yd
+        list_ulines.append(uline)
+    return list_ulines
+
+
+def _func_diff(ru, rd, *list_fact):
+    poly = np.sum(np.asarray([a * ru ** i for i, a in enumerate(list_fact)]))
+    return (rd - ru * poly) ** 2
+
+
+def unwarp_line_backward(list_lines, xcenter, ycenter, list_fact):
+    """
+    Unwarp lines of dot-centroids using a backward model (reference
+    ``:72-108``): the undistorted radius of every dot is found by numerical
+    minimisation of ``(rd - ru * F(ru))**2`` started at ``rd``.
+    """
+    list_ulines = []
+    for line in list_lines:
+        line = np.asarray(line)
+        uline = np.zeros_like(line)
+        for j in range(len(line)):
+            xd = line[j, 1] - xcenter
+            yd = line[j, 0] - ycenter
+            rd = np.sqrt(xd * xd + yd * yd)
+            res = optimize.minimize(_func_diff, rd,
+                                    args=(rd,) + tuple(list_fact))
+            ru = res.x[0]
+            factor = ru / rd if rd != 0.0 else 0.0
+            uline[j, 1] = xcenter + factor * xd
+            uline[j, 0] = ycenter + factor * yd
+        list_ulines.append(uline)
+    return list_ulines
+
+
+def _residual(list_ulines, xcenter, ycenter, horizontal):
+    rows = []
+    for line in list_ulines:
+        line = np.asarray(line)
+        y = line[:, 0] - ycenter
+        x = line[:, 1] - xcenter
+        if horizontal:
+            (a, b) = np.polyfit(x, y, 1)
+            dist = np.abs(a * x - y + b) / np.sqrt(a ** 2 + 1)
+        else:
+            (a, b) = np.polyfit(y, x, 1)
+            dist = np.abs(a * y - x + b) / np.sqrt(a ** 2 + 1)
+        radius = np.sqrt(x ** 2 + y ** 2)
+        rows.extend(np.stack([radius, dist], axis=1))
+    data = np.asarray(rows)
+    return data[data[:, 0].argsort()]
+
+
+def calc_residual_hor(list_ulines, xcenter, ycenter):
+    """
+    Distances of unwarped dots on each horizontal line to its fitted straight
+    line (reference ``:316-351``).  Returns rows ``[radius, residual]`` sorted
+    by radius.
+    """
+    return _residual(list_ulines, xcenter, ycenter, True)
+
+
+def calc_residual_ver(list_ulines, xcenter, ycenter):
+    """Same as :func:`calc_residual_hor` for vertical lines (``:354-388``)."""
+    return _residual(list_ulines, xcenter, ycenter, False)
+
+
+def check_distortion(list_data):
+    """
+    True if more than 15% of the dots have a residual above one pixel
+    (reference ``:391-411``).
+    """
+    res = np.asarray(list_data[:, 1])
+    return bool(1.0 * np.count_nonzero(res > 1.0) / len(res) > 0.15)
+
+
+def correct_perspective_line(list_lines, list_coef):
+    """
+    Apply perspective correction to lines of (y, x) points (reference
+    ``:414-441``).
+    """
+    if len(list_coef) != 8:
+        raise ValueError("!!! Eight coefficients are required !!!")
+    c1, c2, c3, c4, c5, c6, c7, c8 = list_coef
+    list_clines = []
+    for iline in list_lines:
+        line = np.asarray(iline)
+        x = line[:, 1]
+        y = line[:, 0]
+        den = c7 * x + c8 * y + 1.0
+        xn = (c1 * x + c2 * y + c3) / den
+        yn = (c4 * x + c5 * y + c6) / den
+        list_clines.append(np.stack([yn, xn], axis=1))
+    return list_clines

@@ -1,0 +1,215 @@
+/*
+ * discorpy_b200.h -- C ABI of libdiscorpy_b200.so
+ *
+ * A from-scratch sm_100a (NVIDIA B200) implementation of the image-unwarping
+ * hot path of Discorpy's `discorpy/post/postprocessing.py`.  The reference is
+ * pure Python and has no FFI of its own: the functions
+ * below are what a `discorpy.post.postprocessing` replacement binds with
+ * ctypes/cffi -- see INTEGRATION.md for the stub -- and each one names the
+ * reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++ / torch types; every function returns an int status
+ *     (DCB_OK == 0, negative on error) and leaves a thread-local message for
+ *     dcb_last_error().
+ *   - pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *     compute calls are asynchronous on it, the caller owns every buffer.
+ *   - pitches / strides are in BYTES.  The TMA-staged path needs the source
+ *     base 16-byte aligned and the source pitch and slice stride multiples of
+ *     16 bytes; otherwise DCB_PATH_AUTO silently takes the direct-gather path
+ *     (same numerics) and DCB_PATH_TMA returns DCB_ERR_ARG.
+ *   - the library never falls back to a CPU implementation.
+ */
+#ifndef DISCORPY_B200_H
+#define DISCORPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCB_VERSION_MAJOR 0
+#define DCB_VERSION_MINOR 1
+#define DCB_MAX_TERMS 16 /* polynomial coefficients a_0 .. a_15 */
+
+enum dcb_status {
+    DCB_OK = 0,
+    DCB_ERR_ARG = -1,         /* bad argument (message says which) */
+    DCB_ERR_CUDA = -2,        /* CUDA runtime / driver error */
+    DCB_ERR_UNSUPPORTED = -3, /* valid request the library does not implement */
+    DCB_ERR_NO_DEVICE = -4
+};
+
+/* How the four bilinear taps are blended (order 1).  All variants read and
+ * multiply all four taps (a NaN tap contaminates like it does in SciPy). */
+enum dcb_blend {
+    DCB_BLEND_EXACT = 0,  /* fp64, SciPy's operation order: bit-faithful (default) */
+    DCB_BLEND_LERP64 = 1, /* fp64 three-lerp form: fewer fp64 ops, <= 1 fp32 ulp from EXACT in rare cases */
+    DCB_BLEND_LERP32 = 2  /* fp32 three-lerp: +-1 fp32 ulp; opt-in fast mode */
+};
+
+enum dcb_path {
+    DCB_PATH_AUTO = 0,   /* TMA-staged tiles where the source footprint fits, direct gathers elsewhere */
+    DCB_PATH_DIRECT = 1, /* ld.global.nc gathers only */
+    DCB_PATH_TMA = 2     /* like AUTO but refuses (DCB_ERR_ARG) when the layout cannot be described to TMA */
+};
+
+/* Radial backward model: F(r) = sum_{i<n} a[i] r^i, r = |(x,y) - (xc,yc)|
+ * (postprocessing.py:138-145). */
+typedef struct dcb_radial {
+    double xc;
+    double yc;
+    int32_t n;
+    int32_t reserved;
+    double a[DCB_MAX_TERMS];
+} dcb_radial;
+
+/* Projective backward map, c[0..7] = c1..c8 of postprocessing.py:448-455. */
+typedef struct dcb_persp {
+    double c[8];
+} dcb_persp;
+
+typedef struct dcb_options {
+    int32_t order; /* 0 nearest, 1 bilinear */
+    int32_t blend; /* enum dcb_blend */
+    int32_t path;  /* enum dcb_path */
+    int32_t flags; /* reserved, 0 */
+} dcb_options;
+
+/* ---- library / device ---------------------------------------------------- */
+int dcb_version(void);                 /* major*1000 + minor */
+const char *dcb_last_error(void);      /* thread-local, never NULL */
+int dcb_device_count(int *count);
+int dcb_init(int device);              /* cudaSetDevice + resolve the TMA encoder; idempotent */
+int dcb_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
+                    size_t *total_mem, size_t *free_mem, char *name, int name_len);
+
+/* ---- memory, streams, events (thin cudart wrappers so that the Python host
+ *      needs neither torch nor cuda-python) --------------------------------- */
+int dcb_malloc(void **dptr, size_t nbytes);
+int dcb_free(void *dptr);
+int dcb_memset(void *dptr, int value, size_t nbytes, void *stream);
+int dcb_host_alloc(void **hptr_host, size_t nbytes);   /* pinned */
+int dcb_host_free(void *hptr_host);
+int dcb_host_register(void *hptr_host, size_t nbytes); /* pin caller memory in place */
+int dcb_host_unregister(void *hptr_host);
+int dcb_is_pinned(const void *hptr_host, int *pinned);
+int dcb_h2d(void *dst, const void *src_host, size_t nbytes, void *stream);
+int dcb_d2h(void *dst_host, const void *src, size_t nbytes, void *stream);
+int dcb_d2d(void *dst, const void *src, size_t nbytes, void *stream);
+int dcb_h2d_2d(void *dst, size_t dst_pitch, const void *src_host, size_t src_pitch,
+               size_t width_bytes, size_t rows, void *stream);
+int dcb_d2h_2d(void *dst_host, size_t dst_pitch, const void *src, size_t src_pitch,
+               size_t width_bytes, size_t rows, void *stream);
+int dcb_stream_create(void **stream);
+int dcb_stream_destroy(void *stream);
+int dcb_stream_sync(void *stream);
+int dcb_device_sync(void);
+int dcb_event_create(void **event);
+int dcb_event_destroy(void *event);
+int dcb_event_record(void *event, void *stream);
+int dcb_event_sync(void *event);
+int dcb_event_elapsed_ms(void *start, void *stop, float *ms);
+
+/* ---- the hot path -------------------------------------------------------- */
+
+/* Replaces discorpy/post/postprocessing.py:111-148 `unwarp_image_backward`
+ * for a float32 image: coordinates in fp64, clipped, rounded once to fp32
+ * (:144-145), then the order-0/1 sampling that scipy.ndimage.map_coordinates
+ * performs (:147).  src and dst are (H, W) float32, dst must not alias src. */
+int dcb_unwarp_image_backward_f32(const float *src, float *dst, int H, int W,
+                                  size_t src_pitch, size_t dst_pitch,
+                                  const dcb_radial *model_host,
+                                  const dcb_options *opt_host, void *stream);
+
+/* Replaces the per-slice Python loops of
+ *   postprocessing.py:188-229 `unwarp_slice_backward`        (coord_round = 0,
+ *       row0 = index, nrows = 1: float64 coordinates, never rounded), and
+ *   postprocessing.py:255-313 `unwarp_chunk_slices_backward` (coord_round = 1,
+ *       row0 = start_index, nrows = stop-start+1: fp32-rounded coordinates),
+ * and, with row0 = 0, nrows = H, a whole stack / batch of independent images
+ * (BASELINE configs 4 and 5).  The images are (D, H, W) float32; dst is
+ * (D, nrows, W) float32.  The radial map is evaluated once per output tile and
+ * reused for every slice.
+ * Like the reference (:221-223, :300-301) the caller may hold only a window of
+ * source rows on the device: `src` points at image row `src_row0` of slice 0
+ * and every slice holds `src_rows` rows (src_row0 = 0, src_rows = H for whole
+ * slices).  Tap rows are clamped into the window, and the "+1" bilinear tap
+ * never goes past its last row -- exactly what sampling the reference's cropped
+ * view does. */
+int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, int W,
+                                  int src_row0, int src_rows,
+                                  size_t src_pitch, size_t src_slice_stride,
+                                  size_t dst_pitch, size_t dst_slice_stride,
+                                  int row0, int nrows, int coord_round,
+                                  const dcb_radial *model_host,
+                                  const dcb_options *opt_host, void *stream);
+
+/* Replaces postprocessing.py:444-459 `_generate_perspective_map` +
+ * :462-492 `correct_perspective_image` (map_index=None). */
+int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W,
+                                      size_t src_pitch, size_t dst_pitch,
+                                      const dcb_persp *model_host,
+                                      const dcb_options *opt_host, void *stream);
+
+/* Replaces the scipy.ndimage.map_coordinates call itself for caller-supplied
+ * coordinates: postprocessing.py:232-252 `_mapping` and the `map_index=`
+ * argument of `correct_perspective_image` (:489-491).  yd/xd are device arrays
+ * of n_out coordinates, float32 (coord_is_f64 = 0) or float64 (= 1); they are
+ * clamped to the image like every coordinate the reference produces.  dst
+ * receives n_out float32 values.  If oob_count (device uint32, caller-zeroed,
+ * may be NULL) is given it is incremented by the number of coordinates that
+ * lay outside [0,H-1]x[0,W-1] (or were NaN) before clamping, so the host can
+ * refuse boundary modes for which clamping is not what SciPy does. */
+int dcb_map_coordinates_f32(const float *src, float *dst, int H, int W, size_t src_pitch,
+                            const void *yd, const void *xd, int coord_is_f64,
+                            size_t n_out, uint32_t *oob_count,
+                            const dcb_options *opt_host, void *stream);
+
+/* The combined entry BASELINE.json's north_star names
+ * (`unwarp_image_backward_perspective`; not in the reference).  Defined as the
+ * two-pass composition of examples/readthedocs_demo/demo_05.py:127 then :147
+ * with the intermediate image rounded to float32.  `scratch` is a caller-owned
+ * (H, W) float32 device buffer with pitch `scratch_pitch` for the intermediate. */
+int dcb_unwarp_image_backward_perspective_f32(const float *src, float *dst, float *scratch,
+                                              int H, int W, size_t src_pitch,
+                                              size_t dst_pitch, size_t scratch_pitch,
+                                              const dcb_radial *radial_host,
+                                              const dcb_persp *persp_host,
+                                              const dcb_options *opt_host, void *stream);
+
+/* Benchmark input generator (no reference counterpart): dst[i] =
+ * top24(splitmix64(seed ^ (offset + i))) / 2^24, float32 in [0,1).  Lets
+ * multi-GB stacks be created in HBM without crossing PCIe. */
+int dcb_fill_synthetic_f32(float *dst, size_t n, uint64_t seed, uint64_t offset,
+                           void *stream);
+
+/* ---- diagnostics --------------------------------------------------------- */
+
+/* Number of kernel launches issued by this library in the calling process
+ * (all threads) since load / since the last reset. */
+int dcb_launch_count(uint64_t *count);
+int dcb_launch_count_reset(void);
+
+/* What the last compute call on this thread decided: path actually used
+ * (enum dcb_path, never AUTO), staged box width/height, grid size, dynamic
+ * shared memory bytes. */
+int dcb_last_plan(int *path, int *box_w, int *box_h, int *grid, int *smem_bytes);
+
+/* Device self-test of the custom fp64 square root used by the radial kernels
+ * against IEEE sqrt on n pseudo-random inputs; *mismatch receives the number
+ * of inputs whose result differs from the correctly rounded one. */
+int dcb_selftest_sqrt(size_t n, uint64_t seed, uint64_t *mismatch);
+
+/* Micro-benchmarks used to size the kernels (DESIGN.md "fp64 budget"):
+ * which = 0 DFMA chain, 1 f32<->f64 conversions, 2 MUFU.RSQ64H, 3 the radial
+ * coordinate evaluation alone (5 terms), 4 FFMA.  Returns giga-ops/s. */
+int dcb_microbench(int which, double *gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISCORPY_B200_H */

@@ -1,0 +1,131 @@
+"""The oracle against the reference's outputs (CPU only).
+
+tests/golden/reference_outputs.npz was produced by oracle/make_golden.py from
+the unmodified reference in the build container; here the NumPy and the C
+restatement are re-checked against it wherever the repo travels.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_cases, golden_output
+from oracle import oracle_np as orc
+from oracle import oracle_c
+from oracle.make_golden import make_input
+
+CASES = load_cases()
+
+
+def _run_np(c, mat):
+    fn = c["fn"]
+    if fn == "image":
+        return orc.unwarp_image_backward(mat, c["xc"], c["yc"], c["fact"],
+                                         order=c["order"])
+    if fn == "slice":
+        return orc.unwarp_slice_backward(mat, c["xc"], c["yc"], c["fact"],
+                                         c["index"])
+    if fn == "chunk":
+        return orc.unwarp_chunk_slices_backward(mat, c["xc"], c["yc"],
+                                                c["fact"], c["start"],
+                                                c["stop"])
+    if fn == "persp":
+        return orc.correct_perspective_image(mat, c["coef"], order=c["order"])
+    if fn == "combined":
+        return orc.unwarp_image_backward_perspective(
+            mat, c["xc"], c["yc"], c["fact"], c["coef"])
+    raise AssertionError(fn)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_numpy_oracle_matches_reference_bit_for_bit(case):
+    mat = make_input(case["kind"], tuple(case["shape"]), case["seed"],
+                     case.get("dtype", "float32"))
+    got = _run_np(case, mat)
+    want = golden_output(case["id"])
+    assert got.dtype == want.dtype and got.shape == want.shape
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+F32 = [c for c in CASES if c.get("dtype", "float32") == "float32"]
+
+
+@pytest.mark.parametrize("case", F32, ids=[c["id"] for c in F32])
+def test_c_oracle_matches_reference(case):
+    mat = make_input(case["kind"], tuple(case["shape"]), case["seed"])
+    fn = case["fn"]
+    want = golden_output(case["id"])
+    if fn == "image":
+        got = oracle_c.unwarp_image_backward(mat, case["xc"], case["yc"],
+                                             case["fact"], case["order"])
+    elif fn == "slice":
+        h, w = mat.shape[1:]
+        yd, _ = orc.radial_coords_row(h, w, case["xc"], case["yc"],
+                                      case["fact"], case["index"])
+        ylo = int(np.floor(yd.min()))
+        yhi = int(np.ceil(yd.max()))
+        got = oracle_c.unwarp_stack_backward(
+            mat, case["xc"], case["yc"], case["fact"], case["index"], 1,
+            coord_round=False, ylo=ylo, yhi=yhi)[:, 0, :]
+    elif fn == "chunk":
+        h, w = mat.shape[1:]
+        ylo, yend = orc.chunk_row_window(h, w, case["xc"], case["yc"],
+                                         case["fact"], case["start"],
+                                         case["stop"])
+        got = oracle_c.unwarp_stack_backward(
+            mat, case["xc"], case["yc"], case["fact"], case["start"],
+            case["stop"] - case["start"] + 1, coord_round=True, ylo=ylo,
+            yhi=yend - 1)
+    elif fn == "persp":
+        got = oracle_c.correct_perspective_image(mat, case["coef"],
+                                                 case["order"])
+    else:
+        tmp = oracle_c.unwarp_image_backward(mat, case["xc"], case["yc"],
+                                             case["fact"], 1)
+        got = oracle_c.correct_perspective_image(tmp, case["coef"], 1)
+    assert got.shape == want.shape
+    # libm pow vs NumPy power may flip a float32 coordinate very rarely
+    # (oracle_c.c header); on these fixtures it does not.
+    assert np.array_equal(got, want)
+
+
+def test_sampler_matches_scipy_map_coordinates():
+    """The vectorised sampler restates SciPy's C loop: compare directly."""
+    from scipy.ndimage import map_coordinates
+    rng = np.random.default_rng(7)
+    mat = rng.standard_normal((83, 117)).astype(np.float32) * 100
+    yd = np.float32(rng.random(20000) * 82)
+    xd = np.float32(rng.random(20000) * 116)
+    yd[:50] = np.float32(np.arange(50) % 83)        # exact integers
+    xd[:50] = 116.0                                  # last column
+    yd[50:100] = 82.0                                # last row
+    xd[100:150] = np.float32(np.arange(50)) + np.float32(0.5)   # halves
+    for order in (0, 1):
+        want = map_coordinates(mat, (yd, xd), order=order, mode="reflect")
+        got = orc.sample(mat, yd, xd, order)
+        assert np.array_equal(got, want)
+    for mode in ("constant", "nearest", "mirror", "wrap", "grid-wrap"):
+        want = map_coordinates(mat, (yd, xd), order=1, mode=mode)
+        assert np.array_equal(orc.sample(mat, yd, xd, 1), want), mode
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/discorpy"),
+                    reason="the reference tree only exists in the build container")
+def test_numpy_oracle_vs_live_reference_large():
+    import importlib
+    import sys
+    sys.path.insert(0, "/root/reference")
+    try:
+        ref = importlib.import_module("discorpy.post.postprocessing")
+    finally:
+        sys.path.remove("/root/reference")
+    rng = np.random.default_rng(11)
+    mat = rng.random((700, 900), dtype=np.float32)
+    fact = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]
+    for order in (0, 1):
+        a = ref.unwarp_image_backward(mat, 451.3, 340.9, fact, order=order)
+        b = orc.unwarp_image_backward(mat, 451.3, 340.9, fact, order=order)
+        assert np.array_equal(a, b)
+    coef = [1.02, 0.01, -15.0, 0.005, 1.01, -8.0, 8e-6, -5e-6]
+    assert np.array_equal(ref.correct_perspective_image(mat, coef),
+                          orc.correct_perspective_image(mat, coef))
