@@ -257,3 +257,23 @@ def unwarp_image_backward_perspective(mat, xcenter, ycenter, list_fact,
     rounded to ``mat.dtype``)."""
     tmp = unwarp_image_backward(mat, xcenter, ycenter, list_fact, order, mode)
     return correct_perspective_image(tmp, list_coef, order, mode)
+
+
+# --------------------------------------------------------------------------
+# CPU-baseline helpers (bench.py's cpu_baseline / --impl reference legs only)
+# --------------------------------------------------------------------------
+def unwarp_rows_scipy(mat, xcenter, ycenter, list_fact, row0, nrows, order=1,
+                      mode="reflect"):
+    """Rows ``row0 .. row0+nrows-1`` of ``unwarp_image_backward`` computed the
+    way the reference computes them -- NumPy float64 temporaries for the
+    coordinates (``postprocessing.py:138-145``) then SciPy's own
+    ``map_coordinates`` (``:147``).  This, not the vectorised ``sample``
+    above, is what the CPU baseline times: it is the reference's code path
+    split over row blocks so that several cores can be used."""
+    from scipy.ndimage import map_coordinates
+    (height, width) = np.shape(mat)
+    yd, xd = radial_coords(height, width, xcenter, ycenter, list_fact,
+                           row0=row0, nrows=nrows)
+    indices = np.reshape(yd, (-1, 1)), np.reshape(xd, (-1, 1))
+    out = map_coordinates(mat, indices, order=order, mode=mode)
+    return out.reshape((nrows, width))

@@ -1,0 +1,298 @@
+"""GPU parity: the CUDA path (through the Python drop-in -> ctypes -> C ABI)
+against the reference's golden outputs and against the oracle.
+
+Bars (SURVEY.md 8d / BASELINE north_star):
+  * order 0 (nearest): bit-exact;
+  * order 1: |gpu - ref| <= 1e-5 * max(1, max|mat|).  With the default
+    DCB_BLEND_EXACT the result is expected to be bit-identical as well; the
+    tests assert equality on the golden fixtures and report/limit the number
+    of non-identical pixels on the big seeded images, where an fp64
+    last-bit difference in the coordinate polynomial (Horner + FMA here,
+    term-by-term NumPy `power` in the reference) can flip a float32-rounded
+    coordinate with probability ~1e-8 per pixel (hard part 6).
+"""
+import numpy as np
+import pytest
+
+from conftest import load_cases, golden_output, tolerance
+from oracle import oracle_np as orc
+from oracle import oracle_c
+from oracle.make_golden import make_input
+
+import discorpy_b200 as dcb
+import discorpy_b200.post.postprocessing as post
+
+pytestmark = pytest.mark.gpu
+
+CASES = [c for c in load_cases() if c.get("dtype", "float32") == "float32"]
+FACT5 = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]
+COEF_DOT_05 = [1.00227490554, -2.99523692178e-05, 8.99519088e-08,
+               -1.57066461911e-10, 8.08880211618e-14]
+
+
+def _run_gpu(c, mat):
+    fn = c["fn"]
+    if fn == "image":
+        return post.unwarp_image_backward(mat, c["xc"], c["yc"], c["fact"],
+                                          order=c["order"])
+    if fn == "slice":
+        return post.unwarp_slice_backward(mat, c["xc"], c["yc"], c["fact"],
+                                          c["index"])
+    if fn == "chunk":
+        return post.unwarp_chunk_slices_backward(mat, c["xc"], c["yc"],
+                                                 c["fact"], c["start"],
+                                                 c["stop"])
+    if fn == "persp":
+        return post.correct_perspective_image(mat, c["coef"], order=c["order"])
+    if fn == "combined":
+        return post.unwarp_image_backward_perspective(
+            mat, c["xc"], c["yc"], c["fact"], c["coef"])
+    raise AssertionError(fn)
+
+
+@pytest.fixture(autouse=True)
+def _default_config():
+    post.config["blend"] = dcb.BLEND_EXACT
+    post.config["path"] = dcb.PATH_AUTO
+    yield
+    post.config["blend"] = dcb.BLEND_EXACT
+    post.config["path"] = dcb.PATH_AUTO
+
+
+@pytest.mark.parametrize("path", [dcb.PATH_AUTO, dcb.PATH_DIRECT],
+                         ids=["auto", "direct"])
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_golden_vectors_bit_exact(case, path):
+    post.config["path"] = path
+    mat = make_input(case["kind"], tuple(case["shape"]), case["seed"])
+    got = _run_gpu(case, mat)
+    want = golden_output(case["id"])
+    assert got.dtype == want.dtype and got.shape == want.shape
+    assert isinstance(got, np.ndarray) and got.flags.c_contiguous
+    nbad = int(np.count_nonzero(got != want))
+    assert nbad == 0, "%d of %d pixels differ, max %g" % (
+        nbad, got.size, float(np.max(np.abs(got - want))))
+
+
+def _compare(got, want, mat, order, flips_allowed):
+    """Returns (n_not_identical, n_above_tol)."""
+    diff = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    n_ne = int(np.count_nonzero(got != want))
+    n_tol = int(np.count_nonzero(diff > tolerance(mat)))
+    if order == 0:
+        assert n_ne <= flips_allowed, "nearest: %d pixels differ" % n_ne
+    else:
+        assert n_tol <= flips_allowed, (
+            "%d pixels above tol (max %g), %d not identical"
+            % (n_tol, float(diff.max()), n_ne))
+    return n_ne, n_tol
+
+
+@pytest.mark.parametrize("shape,xc,yc,fact", [
+    ((1024, 1024), 510.3, 500.7, FACT5),
+    ((1536, 2050), 1030.2, 760.4, FACT5),              # W % 4 != 0 -> pitched
+    ((801, 1283), 588.692801577, 462.092631791, COEF_DOT_05),
+    ((2160, 2560), 588.692801577, 462.092631791, COEF_DOT_05),   # BASELINE cfg 1 geometry
+    ((1000, 1000), 500, 500, [1.0, 3.0e-3]),           # integer centre
+    ((2048, 2048), 1030.2, 1019.6,
+     [1.0, -1e-5, 3e-8, -2e-11, 5e-15, -8e-19, 6e-23, -2e-27, 3e-32]),
+])
+@pytest.mark.parametrize("order", [0, 1])
+def test_seeded_images_against_oracle(shape, xc, yc, fact, order):
+    rng = np.random.default_rng(shape[0] + shape[1] + order)
+    mat = np.floor(rng.random(shape, dtype=np.float32) * 256.0)   # 0..255 like a camera frame
+    want = oracle_c.unwarp_image_backward(mat, xc, yc, fact, order)
+    outs = {}
+    for name, path in (("auto", dcb.PATH_AUTO), ("direct", dcb.PATH_DIRECT)):
+        post.config["path"] = path
+        outs[name] = post.unwarp_image_backward(mat, xc, yc, fact, order=order)
+    # the two memory paths implement the same arithmetic: always identical
+    assert np.array_equal(outs["auto"], outs["direct"])
+    # <= 1 flipped coordinate per ~4 Mpix tolerated (expected ~0.03)
+    _compare(outs["auto"], want, mat, order, flips_allowed=1 + mat.size // (4 << 20))
+
+
+def test_numpy_oracle_full_compare_one_image():
+    """Same check against the NumPy oracle (the one pinned bit-for-bit to the
+    reference), one mid-size image."""
+    rng = np.random.default_rng(5)
+    mat = rng.random((1200, 1600), dtype=np.float32)
+    for order in (0, 1):
+        want = orc.unwarp_image_backward(mat, 801.7, 590.2, FACT5, order)
+        got = post.unwarp_image_backward(mat, 801.7, 590.2, FACT5, order=order)
+        _compare(got, want, mat, order, flips_allowed=1)
+
+
+@pytest.mark.parametrize("blend,rel", [(dcb.BLEND_LERP64, 1e-5),
+                                       (dcb.BLEND_LERP32, 1e-5)])
+def test_fast_blends_within_tolerance(blend, rel):
+    rng = np.random.default_rng(9)
+    mat = rng.random((1024, 1280), dtype=np.float32)          # [0,1) data
+    want = orc.unwarp_image_backward(mat, 640.4, 511.6, FACT5, 1)
+    post.config["blend"] = blend
+    got = post.unwarp_image_backward(mat, 640.4, 511.6, FACT5)
+    diff = np.abs(got.astype(np.float64) - want)
+    assert int(np.count_nonzero(diff > rel)) <= 1
+    if blend == dcb.BLEND_LERP32:
+        assert float(np.median(diff)) < 1e-7
+
+
+def test_baseline_config2_full_size():
+    """BASELINE config 2 at full size (4096 x 4096, 5 terms),
+    full compare with the C oracle plus size-independent properties."""
+    xc, yc = 2050.37, 2040.81
+    fact = [COEF_DOT_05[i] / 3.0 ** i for i in range(5)]
+    rng = np.random.default_rng(2)
+    mat = rng.random((4096, 4096), dtype=np.float32)
+    for order in (0, 1):
+        want = oracle_c.unwarp_image_backward(mat, xc, yc, fact, order)
+        got = post.unwarp_image_backward(mat, xc, yc, fact, order=order)
+        n_ne, n_tol = _compare(got, want, mat, order, flips_allowed=4)
+        print("cfg2 order %d: %d px not identical, %d above tol" % (order, n_ne, n_tol))
+    # identity model: output == input exactly
+    ident = post.unwarp_image_backward(mat, xc, yc, [1.0])
+    assert np.array_equal(ident, mat)
+    # a constant image stays constant under any model
+    const = np.full((4096, 4096), 3.25, dtype=np.float32)
+    assert np.all(post.unwarp_image_backward(const, xc, yc, fact) == 3.25)
+    # idempotence of the data path: same input twice -> same bytes
+    again = post.unwarp_image_backward(mat, xc, yc, fact)
+    assert np.array_equal(again, got)
+
+
+def test_baseline_config3_combined_two_pass():
+    rng = np.random.default_rng(3)
+    mat = rng.random((2048, 2048), dtype=np.float32)
+    fact = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]
+    coef = [1.02, 0.01, -15.0, 0.005, 1.01, -8.0, 8e-6, -5e-6]
+    tmp = oracle_c.unwarp_image_backward(mat, 1030.2, 1019.6, fact, 1)
+    want = oracle_c.correct_perspective_image(tmp, coef, 1)
+    got = post.unwarp_image_backward_perspective(mat, 1030.2, 1019.6, fact, coef)
+    _compare(got, want, mat, 1, flips_allowed=2)
+    # and the two public calls chained give the same bytes as the fused entry
+    chained = post.correct_perspective_image(
+        post.unwarp_image_backward(mat, 1030.2, 1019.6, fact), coef)
+    assert np.array_equal(chained, got)
+
+
+def test_perspective_map_index_route_and_mapping():
+    rng = np.random.default_rng(13)
+    mat = rng.random((300, 421), dtype=np.float32)
+    coef = [0.9, -0.05, 3.0, 0.04, 0.95, 2.0, -3e-4, 2e-4]
+    direct = post.correct_perspective_image(mat, coef)
+    mi = post._generate_perspective_map(mat, coef)
+    via_index = post.correct_perspective_image(mat, coef, map_index=mi)
+    assert np.array_equal(direct, via_index)
+    assert np.array_equal(direct, orc.correct_perspective_image(mat, coef))
+    yd, xd = mi
+    got = post._mapping(mat, xd.reshape(300, 421), yd.reshape(300, 421))
+    assert np.array_equal(got, direct)
+    # float64 coordinates (the slice path's kind) through the generic entry
+    y64 = rng.random(5000) * 299
+    x64 = rng.random(5000) * 420
+    got = post._mapping(mat, x64, y64)
+    assert np.array_equal(got, orc.sample(mat, y64, x64, 1))
+    with pytest.raises(NotImplementedError, match="outside the image"):
+        post._mapping(mat, x64 + 1000.0, y64)
+
+
+def test_stack_paths_against_oracle():
+    """BASELINE config 4 geometry on a host-sized subset: D' = 8 slices."""
+    rng = np.random.default_rng(4)
+    stack = rng.random((8, 640, 2560), dtype=np.float32)
+    xc, yc = 1283.4, 318.9
+    for index in (0, 317, 639):
+        want = orc.unwarp_slice_backward(stack, xc, yc, FACT5, index)
+        got = post.unwarp_slice_backward(stack, xc, yc, FACT5, index)
+        assert got.dtype == np.float32 and got.shape == (8, 2560)
+        diff = np.abs(got.astype(np.float64) - want)
+        assert int(np.count_nonzero(diff > 1e-5)) == 0
+        assert int(np.count_nonzero(got != want)) <= 2      # fp64 last-bit coordinate effects
+    want = orc.unwarp_chunk_slices_backward(stack, xc, yc, FACT5, 100, 227)
+    got = post.unwarp_chunk_slices_backward(stack, xc, yc, FACT5, 100, 227)
+    assert got.shape == (8, 128, 2560)
+    assert int(np.count_nonzero(got != want)) <= 1
+    # chunk over all rows == unwarp_image_backward per slice
+    full = post.unwarp_chunk_slices_backward(stack, xc, yc, FACT5, 0, 639)
+    for z in (0, 5):
+        assert np.array_equal(full[z], post.unwarp_image_backward(stack[z], xc, yc, FACT5))
+    # uint16 stacks are widened exactly (output is float32 in the reference too)
+    st16 = (stack[:2] * 60000).astype(np.uint16)
+    got = post.unwarp_slice_backward(st16, xc, yc, FACT5, 300)
+    want = orc.unwarp_slice_backward(st16, xc, yc, FACT5, 300)
+    assert int(np.count_nonzero(np.abs(got - want) > 1e-5 * 60000)) == 0
+
+
+def test_device_resident_api_and_sharding_gives_same_bytes():
+    rng = np.random.default_rng(21)
+    stack = rng.random((6, 256, 512), dtype=np.float32)
+    dstack = dcb.DeviceArray.from_host(stack)
+    out = post.unwarp_chunk_slices_backward(dstack, 255.5, 127.2, FACT5, 0, 255)
+    assert isinstance(out, dcb.DeviceArray)
+    whole = out.to_host()
+    from discorpy_b200.multigpu import shard_range
+    for world in (2, 4):
+        parts = []
+        for rank in range(world):
+            lo, hi = shard_range(6, rank, world)
+            if hi > lo:
+                parts.append(post.unwarp_chunk_slices_backward(
+                    stack[lo:hi], 255.5, 127.2, FACT5, 0, 255))
+        assert np.array_equal(np.concatenate(parts), whole)
+    img = dcb.DeviceArray.from_host(stack[0])
+    res = post.unwarp_image_backward(img, 255.5, 127.2, FACT5)
+    assert np.array_equal(res.to_host(), whole[0])
+
+
+def test_edge_shapes_and_values():
+    for shape in ((1, 1), (1, 300), (300, 1), (2, 2), (33, 129), (7, 4097)):
+        rng = np.random.default_rng(shape[0] * 31 + shape[1])
+        mat = rng.standard_normal(shape).astype(np.float32)
+        xc, yc = shape[1] / 2.0 + 0.25, shape[0] / 2.0 - 0.5
+        for order in (0, 1):
+            want = orc.unwarp_image_backward(mat, xc, yc, [1.01, -1e-4], order)
+            got = post.unwarp_image_backward(mat, xc, yc, [1.01, -1e-4], order=order)
+            assert np.array_equal(got, want), (shape, order)
+    # a NaN pixel contaminates every output whose 2x2 footprint touches it
+    mat = np.ones((64, 64), np.float32)
+    mat[20, 30] = np.nan
+    got = post.unwarp_image_backward(mat, 32, 32, [1.0])
+    want = orc.unwarp_image_backward(mat, 32, 32, [1.0])
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert int(np.isnan(got).sum()) == 4
+    # non-contiguous input view (a colour channel, demo_07.py:25)
+    rgb = np.random.default_rng(3).random((50, 60, 3)).astype(np.float32)
+    got = post.unwarp_image_backward(rgb[:, :, 1], 30.2, 24.9, [1.0, 2e-3])
+    want = orc.unwarp_image_backward(rgb[:, :, 1], 30.2, 24.9, [1.0, 2e-3])
+    assert np.array_equal(got, want)
+    with pytest.raises(NotImplementedError, match="dtype"):
+        post.unwarp_image_backward(np.zeros((8, 8), np.float64), 4, 4, [1.0])
+
+
+def test_tma_path_is_actually_taken_and_launches_counted():
+    rng = np.random.default_rng(1)
+    mat = rng.random((1024, 1024), dtype=np.float32)
+    before = dcb.launch_count()
+    post.config["path"] = dcb.PATH_TMA
+    post.unwarp_image_backward(mat, 512.2, 511.1, FACT5)
+    plan = dcb.last_plan()
+    assert plan["path"] == dcb.PATH_TMA and plan["box_w"] >= 128 and plan["smem_bytes"] > 0
+    assert dcb.launch_count() == before + 1
+    post.config["path"] = dcb.PATH_DIRECT
+    post.unwarp_image_backward(mat, 512.2, 511.1, FACT5)
+    assert dcb.last_plan()["path"] == dcb.PATH_DIRECT
+
+
+def test_custom_sqrt_is_correctly_rounded():
+    import ctypes
+    from discorpy_b200 import _cabi
+    bad = ctypes.c_uint64(123)
+    _cabi.call("dcb_selftest_sqrt", 1 << 26, 12345, ctypes.byref(bad))
+    assert bad.value == 0, "%d of 2^26 inputs not correctly rounded" % bad.value
+
+
+def test_synthetic_fill_matches_host_restatement():
+    from discorpy_b200.device import synthetic_host
+    arr = dcb.DeviceArray((64, 256)).fill_synthetic(seed=4, offset=1000)
+    got = arr.to_host().ravel()
+    assert np.array_equal(got, synthetic_host(64 * 256, 4, 1000))
