@@ -179,9 +179,10 @@ static int plan_and_launch(TileKernel kern, int rpt, RemapParams &p, double gmai
     if (staged) {
         if (!(gmain < 64.0) || !(gcross < 64.0)) gmain = gcross = 64.0;  // NaN / absurd
         const double tw = std::min(kTileW, p.W) - 1, th = std::min(TH, p.nrows) - 1;
-        long long need_w = (long long)std::ceil(gmain * tw + gcross * th) + 3;
+        // +3 footprint slack, +3 because the box start is aligned down to 4 floats
+        long long need_w = (long long)std::ceil(gmain * tw + gcross * th) + 3 + 3;
         long long need_h = (long long)std::ceil(gmain * th + gcross * tw) + 3;
-        need_w = std::min<long long>(need_w, p.W);
+        need_w = std::min<long long>(need_w, (long long)p.W + 3);
         need_h = std::min<long long>(need_h, p.ylast - p.yorg + 1);
         bw = (int)((need_w + 3) / 4 * 4);
         bh = (int)need_h;
@@ -190,7 +191,7 @@ static int plan_and_launch(TileKernel kern, int rpt, RemapParams &p, double gmai
         if (bw > 256 || bh > 256 || (long long)bw * bh * 4 > max_stage) {
             // footprint bound too large (strong magnification somewhere): stage a
             // modest box; tiles that do not fit fall back to direct gathers.
-            bw = std::min(256, (std::min(kTileW + 16, (p.W + 3) / 4 * 4)));
+            bw = std::min(256, (std::min(kTileW + 16, (p.W + 3) / 4 * 4 + 4)));
             bh = std::min(std::min(TH + 8, p.ylast - p.yorg + 1), max_stage / (bw * 4));
         }
         nstage = (p.D > 1) ? 3 : 1;
@@ -675,6 +676,36 @@ int dcb_selftest_sqrt(size_t n, uint64_t seed, uint64_t *mismatch) {
     cudaFree(d);
     if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
     *mismatch = h;
+    return DCB_OK;
+}
+
+int dcb_selftest_tma(const float *src, int D, int H, int W, size_t pitch, size_t slice_stride,
+                     int box_w, int box_h, int x0, int y0, int z0, float *out, int *status) {
+    REQUIRE(src && out && status, "null pointer");
+    REQUIRE(tma_encoder() != nullptr, "driver does not export cuTensorMapEncodeTiled");
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D};
+    const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)slice_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult cr = tma_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)src, gdim, gstr,
+                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS)
+        return fail(DCB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+    int *dstatus = nullptr;
+    CUDA_TRY(cudaMalloc(&dstatus, sizeof(int)));
+    CUDA_TRY(cudaMemset(dstatus, 0, sizeof(int)));
+    const size_t smem = (size_t)box_w * box_h * 4;
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute((const void *)selftest_tma_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selftest_tma_kernel<<<1, 256, smem>>>(tmap, box_w, box_h, x0, y0, z0, out, dstatus);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaMemcpy(status, dstatus, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(dstatus);
+    if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "selftest_tma: %s", cudaGetErrorString(e));
     return DCB_OK;
 }
 

@@ -94,4 +94,46 @@ __global__ void __launch_bounds__(256)
     if (bad) atomicAdd(mismatch, bad);
 }
 
+// TMA probe: load one (bw x bh) box at element coordinates (x0, y0, z0) of a
+// (D, H, W) float tensor into shared memory and copy it out.  status[0] = 0 ok,
+// 1 = the mbarrier never completed within ~0.2 s (no trap, so the context
+// survives and the host can report which geometry failed).
+__global__ void __launch_bounds__(256)
+    selftest_tma_kernel(const __grid_constant__ CUtensorMap tmap, int bw, int bh, int x0, int y0,
+                        int z0, float *out, int *status) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (uint32_t)(bw * bh * 4));
+        tma_load_3d(smem, &tmap, x0, y0, z0, &bar);
+    }
+    const long long t0 = clock64();
+    bool ok = false;
+    while (clock64() - t0 < 400000000LL) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(&bar)), "r"(0u)
+            : "memory");
+        if (done) {
+            ok = true;
+            break;
+        }
+    }
+    if (!ok) {
+        if (threadIdx.x == 0) status[0] = 1;
+        return;
+    }
+    const float *tile = reinterpret_cast<const float *>(smem);
+    for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) out[i] = tile[i];
+}
+
 }  // namespace dcb

@@ -274,7 +274,9 @@ __global__ void __launch_bounds__(kThreads, (RPT >= 4 ? 2 : 3))
             }
             const int bx1 = min(mxx + 1, wmax);
             const int by1 = min(max(mxy + 1, p.yorg), p.ylast);
-            bx0 = mnx;
+            // measured on B200: the box's innermost start coordinate must be a
+            // multiple of 16 bytes, otherwise UTMALDG raises "illegal instruction"
+            bx0 = mnx & ~3;
             by0 = min(max(mny, p.yorg), p.ylast);
             fits = (bx1 - bx0 + 1 <= p.bw) && (by1 - by0 + 1 <= p.bh);
         }

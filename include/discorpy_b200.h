@@ -204,6 +204,14 @@ int dcb_last_plan(int *path, int *box_w, int *box_h, int *grid, int *smem_bytes)
  * of inputs whose result differs from the correctly rounded one. */
 int dcb_selftest_sqrt(size_t n, uint64_t seed, uint64_t *mismatch);
 
+/* TMA probe (diagnostics): loads the (box_w x box_h) box whose first element is
+ * (x0, y0, z0) of the (D, H, W) float32 tensor `src` (row pitch / slice stride
+ * in bytes, multiples of 16) through cp.async.bulk.tensor into shared memory
+ * and copies it to `out` (box_w*box_h floats, device).  *status: 0 = ok,
+ * 1 = the copy never completed.  Out-of-range elements arrive as 0. */
+int dcb_selftest_tma(const float *src, int D, int H, int W, size_t pitch, size_t slice_stride,
+                     int box_w, int box_h, int x0, int y0, int z0, float *out, int *status);
+
 /* Micro-benchmarks used to size the kernels (DESIGN.md "fp64 budget"):
  * which = 0 DFMA chain, 1 f32<->f64 conversions, 2 MUFU.RSQ64H, 3 the radial
  * coordinate evaluation alone (5 terms), 4 FFMA.  Returns giga-ops/s. */
