@@ -10,6 +10,7 @@
 #include <mutex>
 
 #include "remap.cuh"
+#include "remap_image.cuh"
 #include "microbench.cuh"
 
 using namespace dcb;
@@ -257,6 +258,104 @@ static int plan_and_launch(TileKernel kern, int rpt, RemapParams &p, double gmai
     return DCB_OK;
 }
 
+typedef void (*ImageKernel)(const ImageParams, const CUtensorMap);
+
+// Launch planning for the single-image kernel (remap_image.cuh).
+static int plan_and_launch_image(ImageKernel kern, bool wide, ImageParams &p, double gmain,
+                                 double gcross, int path_req, size_t src_pitch_bytes,
+                                 cudaStream_t stream) {
+    DevProps props;
+    int rc = device_props(&props);
+    if (rc != DCB_OK) return rc;
+    p.tiles_x = (p.W + kTileW - 1) / kTileW;
+    const long long tiles_y = (p.nrows + kImgTileH - 1) / kImgTileH;
+    const long long ntiles = (long long)p.tiles_x * tiles_y;
+    if (ntiles > INT_MAX) return fail(DCB_ERR_UNSUPPORTED, "too many tiles (%lld)", ntiles);
+    p.ntiles = (int)ntiles;
+    const int src_rows = p.ylast - p.yorg + 1;
+
+    const bool layout_ok = ((uintptr_t)p.src % 16 == 0) && (src_pitch_bytes % 16 == 0) &&
+                           tma_encoder() != nullptr;
+    if (path_req == DCB_PATH_TMA && !layout_ok)
+        return fail(DCB_ERR_ARG,
+                    "DCB_PATH_TMA needs a 16-byte aligned source with a pitch that is a multiple "
+                    "of 16 bytes (and a driver exporting cuTensorMapEncodeTiled)");
+    bool staged = layout_ok && path_req != DCB_PATH_DIRECT;
+    int bw = 0, bh = 0;
+    if (staged) {
+        if (!(gmain < 64.0) || !(gcross < 64.0)) gmain = gcross = 64.0;
+        const double tw = std::min(kTileW, p.W) - 1, th = std::min(kImgTileH, p.nrows) - 1;
+        // footprint bound + 2 (floor and the +1 tap) + 2 (probe slack) + 3 (16-byte alignment)
+        long long need_w = (long long)std::ceil(gmain * tw + gcross * th) + 8;
+        long long need_h = (long long)std::ceil(gmain * th + gcross * tw) + 5;
+        need_w = std::min<long long>(need_w, (long long)p.W + 3);
+        need_h = std::min<long long>(need_h, src_rows);
+        bw = (int)((need_w + 3) / 4 * 4);
+        bh = (int)need_h;
+        const int max_stage = 24 * 1024;
+        if (bw > 256 || bh > 256 || (long long)bw * bh * 4 > max_stage) {
+            // strong magnification somewhere: stage a modest box, tiles whose
+            // probes do not fit are gathered straight from global memory
+            bw = std::min(256, std::min(kTileW + 16, (p.W + 3) / 4 * 4 + 4));
+            bh = std::min(std::min(kImgTileH + 8, src_rows), max_stage / (bw * 4));
+        }
+        bw = std::max(bw, 4);
+        bh = std::max(bh, 1);
+    }
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (staged) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)p.W, (cuuint64_t)src_rows, 1};
+        const cuuint64_t gstr[2] = {(cuuint64_t)src_pitch_bytes,
+                                    (cuuint64_t)src_pitch_bytes * (cuuint64_t)src_rows};
+        const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        CUresult cr = tma_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)p.src, gdim,
+                                    gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            if (path_req == DCB_PATH_TMA)
+                return fail(DCB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+            staged = false;
+        }
+    }
+    if (!staged) bw = bh = 0;
+    p.bw = bw;
+    p.bh = bh;
+    p.box_bytes = (unsigned)(bw * bh * 4);
+    p.stage_bytes = (p.box_bytes + 127u) / 128u * 128u;
+    const size_t smem = (size_t)(wide ? 3 : 2) * p.stage_bytes + 16 + 2 * sizeof(TileBox);
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute((const void *)kern,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)kern, kThreads, smem));
+    if (occ < 1) return fail(DCB_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
+    const int grid = (int)std::min<long long>(ntiles, (long long)occ * props.sm_count);
+    kern<<<grid, kThreads, smem, stream>>>(p, tmap);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_last_plan = {staged ? DCB_PATH_TMA : DCB_PATH_DIRECT, bw, bh, grid, (int)smem};
+    return DCB_OK;
+}
+
+template <int MAP>
+static ImageKernel pick_image_kernel(int order, int blend, bool *wide) {
+    *wide = false;
+    if (order == 0) return remap_image_kernel<MAP, 0, DCB_BLEND_EXACT>;
+    switch (blend) {
+        case DCB_BLEND_LERP64:
+            *wide = true;
+            return remap_image_kernel<MAP, 1, DCB_BLEND_LERP64>;
+        case DCB_BLEND_LERP32:
+            return remap_image_kernel<MAP, 1, DCB_BLEND_LERP32>;
+        default:
+            *wide = true;
+            return remap_image_kernel<MAP, 1, DCB_BLEND_EXACT>;
+    }
+}
+
 static int check_options(const dcb_options *opt, dcb_options *o) {
     if (opt == nullptr) {
         *o = {1, DCB_BLEND_EXACT, DCB_PATH_AUTO, 0};
@@ -288,7 +387,7 @@ static int check_image_args(const void *src, const void *dst, int H, int W, size
     REQUIRE(src != nullptr && dst != nullptr, "null image pointer");
     REQUIRE(src != dst, "dst must not alias src");
     REQUIRE(H >= 1 && W >= 1, "image must be at least 1x1 (got %dx%d)", H, W);
-    REQUIRE(H < (1 << 24) && W < (1 << 24), "image dimension exceeds 2^24 (fp32-exact bound)");
+    REQUIRE(H < (1 << 23) && W < (1 << 23), "image dimension exceeds 2^23");
     REQUIRE(src_pitch >= (size_t)W * 4 && src_pitch % 4 == 0, "bad source pitch %zu", src_pitch);
     REQUIRE(dst_pitch >= (size_t)W * 4 && dst_pitch % 4 == 0, "bad destination pitch %zu",
             dst_pitch);
@@ -521,6 +620,24 @@ int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, in
     p.ylast = src_row0 + src_rows - 1;
     double gm, gc;
     radial_slopes(*model, W, row0, nrows, &gm, &gc);
+    if (coord_round && D == 1) {
+        ImageParams q;
+        memset(&q, 0, sizeof(q));
+        q.rad = p.rad;
+        q.src = src;
+        q.dst = dst;
+        q.src_pitch = p.src_pitch;
+        q.dst_pitch = p.dst_pitch;
+        q.H = H;
+        q.W = W;
+        q.row0 = row0;
+        q.nrows = nrows;
+        q.yorg = p.yorg;
+        q.ylast = p.ylast;
+        bool wide = false;
+        ImageKernel k = pick_image_kernel<MAP_RADIAL>(o.order, o.blend, &wide);
+        return plan_and_launch_image(k, wide, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
+    }
     if (coord_round) {
         const int rpt = 4;
         return plan_and_launch(pick_kernel<MAP_RADIAL, true, 4>(o.order, o.blend), rpt, p, gm, gc,
@@ -565,8 +682,22 @@ int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W
     p.ylast = H - 1;
     double gm, gc;
     persp_slopes(*model, H, W, &gm, &gc);
-    return plan_and_launch(pick_kernel<MAP_PERSP, true, 4>(o.order, o.blend), 4, p, gm, gc, o.path,
-                           src_pitch, src_pitch * (size_t)H, (cudaStream_t)stream);
+    ImageParams q;
+    memset(&q, 0, sizeof(q));
+    q.per = p.per;
+    q.src = src;
+    q.dst = dst;
+    q.src_pitch = p.src_pitch;
+    q.dst_pitch = p.dst_pitch;
+    q.H = H;
+    q.W = W;
+    q.row0 = 0;
+    q.nrows = H;
+    q.yorg = 0;
+    q.ylast = H - 1;
+    bool wide = false;
+    ImageKernel k = pick_image_kernel<MAP_PERSP>(o.order, o.blend, &wide);
+    return plan_and_launch_image(k, wide, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
 }
 
 int dcb_unwarp_image_backward_perspective_f32(const float *src, float *dst, float *scratch, int H,
