@@ -340,20 +340,39 @@ static int plan_and_launch_image(ImageKernel kern, bool wide, ImageParams &p, do
     return DCB_OK;
 }
 
-template <int MAP>
-static ImageKernel pick_image_kernel(int order, int blend, bool *wide) {
+template <int MAP, int NT>
+static ImageKernel pick_image_kernel_nt(int order, int blend, bool *wide) {
     *wide = false;
-    if (order == 0) return remap_image_kernel<MAP, 0, DCB_BLEND_EXACT>;
+    if (order == 0) return remap_image_kernel<MAP, 0, DCB_BLEND_EXACT, NT>;
     switch (blend) {
         case DCB_BLEND_LERP64:
             *wide = true;
-            return remap_image_kernel<MAP, 1, DCB_BLEND_LERP64>;
+            return remap_image_kernel<MAP, 1, DCB_BLEND_LERP64, NT>;
         case DCB_BLEND_LERP32:
-            return remap_image_kernel<MAP, 1, DCB_BLEND_LERP32>;
+            return remap_image_kernel<MAP, 1, DCB_BLEND_LERP32, NT>;
         default:
             *wide = true;
-            return remap_image_kernel<MAP, 1, DCB_BLEND_EXACT>;
+            return remap_image_kernel<MAP, 1, DCB_BLEND_EXACT, NT>;
     }
+}
+
+// nterms: number of polynomial coefficients (radial map); 1..10 have kernels
+// with the Horner chain unrolled at compile time, the rest use the generic one.
+template <int MAP>
+static ImageKernel pick_image_kernel(int order, int blend, int nterms, bool *wide) {
+    if (MAP == MAP_RADIAL) {
+        switch (nterms) {
+#define DCB_NT(N) \
+    case N:       \
+        return pick_image_kernel_nt<MAP, N>(order, blend, wide);
+            DCB_NT(1) DCB_NT(2) DCB_NT(3) DCB_NT(4) DCB_NT(5) DCB_NT(6) DCB_NT(7) DCB_NT(8)
+            DCB_NT(9) DCB_NT(10)
+#undef DCB_NT
+            default:
+                break;
+        }
+    }
+    return pick_image_kernel_nt<MAP, 0>(order, blend, wide);
 }
 
 static int check_options(const dcb_options *opt, dcb_options *o) {
@@ -635,7 +654,7 @@ int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, in
         q.yorg = p.yorg;
         q.ylast = p.ylast;
         bool wide = false;
-        ImageKernel k = pick_image_kernel<MAP_RADIAL>(o.order, o.blend, &wide);
+        ImageKernel k = pick_image_kernel<MAP_RADIAL>(o.order, o.blend, model->n, &wide);
         return plan_and_launch_image(k, wide, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
     }
     if (coord_round) {
@@ -696,7 +715,7 @@ int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W
     q.yorg = 0;
     q.ylast = H - 1;
     bool wide = false;
-    ImageKernel k = pick_image_kernel<MAP_PERSP>(o.order, o.blend, &wide);
+    ImageKernel k = pick_image_kernel<MAP_PERSP>(o.order, o.blend, 0, &wide);
     return plan_and_launch_image(k, wide, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
 }
 

@@ -53,27 +53,37 @@ struct TileBox {
     int pad;
 };
 
-// floor of a float in [0, 2^23): returns the floor as float and as int without
-// touching the XU pipe.  0x4B000000 is the bit pattern of 2^23.
-__device__ __forceinline__ void floor_pos(float v, float &fl, int &il) {
-    const float t = __fadd_rn(v, 8388608.0f);       // nearest integer, as 2^23 + n
-    float r = __fadd_rn(t, -8388608.0f);
-    int i = __float_as_int(t) - 0x4B000000;
-    if (r > v) {
-        r -= 1.0f;
-        i -= 1;
-    }
-    fl = r;
-    il = i;
+// floor of a float v in [0, 2^23) without the XU pipe: one round-toward-minus-
+// infinity add puts floor(v) in the low mantissa bits of t = 2^23 + floor(v)
+// (0x4B000000 is the bit pattern of 2^23).
+__device__ __forceinline__ float floor_magic(float v) { return __fadd_rd(v, 8388608.0f); }
+
+// clip(round_to_f32(d), 0, vmax) on the integer pipe: non-negative floats order
+// like their bit patterns, negative ones (sign bit set) are negative integers.
+__device__ __forceinline__ float clamp_coord_bits(double d, int vmax_bits) {
+    return __int_as_float(__vimin_s32_relu(__float_as_int(__double2float_rn(d)), vmax_bits));
+}
+
+// sqrt for s > 0 (callers keep s away from 0, see MapEval<MAP_RADIAL>::row)
+__device__ __forceinline__ double dsqrt_nz(double s) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    double g = s * y;
+    double h = 0.5 * y;
+    const double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, s);
+    return fma(d, h, g);
 }
 
 // Per-thread column terms of the map (constant down a tile) and the row
 // evaluation producing clamped fp32 coordinates for 4 pixels.
-template <int MAP>
+template <int MAP, int NT>
 struct MapEval;
 
-template <>
-struct MapEval<MAP_RADIAL> {
+template <int NT>
+struct MapEval<MAP_RADIAL, NT> {
     double xu[kCols], xu2[kCols];
     __device__ __forceinline__ void set_columns(const ImageParams &p, const int (&x)[kCols]) {
 #pragma unroll
@@ -82,24 +92,34 @@ struct MapEval<MAP_RADIAL> {
             xu2[k] = __dmul_rn(xu[k], xu[k]);
         }
     }
-    __device__ __forceinline__ void row(const ImageParams &p, int y, float (&xf)[kCols],
-                                        float (&yf)[kCols]) const {
+    __device__ __forceinline__ void row(const ImageParams &p, int y, int wbits, int hbits,
+                                        float (&xf)[kCols], float (&yf)[kCols]) const {
         const double yu = (double)y - p.rad.yc;
-        const double yu2 = __dmul_rn(yu, yu);
+        double yu2 = __dmul_rn(yu, yu);
+        // r = 0 only at a pixel sitting exactly on the centre.  Keeping s >= 1e-300
+        // there gives r = 1e-150, hence the same F (= a0 after rounding) and the same
+        // coordinates (F * 0), and it leaves every other s bit-identical -- so the
+        // per-pixel zero test of dsqrt_pos is not needed in the hot loop.
+        yu2 = (yu2 < 1e-300) ? 1e-300 : yu2;
         double r[kCols], f[kCols];
 #pragma unroll
-        for (int k = 0; k < kCols; ++k) r[k] = dsqrt_pos(__dadd_rn(xu2[k], yu2));
-        radial_factor<kCols>(p.rad.a, p.rad.n, r, f);
+        for (int k = 0; k < kCols; ++k) r[k] = dsqrt_nz(__dadd_rn(xu2[k], yu2));
+        if (NT > 0) {
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) f[k] = horner<(NT > 0 ? NT : 1)>(p.rad.a, r[k]);
+        } else {
+            radial_factor<kCols>(p.rad.a, p.rad.n, r, f);
+        }
 #pragma unroll
         for (int k = 0; k < kCols; ++k) {
-            xf[k] = clamp_coord<float>(fma(f[k], xu[k], p.rad.xc), p.W - 1);
-            yf[k] = clamp_coord<float>(fma(f[k], yu, p.rad.yc), p.H - 1);
+            xf[k] = clamp_coord_bits(fma(f[k], xu[k], p.rad.xc), wbits);
+            yf[k] = clamp_coord_bits(fma(f[k], yu, p.rad.yc), hbits);
         }
     }
 };
 
-template <>
-struct MapEval<MAP_PERSP> {
+template <int NT>
+struct MapEval<MAP_PERSP, NT> {
     double c1x[kCols], c4x[kCols], c7x[kCols];
     __device__ __forceinline__ void set_columns(const ImageParams &p, const int (&x)[kCols]) {
 #pragma unroll
@@ -110,8 +130,8 @@ struct MapEval<MAP_PERSP> {
             c7x[k] = __dmul_rn(p.per.c[6], xd);
         }
     }
-    __device__ __forceinline__ void row(const ImageParams &p, int y, float (&xf)[kCols],
-                                        float (&yf)[kCols]) const {
+    __device__ __forceinline__ void row(const ImageParams &p, int y, int wbits, int hbits,
+                                        float (&xf)[kCols], float (&yf)[kCols]) const {
         const double yd = (double)y;
         const double c2y = __dmul_rn(p.per.c[1], yd);
         const double c5y = __dmul_rn(p.per.c[4], yd);
@@ -121,8 +141,8 @@ struct MapEval<MAP_PERSP> {
             const double den = __dadd_rn(__dadd_rn(c7x[k], c8y), 1.0);
             const double nx = __dadd_rn(__dadd_rn(c1x[k], c2y), p.per.c[2]);
             const double ny = __dadd_rn(__dadd_rn(c4x[k], c5y), p.per.c[5]);
-            xf[k] = clamp_coord<float>(__ddiv_rn(nx, den), p.W - 1);
-            yf[k] = clamp_coord<float>(__ddiv_rn(ny, den), p.H - 1);
+            xf[k] = clamp_coord_bits(__ddiv_rn(nx, den), wbits);
+            yf[k] = clamp_coord_bits(__ddiv_rn(ny, den), hbits);
         }
     }
 };
@@ -153,7 +173,9 @@ struct ImageKernelTraits {
     static constexpr bool kWide = (ORDER == 1 && BLEND != DCB_BLEND_LERP32);
 };
 
-template <int MAP, int ORDER, int BLEND>
+// NT > 0: number of polynomial terms known at compile time (coefficients become
+// constant-bank operands of the DFMAs); NT == 0: any p.rad.n through a switch.
+template <int MAP, int ORDER, int BLEND, int NT>
 __global__ void __launch_bounds__(kThreads, 3)
     remap_image_kernel(const __grid_constant__ ImageParams p,
                        const __grid_constant__ CUtensorMap tmap) {
@@ -249,8 +271,11 @@ __global__ void __launch_bounds__(kThreads, 3)
             int xs[kCols];
 #pragma unroll
             for (int k = 0; k < kCols; ++k) xs[k] = min(x_base + 32 * k, wmax);  // clamp: edge lanes recompute a valid pixel
-            MapEval<MAP> ev;
+            MapEval<MAP, NT> ev;
             ev.set_columns(p, xs);
+            const int wbits = __float_as_int((float)wmax), hbits = __float_as_int((float)(p.H - 1));
+            // bits(2^23 + n) - magic = n - box origin
+            const int magic_x = 0x4B000000 + box.bx0, magic_y = 0x4B000000 + box.by0;
             // fast-path window: footprint inside the box and strictly inside the image
             const int lim_x = box.use ? min(p.bw - 1, wmax - box.bx0) : 0;
             const int lim_y = box.use ? min(p.bh - 1, p.ylast - box.by0) : 0;
@@ -261,23 +286,26 @@ __global__ void __launch_bounds__(kThreads, 3)
                 const int y = y_base + j;
                 if (y >= y_end) break;  // warp-uniform
                 float xf[kCols], yf[kCols];
-                ev.row(p, y, xf, yf);
-                float x0f[kCols], y0f[kCols];
-                int x0[kCols], y0[kCols];
+                ev.row(p, y, wbits, hbits, xf, yf);
+                float tfx[kCols], tfy[kCols];
+                int ix[kCols], iy[kCols];
                 bool ok = true;
 #pragma unroll
                 for (int k = 0; k < kCols; ++k) {
-                    floor_pos(xf[k], x0f[k], x0[k]);
-                    floor_pos(yf[k], y0f[k], y0[k]);
-                    ok = ok && ((unsigned)(x0[k] - box.bx0) < (unsigned)lim_x) &&
-                         ((unsigned)(y0[k] - box.by0) < (unsigned)lim_y);
+                    tfx[k] = floor_magic(xf[k]);
+                    tfy[k] = floor_magic(yf[k]);
+                    ix[k] = __float_as_int(tfx[k]) - magic_x;  // x0 - bx0
+                    iy[k] = __float_as_int(tfy[k]) - magic_y;  // y0 - by0
+                    ok = ok && ((unsigned)ix[k] < (unsigned)lim_x) &&
+                         ((unsigned)iy[k] < (unsigned)lim_y);
                 }
                 float v[kCols];
                 if (__all_sync(0xffffffffu, ok)) {
 #pragma unroll
                     for (int k = 0; k < kCols; ++k) {
-                        const float tx = xf[k] - x0f[k], ty = yf[k] - y0f[k];  // exact
-                        const int idx = (y0[k] - box.by0) * p.bw + (x0[k] - box.bx0);
+                        const float tx = xf[k] - (tfx[k] - 8388608.0f);  // exact
+                        const float ty = yf[k] - (tfy[k] - 8388608.0f);
+                        const int idx = iy[k] * p.bw + ix[k];
                         if (ORDER == 0) {
                             const int sel = idx + (tx >= 0.5f ? 1 : 0) + (ty >= 0.5f ? p.bw : 0);
                             v[k] = WIDE ? (float)wide[sel] : rawt[sel];
