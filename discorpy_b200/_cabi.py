@@ -171,5 +171,9 @@ def make_persp(list_coef):
     return m
 
 
-def make_options(order=1, blend=BLEND_EXACT, path=PATH_AUTO):
-    return Options(int(order), int(blend), int(path), 0)
+def make_options(order=1, blend=BLEND_EXACT, path=PATH_AUTO, flags=None):
+    """``flags`` is reserved (0); A/B builds of the library (-DDCB_AB) read an
+    experimental kernel variant from it, settable through ``DCB_FLAGS``."""
+    if flags is None:
+        flags = int(os.environ.get("DCB_FLAGS", "0") or 0)
+    return Options(int(order), int(blend), int(path), int(flags))

@@ -261,16 +261,24 @@ static int plan_and_launch(TileKernel kern, int rpt, RemapParams &p, double gmai
 typedef void (*ImageKernel)(const ImageParams, const CUtensorMap);
 
 // Launch planning for the single-image kernel (remap_image.cuh).
-static int plan_and_launch_image(ImageKernel kern, bool wide, ImageParams &p, double gmain,
+struct ImageKernelSel {
+    ImageKernel kern;
+    bool wide;  // samples from the float64 tile (two of them + one raw stage)
+    int th;     // tile height the kernel was instantiated for
+};
+
+static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, double gmain,
                                  double gcross, int path_req, size_t src_pitch_bytes,
                                  cudaStream_t stream) {
     DevProps props;
     int rc = device_props(&props);
     if (rc != DCB_OK) return rc;
-    p.tiles_x = (p.W + kTileW - 1) / kTileW;
-    const long long tiles_y = (p.nrows + kImgTileH - 1) / kImgTileH;
-    const long long ntiles = (long long)p.tiles_x * tiles_y;
+    const int TH = sel.th;
+    const long long tiles_x = (p.W + kTileW - 1) / kTileW;
+    const long long tiles_y = (p.nrows + TH - 1) / TH;
+    const long long ntiles = tiles_x * tiles_y;
     if (ntiles > INT_MAX) return fail(DCB_ERR_UNSUPPORTED, "too many tiles (%lld)", ntiles);
+    p.tiles_y = (int)tiles_y;
     p.ntiles = (int)ntiles;
     const int src_rows = p.ylast - p.yorg + 1;
 
@@ -284,7 +292,7 @@ static int plan_and_launch_image(ImageKernel kern, bool wide, ImageParams &p, do
     int bw = 0, bh = 0;
     if (staged) {
         if (!(gmain < 64.0) || !(gcross < 64.0)) gmain = gcross = 64.0;
-        const double tw = std::min(kTileW, p.W) - 1, th = std::min(kImgTileH, p.nrows) - 1;
+        const double tw = std::min(kTileW, p.W) - 1, th = std::min(TH, p.nrows) - 1;
         // footprint bound + 2 (floor and the +1 tap) + 2 (probe slack) + 3 (16-byte alignment)
         long long need_w = (long long)std::ceil(gmain * tw + gcross * th) + 8;
         long long need_h = (long long)std::ceil(gmain * th + gcross * tw) + 5;
@@ -292,12 +300,12 @@ static int plan_and_launch_image(ImageKernel kern, bool wide, ImageParams &p, do
         need_h = std::min<long long>(need_h, src_rows);
         bw = (int)((need_w + 3) / 4 * 4);
         bh = (int)need_h;
-        const int max_stage = 24 * 1024;
+        const int max_stage = (TH >= 32 ? 24 : 14) * 1024;
         if (bw > 256 || bh > 256 || (long long)bw * bh * 4 > max_stage) {
             // strong magnification somewhere: stage a modest box, tiles whose
             // probes do not fit are gathered straight from global memory
             bw = std::min(256, std::min(kTileW + 16, (p.W + 3) / 4 * 4 + 4));
-            bh = std::min(std::min(kImgTileH + 8, src_rows), max_stage / (bw * 4));
+            bh = std::min(std::min(TH + 8, src_rows), max_stage / (bw * 4));
         }
         bw = std::max(bw, 4);
         bh = std::max(bh, 1);
@@ -325,46 +333,57 @@ static int plan_and_launch_image(ImageKernel kern, bool wide, ImageParams &p, do
     p.bh = bh;
     p.box_bytes = (unsigned)(bw * bh * 4);
     p.stage_bytes = (p.box_bytes + 127u) / 128u * 128u;
-    const size_t smem = (size_t)(wide ? 3 : 2) * p.stage_bytes + 16 + 2 * sizeof(TileBox);
+    const size_t smem = (size_t)(sel.wide ? 5 : 2) * p.stage_bytes + image_tail_bytes();
     if (smem > 48 * 1024)
-        CUDA_TRY(cudaFuncSetAttribute((const void *)kern,
+        CUDA_TRY(cudaFuncSetAttribute((const void *)sel.kern,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)kern, kThreads, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)sel.kern, kThreads,
+                                                           smem));
     if (occ < 1) return fail(DCB_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
     const int grid = (int)std::min<long long>(ntiles, (long long)occ * props.sm_count);
-    kern<<<grid, kThreads, smem, stream>>>(p, tmap);
+    sel.kern<<<grid, kThreads, smem, stream>>>(p, tmap);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     g_last_plan = {staged ? DCB_PATH_TMA : DCB_PATH_DIRECT, bw, bh, grid, (int)smem};
     return DCB_OK;
 }
 
-template <int MAP, int NT>
-static ImageKernel pick_image_kernel_nt(int order, int blend, bool *wide) {
-    *wide = false;
-    if (order == 0) return remap_image_kernel<MAP, 0, DCB_BLEND_EXACT, NT>;
+template <int MAP, int NT, int TH, int MINB>
+static ImageKernelSel pick_image_kernel_nt(int order, int blend) {
+    if (order == 0) return {remap_image_kernel<MAP, 0, DCB_BLEND_EXACT, NT, TH, MINB>, false, TH};
     switch (blend) {
         case DCB_BLEND_LERP64:
-            *wide = true;
-            return remap_image_kernel<MAP, 1, DCB_BLEND_LERP64, NT>;
+            return {remap_image_kernel<MAP, 1, DCB_BLEND_LERP64, NT, TH, MINB>, true, TH};
         case DCB_BLEND_LERP32:
-            return remap_image_kernel<MAP, 1, DCB_BLEND_LERP32, NT>;
+            return {remap_image_kernel<MAP, 1, DCB_BLEND_LERP32, NT, TH, MINB>, false, TH};
         default:
-            *wide = true;
-            return remap_image_kernel<MAP, 1, DCB_BLEND_EXACT, NT>;
+            return {remap_image_kernel<MAP, 1, DCB_BLEND_EXACT, NT, TH, MINB>, true, TH};
     }
 }
+
+constexpr int kImgTileH = 32;     // 128 x 32 output tiles
+constexpr int kImgMinBlocks = 2;  // 128 registers: the per-row loop keeps 4 fp64 chains in flight
 
 // nterms: number of polynomial coefficients (radial map); 1..10 have kernels
 // with the Horner chain unrolled at compile time, the rest use the generic one.
 template <int MAP>
-static ImageKernel pick_image_kernel(int order, int blend, int nterms, bool *wide) {
+static ImageKernelSel pick_image_kernel(int order, int blend, int nterms, int flags) {
+#ifdef DCB_AB
+    // A/B builds only: flags selects an experimental variant of the 5-term radial kernel
+    if (MAP == MAP_RADIAL && nterms == 5 && order == 1 && (flags & 0xf) != 0) {
+        const int v = flags & 0xf;
+        if (v == 1) return pick_image_kernel_nt<MAP, 5, 32, 2>(order, blend);
+        if (v == 2) return pick_image_kernel_nt<MAP, 5, 16, 4>(order, blend);
+        if (v == 3) return pick_image_kernel_nt<MAP, 5, 32, 3>(order, blend);
+    }
+#endif
+    (void)flags;
     if (MAP == MAP_RADIAL) {
         switch (nterms) {
 #define DCB_NT(N) \
     case N:       \
-        return pick_image_kernel_nt<MAP, N>(order, blend, wide);
+        return pick_image_kernel_nt<MAP, N, kImgTileH, kImgMinBlocks>(order, blend);
             DCB_NT(1) DCB_NT(2) DCB_NT(3) DCB_NT(4) DCB_NT(5) DCB_NT(6) DCB_NT(7) DCB_NT(8)
             DCB_NT(9) DCB_NT(10)
 #undef DCB_NT
@@ -372,7 +391,7 @@ static ImageKernel pick_image_kernel(int order, int blend, int nterms, bool *wid
                 break;
         }
     }
-    return pick_image_kernel_nt<MAP, 0>(order, blend, wide);
+    return pick_image_kernel_nt<MAP, 0, kImgTileH, kImgMinBlocks>(order, blend);
 }
 
 static int check_options(const dcb_options *opt, dcb_options *o) {
@@ -653,9 +672,9 @@ int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, in
         q.nrows = nrows;
         q.yorg = p.yorg;
         q.ylast = p.ylast;
-        bool wide = false;
-        ImageKernel k = pick_image_kernel<MAP_RADIAL>(o.order, o.blend, model->n, &wide);
-        return plan_and_launch_image(k, wide, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
+        q.dbg = (o.flags >> 4) & 0xf;
+        const ImageKernelSel k = pick_image_kernel<MAP_RADIAL>(o.order, o.blend, model->n, o.flags);
+        return plan_and_launch_image(k, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
     }
     if (coord_round) {
         const int rpt = 4;
@@ -714,9 +733,8 @@ int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W
     q.nrows = H;
     q.yorg = 0;
     q.ylast = H - 1;
-    bool wide = false;
-    ImageKernel k = pick_image_kernel<MAP_PERSP>(o.order, o.blend, 0, &wide);
-    return plan_and_launch_image(k, wide, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
+    const ImageKernelSel k = pick_image_kernel<MAP_PERSP>(o.order, o.blend, 0, o.flags);
+    return plan_and_launch_image(k, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
 }
 
 int dcb_unwarp_image_backward_perspective_f32(const float *src, float *dst, float *scratch, int H,
@@ -861,9 +879,22 @@ int dcb_selftest_tma(const float *src, int D, int H, int W, size_t pitch, size_t
 
 int dcb_microbench(int which, double *gops) {
     REQUIRE(gops != nullptr, "gops is NULL");
-    REQUIRE(which >= 0 && which <= 5, "which must be 0..5");
+    REQUIRE(which >= 0 && which <= 9, "which must be 0..9");
     double *sink = nullptr;
-    CUDA_TRY(cudaMalloc(&sink, sizeof(double)));
+    CUDA_TRY(cudaMalloc(&sink, 2 * sizeof(double)));
+    if (which >= 6) {  // latency probes: cycles per dependent operation
+        switch (which) {
+            case 6: microbench_latency_kernel<6><<<1, 32>>>(sink); break;
+            case 7: microbench_latency_kernel<7><<<1, 32>>>(sink); break;
+            case 8: microbench_latency_kernel<8><<<1, 32>>>(sink); break;
+            default: microbench_latency_kernel<9><<<1, 32>>>(sink); break;
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaMemcpy(gops, sink, sizeof(double), cudaMemcpyDeviceToHost);
+        cudaFree(sink);
+        if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "microbench: %s", cudaGetErrorString(e));
+        return DCB_OK;
+    }
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));

@@ -45,6 +45,40 @@ __global__ void __launch_bounds__(256) microbench_kernel(double *sink, double se
     if (acc == 123.456) sink[0] = acc;
 }
 
+// which 6..9: dependent-issue latency in cycles of DFMA (6), an F2F f32->f64->f32
+// round trip (7, two conversions), MUFU.RSQ64H (8) and LDS.64 (9): one warp, one
+// dependent chain, clock64 around it.
+template <int WHICH>
+__global__ void microbench_latency_kernel(double *out) {
+    __shared__ double sm[64];
+    sm[threadIdx.x] = 1.0 + threadIdx.x * 1e-3;
+    sm[threadIdx.x + 32] = 0.0;
+    __syncwarp();
+    double d = 1.0 + threadIdx.x * 1e-3;
+    float f = (float)d;
+    int idx = threadIdx.x;
+    const int iters = 4096;
+    const long long t0 = clock64();
+#pragma unroll 16
+    for (int it = 0; it < iters; ++it) {
+        if (WHICH == 6) {
+            d = fma(d, 0.999999, 1e-7);
+        } else if (WHICH == 7) {
+            double w;
+            asm volatile("cvt.f64.f32 %0, %1;" : "=d"(w) : "f"(f));
+            asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f) : "d"(w));
+        } else if (WHICH == 8) {
+            asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(d) : "d"(d));
+        } else {
+            d = sm[idx];
+            idx = (int)__double2hiint(d) & 31;  // stays in range; value-dependent address
+        }
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[0] = (double)(t1 - t0) / iters;
+    if (d + f + idx == 123.456) out[1] = d;
+}
+
 // which == 3: the radial coordinate evaluation alone, 5 terms, 4 px per step
 __global__ void __launch_bounds__(256) microbench_coords_kernel(double *sink, double xc, double yc) {
     const double a[5] = {1.0, -2e-5, 6e-8, -1e-10, 5e-14};

@@ -1,37 +1,38 @@
-// remap_image.cuh -- the single-image backward-remap kernel (sm_100a), v2.
+// remap_image.cuh -- the single-image backward-remap kernel (sm_100a), v4.
 //
 // Serves a1 `unwarp_image_backward` (postprocessing.py:111-148) and a4
 // `correct_perspective_image` (:444-492) for one float32 image, or a range of
 // its output rows.  Numerics are those of remap.cuh (same helpers); what is
-// new is the schedule, shaped by what the first ncu capture showed
-// (profiles/r1): the v1 kernel executed 131 thread-instructions per pixel, 14
-// of them on the 16-lane/clk XU pipe (f32<->f64 conversions, F2I, MUFU), kept
-// 16 coordinates live across the TMA wait (128 registers, spills) and exposed
-// the whole TMA latency in every tile.
+// different is the schedule, shaped by the ncu captures under profiles/r1:
+// at the 70 %-of-HBM target an SM must retire 2 output pixels per clock, i.e.
+// it has 64 issue slots, 32 fp64 slots and 8 XU (conversion / MUFU) slots per
+// pixel -- the kernel is bound by instruction issue, not by memory, so every
+// design decision below removes instructions from the per-pixel loop.
 //
 //   * persistent CTAs walk output tiles of 128 x 32 pixels; while tile i is
 //     sampled, warp 0 estimates the source box of tile i+1 from 9 probe
 //     points and issues its TMA load, so the copy is hidden behind a full
 //     tile of fp64 work;
 //   * the box lands as float32 and is widened ONCE per source pixel into a
-//     float64 tile in shared memory (1.2 conversions per output pixel instead
-//     of 4, the conversions being the scarcest issue slots);
+//     float64 tile in shared memory (1.3 conversions per output pixel instead
+//     of 4 -- the 16-lane XU pipe is the scarcest resource);
 //   * coordinates are evaluated four pixels at a time right before they are
 //     used -- nothing stays live across a barrier except the per-thread column
 //     terms;
-//   * floor() of the clamped fp32 coordinate uses the 2^23 trick on the FP32
+//   * floor() of the fp32 coordinate uses a round-down add of 2^23 on the FP32
 //     pipe instead of F2I/I2F on the XU pipe;
-//   * every pixel checks that its 2x2 footprint lies inside the staged box and
-//     strictly inside the image; the (rare) pixels that do not -- box estimate
-//     too small, last row/column, clipped regions -- take the generic global
-//     gather of remap.cuh, so correctness never depends on the estimate.
+//   * the fast path does not clip: a coordinate outside the image fails the
+//     "2x2 footprint inside the staged box and strictly inside the image"
+//     test that every pixel makes anyway, and the (rare) rows that fail it --
+//     box estimate too small, last row/column, clipped regions -- take the
+//     generic clip + global gather of remap.cuh, so correctness never depends
+//     on the estimate;
+//   * the four fp64 bilinear weights come from one multiplication and four
+//     exact subtractions (see blend_exact below).
 #pragma once
 #include "remap.cuh"
 
 namespace dcb {
-
-constexpr int kImgTileH = 32;
-constexpr int kImgRowsPerWarp = kImgTileH / kWarps;  // 4
 
 struct ImageParams {
     const float *src;
@@ -40,9 +41,10 @@ struct ImageParams {
     int H, W;
     int row0, nrows;   // output rows produced by this launch
     int yorg, ylast;   // image rows held by src (src points at row yorg)
-    int tiles_x, ntiles;
+    int tiles_y, ntiles;  // tiles are numbered column-major: t = txi * tiles_y + tyi
     int bw, bh;        // staged box, bw % 4 == 0; bw == 0 => never stage
     unsigned box_bytes, stage_bytes;
+    int dbg, pad;      // A/B builds (-DDCB_AB): ablation switches, 0 otherwise
     RadialDev rad;
     PerspDev per;
 };
@@ -55,16 +57,17 @@ struct TileBox {
 
 // floor of a float v in [0, 2^23) without the XU pipe: one round-toward-minus-
 // infinity add puts floor(v) in the low mantissa bits of t = 2^23 + floor(v)
-// (0x4B000000 is the bit pattern of 2^23).
+// (0x4B000000 is the bit pattern of 2^23).  For v < 0 the bits of t fall below
+// 0x4B000000, for v >= 2^23 or NaN far above: both fail the box test.
 __device__ __forceinline__ float floor_magic(float v) { return __fadd_rd(v, 8388608.0f); }
 
-// clip(round_to_f32(d), 0, vmax) on the integer pipe: non-negative floats order
-// like their bit patterns, negative ones (sign bit set) are negative integers.
-__device__ __forceinline__ float clamp_coord_bits(double d, int vmax_bits) {
-    return __int_as_float(__vimin_s32_relu(__float_as_int(__double2float_rn(d)), vmax_bits));
+// clip(x, 0, vmax) of an fp32 coordinate on the integer pipe: non-negative
+// floats order like their bit patterns, negative ones are negative integers.
+__device__ __forceinline__ float clamp_bits(float v, int vmax_bits) {
+    return __int_as_float(__vimin_s32_relu(__float_as_int(v), vmax_bits));
 }
 
-// sqrt for s > 0 (callers keep s away from 0, see MapEval<MAP_RADIAL>::row)
+// sqrt for s > 0 (callers keep s away from 0, see MapEval<MAP_RADIAL>)
 __device__ __forceinline__ double dsqrt_nz(double s) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
@@ -77,8 +80,31 @@ __device__ __forceinline__ double dsqrt_nz(double s) {
     return fma(d, h, g);
 }
 
+// SciPy's order-1 value  sum_ij  rn(rn(m_ij * wy_i) * wx_j)  accumulated first
+// tap to last (DCB_BLEND_EXACT), with fewer operations but the same roundings:
+//   * wy_i and wx_j are fp32 fractions widened to fp64 (<= 24 significant
+//     bits), so m * wy (24 + 24 bits) is exact and rn(rn(m wy) wx) equals
+//     rn(m * W_ij) with W_ij = wy_i * wx_j, itself exact (<= 48 bits);
+//   * W11 = ty*tx is one multiplication; W10 = ty - W11, W01 = tx - W11 and
+//     W00 = (1 - ty) - W01 are exact because their results are the <= 48-bit
+//     products ty(1-tx), (1-ty)tx, (1-ty)(1-tx).
+// 5 + 4 + 3 = 12 fp64 operations instead of 13, every one of them rounding
+// exactly where SciPy's does.
+__device__ __forceinline__ float blend_exact(double a, double b, double c, double d, double tx,
+                                             double ty) {
+    const double w11 = __dmul_rn(ty, tx);
+    const double w10 = __dsub_rn(ty, w11);
+    const double w01 = __dsub_rn(tx, w11);
+    const double w00 = __dsub_rn(__dsub_rn(1.0, ty), w01);
+    double s = __dmul_rn(a, w00);
+    s = __dadd_rn(s, __dmul_rn(b, w01));
+    s = __dadd_rn(s, __dmul_rn(c, w10));
+    s = __dadd_rn(s, __dmul_rn(d, w11));
+    return __double2float_rn(s);
+}
+
 // Per-thread column terms of the map (constant down a tile) and the row
-// evaluation producing clamped fp32 coordinates for 4 pixels.
+// evaluation producing UNCLIPPED fp32 coordinates for 4 pixels.
 template <int MAP, int NT>
 struct MapEval;
 
@@ -89,18 +115,20 @@ struct MapEval<MAP_RADIAL, NT> {
 #pragma unroll
         for (int k = 0; k < kCols; ++k) {
             xu[k] = (double)x[k] - p.rad.xc;
-            xu2[k] = __dmul_rn(xu[k], xu[k]);
+            const double q = __dmul_rn(xu[k], xu[k]);
+            // r = 0 only at a pixel sitting exactly on the centre.  Keeping
+            // xu^2 >= 1e-300 gives r = 1e-150 there, hence the same F (= a0 after
+            // rounding) and the same coordinates (F * 0 + centre), and it leaves
+            // every other s = xu^2 + yu^2 bit-identical (1e-300 is far below half
+            // an ulp of any non-zero yu^2) -- so the hot loop needs no zero test.
+            xu2[k] = (q < 1e-300) ? 1e-300 : q;
         }
     }
-    __device__ __forceinline__ void row(const ImageParams &p, int y, int wbits, int hbits,
-                                        float (&xf)[kCols], float (&yf)[kCols]) const {
-        const double yu = (double)y - p.rad.yc;
-        double yu2 = __dmul_rn(yu, yu);
-        // r = 0 only at a pixel sitting exactly on the centre.  Keeping s >= 1e-300
-        // there gives r = 1e-150, hence the same F (= a0 after rounding) and the same
-        // coordinates (F * 0), and it leaves every other s bit-identical -- so the
-        // per-pixel zero test of dsqrt_pos is not needed in the hot loop.
-        yu2 = (yu2 < 1e-300) ? 1e-300 : yu2;
+    // yd: the row as a double
+    __device__ __forceinline__ void row(const ImageParams &p, double yd, float (&xf)[kCols],
+                                        float (&yf)[kCols]) const {
+        const double yu = __dsub_rn(yd, p.rad.yc);
+        const double yu2 = __dmul_rn(yu, yu);
         double r[kCols], f[kCols];
 #pragma unroll
         for (int k = 0; k < kCols; ++k) r[k] = dsqrt_nz(__dadd_rn(xu2[k], yu2));
@@ -112,8 +140,8 @@ struct MapEval<MAP_RADIAL, NT> {
         }
 #pragma unroll
         for (int k = 0; k < kCols; ++k) {
-            xf[k] = clamp_coord_bits(fma(f[k], xu[k], p.rad.xc), wbits);
-            yf[k] = clamp_coord_bits(fma(f[k], yu, p.rad.yc), hbits);
+            xf[k] = __double2float_rn(fma(f[k], xu[k], p.rad.xc));
+            yf[k] = __double2float_rn(fma(f[k], yu, p.rad.yc));
         }
     }
 };
@@ -130,9 +158,8 @@ struct MapEval<MAP_PERSP, NT> {
             c7x[k] = __dmul_rn(p.per.c[6], xd);
         }
     }
-    __device__ __forceinline__ void row(const ImageParams &p, int y, int wbits, int hbits,
-                                        float (&xf)[kCols], float (&yf)[kCols]) const {
-        const double yd = (double)y;
+    __device__ __forceinline__ void row(const ImageParams &p, double yd, float (&xf)[kCols],
+                                        float (&yf)[kCols]) const {
         const double c2y = __dmul_rn(p.per.c[1], yd);
         const double c5y = __dmul_rn(p.per.c[4], yd);
         const double c8y = __dmul_rn(p.per.c[7], yd);
@@ -141,8 +168,8 @@ struct MapEval<MAP_PERSP, NT> {
             const double den = __dadd_rn(__dadd_rn(c7x[k], c8y), 1.0);
             const double nx = __dadd_rn(__dadd_rn(c1x[k], c2y), p.per.c[2]);
             const double ny = __dadd_rn(__dadd_rn(c4x[k], c5y), p.per.c[5]);
-            xf[k] = clamp_coord_bits(__ddiv_rn(nx, den), wbits);
-            yf[k] = clamp_coord_bits(__ddiv_rn(ny, den), hbits);
+            xf[k] = __double2float_rn(__ddiv_rn(nx, den));
+            yf[k] = __double2float_rn(__ddiv_rn(ny, den));
         }
     }
 };
@@ -173,21 +200,28 @@ struct ImageKernelTraits {
     static constexpr bool kWide = (ORDER == 1 && BLEND != DCB_BLEND_LERP32);
 };
 
+constexpr int kBoxRing = 16;  // tile boxes kept in shared memory (placed 8 tiles ahead)
+
+// Shared-memory layout (host side must agree, see image_smem_bytes in api.cu):
+//   WIDE : [raw][wide 0][wide 1][tail]      raw = stage_bytes, wide = 2 * stage_bytes
+//   !WIDE: [raw 0][raw 1][tail]
+//   tail : uint64_t full[2]; TileBox boxes[kBoxRing]
+__host__ __device__ constexpr size_t image_tail_bytes() { return 16 + kBoxRing * sizeof(TileBox); }
+
 // NT > 0: number of polynomial terms known at compile time (coefficients become
 // constant-bank operands of the DFMAs); NT == 0: any p.rad.n through a switch.
-template <int MAP, int ORDER, int BLEND, int NT>
-__global__ void __launch_bounds__(kThreads, 3)
+// TH: tile height (16 or 32 rows); MINB: resident CTAs per SM the register
+// allocation is held to.
+template <int MAP, int ORDER, int BLEND, int NT, int TH, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
     remap_image_kernel(const __grid_constant__ ImageParams p,
                        const __grid_constant__ CUtensorMap tmap) {
     constexpr bool WIDE = ImageKernelTraits<ORDER, BLEND>::kWide;
+    constexpr int RPW = TH / kWarps;  // rows per warp and tile
     extern __shared__ __align__(128) unsigned char smem[];
-    // layout: [raw stage 0][raw stage 1 (only !WIDE)][wide tile (only WIDE)][mbar][TileBox x2]
-    float *raw0 = reinterpret_cast<float *>(smem);
-    unsigned char *after_raw = smem + (WIDE ? 1 : 2) * (size_t)p.stage_bytes;
-    double *wide = reinterpret_cast<double *>(after_raw);
-    unsigned char *tail = after_raw + (WIDE ? 2 * (size_t)p.stage_bytes : 0);
-    uint64_t *full = reinterpret_cast<uint64_t *>(tail);           // [2]
-    TileBox *boxes = reinterpret_cast<TileBox *>(tail + 16);       // [2]
+    unsigned char *tail = smem + (WIDE ? 5 : 2) * (size_t)p.stage_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(tail);       // [2]
+    TileBox *boxes = reinterpret_cast<TileBox *>(tail + 16);   // [kBoxRing]
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -195,20 +229,24 @@ __global__ void __launch_bounds__(kThreads, 3)
     const int wmax = p.W - 1;
     const int y_end = p.row0 + p.nrows;
 
+    // this CTA's tiles: a contiguous range of the column-major tile order, so
+    // consecutive tiles sit below each other and share their column terms
+    const int t0 = (int)((long long)blockIdx.x * p.ntiles / gridDim.x);
+    const int n = (int)((long long)(blockIdx.x + 1) * p.ntiles / gridDim.x) - t0;
+
     if (threadIdx.x == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         fence_mbar_init();
         if (staged) tma_prefetch_desc(&tmap);
     }
-    __syncthreads();
 
-    // ---- warp 0: place the box of tile t and start its copy -------------------
-    auto prefetch_tile = [&](int t, int slot, uint32_t fill_index) {
-        // all 32 lanes of warp 0 execute this
-        const int txi = t % p.tiles_x, tyi = t / p.tiles_x;
-        const int x_lo = txi * kTileW, y_lo = p.row0 + tyi * kImgTileH;
-        const int x_hi = min(x_lo + kTileW - 1, wmax), y_hi = min(y_lo + kImgTileH - 1, y_end - 1);
+    // ---- one warp: place the source box of local tile k from 9 probe points ----
+    auto place_box = [&](int k) {
+        const int t = t0 + k;
+        const int txi = t / p.tiles_y, tyi = t - txi * p.tiles_y;
+        const int x_lo = txi * kTileW, y_lo = p.row0 + tyi * TH;
+        const int x_hi = min(x_lo + kTileW - 1, wmax), y_hi = min(y_lo + TH - 1, y_end - 1);
         const int q = lane % 9;
         const int px = x_lo + ((x_hi - x_lo) * (q % 3)) / 2;
         const int py = y_lo + ((y_hi - y_lo) * (q / 3)) / 2;
@@ -222,71 +260,126 @@ __global__ void __launch_bounds__(kThreads, 3)
         const int bx0 = max(mnx - 1, 0) & ~3;
         const int by0 = min(max(mny - 1, p.yorg), p.ylast);
         const bool use = staged && (mxx + 2 - bx0 < p.bw) && (mxy + 2 - by0 < p.bh);
-        if (lane == 0) {
-            boxes[slot].bx0 = bx0;
-            boxes[slot].by0 = by0;
-            boxes[slot].use = use ? 1 : 0;
-            if (use) {
-                const int st = WIDE ? 0 : (int)(fill_index & 1u);
-                mbar_expect_tx(&full[st], p.box_bytes);
-                tma_load_3d(smem + (size_t)st * p.stage_bytes, &tmap, bx0, by0 - p.yorg, 0,
-                            &full[st]);
-            }
+        if (lane == 0) boxes[k % kBoxRing] = TileBox{bx0, by0, use ? 1 : 0, 0};
+    };
+    // ---- one thread: start the copy of local tile k's box into a raw stage ------
+    auto issue_tma = [&](int k, int stage) {
+        const TileBox b = boxes[k % kBoxRing];
+        if (b.use) {
+            mbar_expect_tx(&full[stage], p.box_bytes);
+            tma_load_3d(smem + (size_t)stage * p.stage_bytes, &tmap, b.bx0, b.by0 - p.yorg, 0,
+                        &full[stage]);
+        }
+    };
+    // ---- all threads: float32 box in the raw stage -> float64 tile `buf` --------
+    auto widen = [&](int buf) {
+        const float4 *src4 = reinterpret_cast<const float4 *>(smem);
+        double2 *dst2 = reinterpret_cast<double2 *>(smem + (size_t)(1 + 2 * buf) * p.stage_bytes);
+        const int n4 = (p.bw * p.bh) >> 2;  // bw % 4 == 0
+        int i = threadIdx.x;
+        for (; i + kThreads < n4; i += 2 * kThreads) {
+            const float4 u = src4[i], v = src4[i + kThreads];
+            dst2[2 * i] = make_double2((double)u.x, (double)u.y);
+            dst2[2 * i + 1] = make_double2((double)u.z, (double)u.w);
+            dst2[2 * (i + kThreads)] = make_double2((double)v.x, (double)v.y);
+            dst2[2 * (i + kThreads) + 1] = make_double2((double)v.z, (double)v.w);
+        }
+        if (i < n4) {
+            const float4 u = src4[i];
+            dst2[2 * i] = make_double2((double)u.x, (double)u.y);
+            dst2[2 * i + 1] = make_double2((double)u.z, (double)u.w);
         }
     };
 
-    uint32_t nfill = 0;  // TMA copies consumed so far (CTA-uniform)
-    int t = blockIdx.x;
-    if (t < p.ntiles && warp == 0) prefetch_tile(t, 0, 0);
-    __syncthreads();
-
-    for (int it = 0; t < p.ntiles; ++it, t += gridDim.x) {
-        const TileBox box = boxes[it & 1];
-        const int st = WIDE ? 0 : (int)(nfill & 1u);
-        if (box.use) {
-            // WIDE: one barrier, phase flips per fill.  !WIDE: two barriers used alternately.
-            const uint32_t parity = WIDE ? (nfill & 1u) : ((nfill >> 1) & 1u);
-            mbar_wait(&full[st], parity);
-            if (WIDE) {
-                // widen the landed box once: float32 -> float64 (exact)
-                const float2 *src2 = reinterpret_cast<const float2 *>(raw0);
-                double2 *dst2 = reinterpret_cast<double2 *>(wide);
-                const int n2 = (p.bw * p.bh) >> 1;
-                for (int i = threadIdx.x; i < n2; i += kThreads) {
-                    const float2 v = src2[i];
-                    dst2[i] = make_double2((double)v.x, (double)v.y);
-                }
+    uint32_t cnt0 = 0, cnt1 = 0;  // fills consumed per raw stage (CTA-uniform)
+    for (int k = warp; k < min(n, 8); k += kWarps) place_box(k);
+    __syncthreads();  // mbarriers initialised, boxes 0..7 placed
+    if (WIDE) {
+        if (n > 0) {
+            if (threadIdx.x == 0) issue_tma(0, 0);
+            if (boxes[0].use) {
+                mbar_wait(&full[0], cnt0 & 1u);
+                ++cnt0;
+                widen(0);
             }
         }
-        __syncthreads();  // wide tile complete, raw stage reusable, boxes[(it+1)&1] free
-        const int t_next = t + gridDim.x;
-        const uint32_t fills_after = nfill + (box.use ? 1u : 0u);
-        if (warp == 0 && t_next < p.ntiles) prefetch_tile(t_next, (it + 1) & 1, fills_after);
+        __syncthreads();
+        if (threadIdx.x == 0 && n > 1) issue_tma(1, 0);
+    } else {
+        if (threadIdx.x == 0) {
+            if (n > 0) issue_tma(0, 0);
+            if (n > 1) issue_tma(1, 1);
+        }
+#ifdef DCB_AB
+        if ((p.dbg & 4) && n > 0 && boxes[0].use) mbar_wait(&full[0], 0);
+#endif
+    }
 
-        // ---- sample tile t ---------------------------------------------------------
-        {
-            const int txi = t % p.tiles_x, tyi = t / p.tiles_x;
-            const int x_base = txi * kTileW + lane;
-            const int y_base = p.row0 + tyi * kImgTileH + warp * kImgRowsPerWarp;
-            int xs[kCols];
+    int txi = t0 / p.tiles_y, tyi = t0 - txi * p.tiles_y;
+    MapEval<MAP, NT> ev;
+    {
+        int xs[kCols];
 #pragma unroll
-            for (int k = 0; k < kCols; ++k) xs[k] = min(x_base + 32 * k, wmax);  // clamp: edge lanes recompute a valid pixel
-            MapEval<MAP, NT> ev;
-            ev.set_columns(p, xs);
-            const int wbits = __float_as_int((float)wmax), hbits = __float_as_int((float)(p.H - 1));
+        for (int k = 0; k < kCols; ++k) xs[k] = min(txi * kTileW + lane + 32 * k, wmax);
+        ev.set_columns(p, xs);
+    }
+
+    for (int i = 0; i < n; ++i) {
+#ifdef DCB_AB
+        const bool compute_only = (p.dbg & 4) != 0;  // ablation: tile 0's box serves every tile
+        const TileBox box = boxes[compute_only ? 0 : i % kBoxRing];
+#else
+        constexpr bool compute_only = false;
+        const TileBox box = boxes[i % kBoxRing];
+#endif
+        if (!WIDE && box.use && !compute_only) {  // raw stage i & 1 holds this tile's box
+            if (i & 1) {
+                mbar_wait(&full[1], cnt1 & 1u);
+                ++cnt1;
+            } else {
+                mbar_wait(&full[0], cnt0 & 1u);
+                ++cnt0;
+            }
+        }
+        // ---- sample tile i ---------------------------------------------------------
+        {
+            const int x_base = txi * kTileW + lane;
+            const int y_base = p.row0 + tyi * TH + warp * RPW;
+            const int nrow = min(RPW, y_end - y_base);  // warp-uniform, may be <= 0
             // bits(2^23 + n) - magic = n - box origin
             const int magic_x = 0x4B000000 + box.bx0, magic_y = 0x4B000000 + box.by0;
             // fast-path window: footprint inside the box and strictly inside the image
             const int lim_x = box.use ? min(p.bw - 1, wmax - box.bx0) : 0;
             const int lim_y = box.use ? min(p.bh - 1, p.ylast - box.by0) : 0;
-            const float *rawt = reinterpret_cast<const float *>(smem + (size_t)st * p.stage_bytes);
-            const GlobalFetch gfetch{p.src - (long long)p.yorg * p.src_pitch, p.src_pitch};
+            const int bw = p.bw;
+            const int sb = compute_only ? 0 : (i & 1);
+            const float *rawt =
+                reinterpret_cast<const float *>(smem + (size_t)sb * p.stage_bytes);
+            const double *widet = reinterpret_cast<const double *>(
+                smem + (size_t)(1 + 2 * sb) * p.stage_bytes);
+            const bool full_w = (txi * kTileW + kTileW - 1 <= wmax);  // CTA-uniform
+            float *orow = p.dst + (long long)(y_base - p.row0) * p.dst_pitch + x_base;
+            double yd = (double)y_base;
 #pragma unroll 1
-            for (int j = 0; j < kImgRowsPerWarp; ++j) {
-                const int y = y_base + j;
-                if (y >= y_end) break;  // warp-uniform
+            for (int j = 0; j < nrow; ++j, yd += 1.0, orow += p.dst_pitch) {
                 float xf[kCols], yf[kCols];
-                ev.row(p, y, wbits, hbits, xf, yf);
+#ifdef DCB_AB
+                if (p.dbg & 2) {  // ablation: no fp64 coordinate evaluation
+#pragma unroll
+                    for (int k = 0; k < kCols; ++k) {
+                        xf[k] = (float)(box.bx0 + 2 + lane + 32 * k) + 0.3f;
+                        yf[k] = (float)(box.by0 + 2 + warp * RPW + j) + 0.6f;
+                    }
+                } else
+#endif
+                    ev.row(p, yd, xf, yf);
+#ifdef DCB_AB
+                if (p.dbg & 1) {  // ablation: no sampling
+#pragma unroll
+                    for (int k = 0; k < kCols; ++k) __stcs(orow + 32 * k, xf[k] + yf[k]);
+                    continue;
+                }
+#endif
                 float tfx[kCols], tfy[kCols];
                 int ix[kCols], iy[kCols];
                 bool ok = true;
@@ -296,6 +389,12 @@ __global__ void __launch_bounds__(kThreads, 3)
                     tfy[k] = floor_magic(yf[k]);
                     ix[k] = __float_as_int(tfx[k]) - magic_x;  // x0 - bx0
                     iy[k] = __float_as_int(tfy[k]) - magic_y;  // y0 - by0
+#ifdef DCB_AB
+                    if (compute_only) {
+                        ix[k] = 2 + lane + 32 * k;
+                        iy[k] = 2 + warp * RPW + j;
+                    }
+#endif
                     ok = ok && ((unsigned)ix[k] < (unsigned)lim_x) &&
                          ((unsigned)iy[k] < (unsigned)lim_y);
                 }
@@ -305,48 +404,80 @@ __global__ void __launch_bounds__(kThreads, 3)
                     for (int k = 0; k < kCols; ++k) {
                         const float tx = xf[k] - (tfx[k] - 8388608.0f);  // exact
                         const float ty = yf[k] - (tfy[k] - 8388608.0f);
-                        const int idx = iy[k] * p.bw + ix[k];
+                        const int idx = iy[k] * bw + ix[k];
                         if (ORDER == 0) {
-                            const int sel = idx + (tx >= 0.5f ? 1 : 0) + (ty >= 0.5f ? p.bw : 0);
-                            v[k] = WIDE ? (float)wide[sel] : rawt[sel];
+                            const int sel = idx + (tx >= 0.5f ? 1 : 0) + (ty >= 0.5f ? bw : 0);
+                            v[k] = rawt[sel];
                         } else if (!WIDE) {
-                            const float a = rawt[idx], b = rawt[idx + 1];
-                            const float c = rawt[idx + p.bw], d = rawt[idx + p.bw + 1];
+                            const float *q = rawt + idx;
+                            const float a = q[0], b = q[1];
+                            const float c = q[bw], d = q[bw + 1];
                             const float top = fmaf(b - a, tx, a);
                             const float bot = fmaf(d - c, tx, c);
                             v[k] = fmaf(bot - top, ty, top);
                         } else {
-                            const double a = wide[idx], b = wide[idx + 1];
-                            const double c = wide[idx + p.bw], d = wide[idx + p.bw + 1];
+                            const double *q = widet + idx;
+                            const double a = q[0], b = q[1];
+                            const double c = q[bw], d = q[bw + 1];
                             const double wx1 = (double)tx, wy1 = (double)ty;
                             if (BLEND == DCB_BLEND_LERP64) {
                                 const double top = fma(b - a, wx1, a);
                                 const double bot = fma(d - c, wx1, c);
                                 v[k] = (float)fma(bot - top, wy1, top);
                             } else {
-                                const double wx0 = __dsub_rn(1.0, wx1), wy0 = __dsub_rn(1.0, wy1);
-                                double s = __dmul_rn(__dmul_rn(a, wy0), wx0);
-                                s = __dadd_rn(s, __dmul_rn(__dmul_rn(b, wy0), wx1));
-                                s = __dadd_rn(s, __dmul_rn(__dmul_rn(c, wy1), wx0));
-                                s = __dadd_rn(s, __dmul_rn(__dmul_rn(d, wy1), wx1));
-                                v[k] = __double2float_rn(s);
+                                v[k] = blend_exact(a, b, c, d, wx1, wy1);
                             }
                         }
                     }
                 } else {
+                    const GlobalFetch gfetch{p.src - (long long)p.yorg * p.src_pitch, p.src_pitch};
+                    const int wbits = __float_as_int((float)wmax);
+                    const int hbits = __float_as_int((float)(p.H - 1));
 #pragma unroll
                     for (int k = 0; k < kCols; ++k)
-                        v[k] = sample_px<ORDER, BLEND, float>(gfetch, xf[k], yf[k], wmax, p.yorg,
-                                                              p.ylast);
+                        v[k] = sample_px<ORDER, BLEND, float>(gfetch, clamp_bits(xf[k], wbits),
+                                                              clamp_bits(yf[k], hbits), wmax,
+                                                              p.yorg, p.ylast);
                 }
-                float *orow = p.dst + (long long)(y - p.row0) * p.dst_pitch;
+                if (full_w) {
 #pragma unroll
-                for (int k = 0; k < kCols; ++k)
-                    if (x_base + 32 * k <= wmax) __stcs(orow + x_base + 32 * k, v[k]);
+                    for (int k = 0; k < kCols; ++k) __stcs(orow + 32 * k, v[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kCols; ++k)
+                        if (x_base + 32 * k <= wmax) __stcs(orow + 32 * k, v[k]);
+                }
             }
         }
-        nfill = fills_after;
-        __syncthreads();  // everyone is done with the wide tile / raw stage and boxes[it&1]
+        // ---- while slower warps still sample: widen tile i+1, place boxes ahead ------
+        if (compute_only) {
+            if (++tyi == p.tiles_y) {
+                tyi = 0;
+                ++txi;
+                int xs[kCols];
+#pragma unroll
+                for (int k = 0; k < kCols; ++k) xs[k] = min(txi * kTileW + lane + 32 * k, wmax);
+                ev.set_columns(p, xs);
+            }
+            continue;
+        }
+        if (WIDE && i + 1 < n && boxes[(i + 1) % kBoxRing].use) {
+            mbar_wait(&full[0], cnt0 & 1u);
+            ++cnt0;
+            widen((i + 1) & 1);
+        }
+        if ((i & 7) == 0 && i + 8 + warp < n) place_box(i + 8 + warp);
+        __syncthreads();  // tile i sampled by all, wide[(i+1)&1] complete, raw stage free
+        if (threadIdx.x == 0 && i + 2 < n) issue_tma(i + 2, WIDE ? 0 : (i & 1));
+        // next tile of the column-major order
+        if (++tyi == p.tiles_y) {
+            tyi = 0;
+            ++txi;
+            int xs[kCols];
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) xs[k] = min(txi * kTileW + lane + 32 * k, wmax);
+            ev.set_columns(p, xs);
+        }
     }
 }
 

@@ -214,7 +214,9 @@ int dcb_selftest_tma(const float *src, int D, int H, int W, size_t pitch, size_t
 
 /* Micro-benchmarks used to size the kernels (DESIGN.md "fp64 budget"):
  * which = 0 DFMA chain, 1 f32<->f64 conversions, 2 MUFU.RSQ64H, 3 the radial
- * coordinate evaluation alone (5 terms), 4 FFMA.  Returns giga-ops/s. */
+ * coordinate evaluation alone (5 terms), 4 FFMA, 5 DFMA + 2 conversions:
+ * giga-ops/s.  which = 6 DFMA, 7 f32->f64->f32 round trip, 8 MUFU.RSQ64H,
+ * 9 LDS.64: dependent-issue latency in clock cycles (one warp, one chain). */
 int dcb_microbench(int which, double *gops);
 
 #ifdef __cplusplus
