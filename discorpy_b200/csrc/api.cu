@@ -11,6 +11,7 @@
 
 #include "remap.cuh"
 #include "remap_image.cuh"
+#include "remap_stack.cuh"
 #include "microbench.cuh"
 
 using namespace dcb;
@@ -145,23 +146,16 @@ static void persp_slopes(const dcb_persp &m, int H, int W, double *gmain, double
     *gcross = gc;
 }
 
-struct Plan {
-    RemapParams p;
-    CUtensorMap tmap;
-    int grid;
-    size_t smem;
-    int path;
-};
+typedef void (*StackKernel)(const RemapParams, const CUtensorMap);
 
-typedef void (*TileKernel)(const RemapParams, const CUtensorMap);
-
-static int plan_and_launch(TileKernel kern, int rpt, RemapParams &p, double gmain, double gcross,
-                           int path_req, size_t src_pitch_bytes, size_t src_slice_bytes,
-                           cudaStream_t stream) {
+// Launch planning for the Z-stack kernel (remap_stack.cuh).
+static int plan_and_launch_stack(StackKernel kern, RemapParams &p, double gmain, double gcross,
+                                 int path_req, size_t src_pitch_bytes, size_t src_slice_bytes,
+                                 cudaStream_t stream) {
     DevProps props;
     int rc = device_props(&props);
     if (rc != DCB_OK) return rc;
-    const int TH = kWarps * rpt;
+    const int TH = kStkTileH;
     p.tiles_x = (p.W + kTileW - 1) / kTileW;
     p.tiles_y = (p.nrows + TH - 1) / TH;
     const long long tiles_xy = (long long)p.tiles_x * p.tiles_y;
@@ -176,6 +170,7 @@ static int plan_and_launch(TileKernel kern, int rpt, RemapParams &p, double gmai
     bool staged = layout_ok && path_req != DCB_PATH_DIRECT;
 
     // --- staged box: bound of the tile's source footprint --------------------
+    const int src_rows = p.ylast - p.yorg + 1;
     int bw = 0, bh = 0, nstage = 0;
     if (staged) {
         if (!(gmain < 64.0) || !(gcross < 64.0)) gmain = gcross = 64.0;  // NaN / absurd
@@ -184,47 +179,49 @@ static int plan_and_launch(TileKernel kern, int rpt, RemapParams &p, double gmai
         long long need_w = (long long)std::ceil(gmain * tw + gcross * th) + 3 + 3;
         long long need_h = (long long)std::ceil(gmain * th + gcross * tw) + 3;
         need_w = std::min<long long>(need_w, (long long)p.W + 3);
-        need_h = std::min<long long>(need_h, p.ylast - p.yorg + 1);
+        need_h = std::min<long long>(need_h, src_rows);
         bw = (int)((need_w + 3) / 4 * 4);
         bh = (int)need_h;
-        // budget: at most ~24 KB per stage so that >= 4 CTAs fit per SM with a 2-deep ring
         const int max_stage = 24 * 1024;
         if (bw > 256 || bh > 256 || (long long)bw * bh * 4 > max_stage) {
             // footprint bound too large (strong magnification somewhere): stage a
             // modest box; tiles that do not fit fall back to direct gathers.
             bw = std::min(256, (std::min(kTileW + 16, (p.W + 3) / 4 * 4 + 4)));
-            bh = std::min(std::min(TH + 8, p.ylast - p.yorg + 1), max_stage / (bw * 4));
+            bh = std::min(std::min(TH + 8, src_rows), max_stage / (bw * 4));
         }
-        nstage = (p.D > 1) ? 3 : 1;
+        bw = std::max(bw, 4);
+        bh = std::max(bh, 1);
+        // ring depth: as many slices in flight as ~96 KB per CTA hold (two CTAs per SM)
+        const long long stage = ((long long)bw * bh * 4 + 127) / 128 * 128;
+        nstage = (int)std::max<long long>(2, std::min<long long>(kStkMaxStages, (96 * 1024) / stage));
     }
     p.bw = bw;
     p.bh = bh;
     p.nstage = nstage;
     p.box_bytes = (unsigned)(bw * bh * 4);
     p.stage_bytes = (p.box_bytes + 127u) / 128u * 128u;
-    size_t smem = (size_t)nstage * p.stage_bytes + kMaxStages * sizeof(uint64_t) +
-                  2 * 4 * kWarps * sizeof(int);
+    const size_t tail = 2 * kStkMaxStages * sizeof(uint64_t) + 2 * 4 * kWarps * sizeof(int);
+    size_t smem = (size_t)nstage * p.stage_bytes + tail;
 
-    // --- z chunking: enough CTAs to fill the machine, long enough chunks to
-    //     amortise the fp64 coordinate evaluation --------------------------------
+    // --- z chunking: enough items to balance the machine, long enough chunks to
+    //     amortise the per-tile geometry ----------------------------------------------
     int zchunk = 1;
     if (p.D > 1) {
-        const long long want_ctas = (long long)props.sm_count * 16;
-        long long nchunks = std::max<long long>(1, (want_ctas + tiles_xy - 1) / tiles_xy);
+        const long long want_items = (long long)props.sm_count * 2 * 8;
+        long long nchunks = std::max<long long>(1, (want_items + tiles_xy - 1) / tiles_xy);
         nchunks = std::min<long long>(nchunks, p.D);
         zchunk = (int)((p.D + nchunks - 1) / nchunks);
         zchunk = std::min(zchunk, 64);
     }
     p.zchunk = zchunk;
     const long long nzc = (p.D + zchunk - 1) / zchunk;
-    const long long ntiles = tiles_xy * nzc;
-    if (ntiles > INT_MAX) return fail(DCB_ERR_UNSUPPORTED, "too many tiles (%lld)", ntiles);
-    p.ntiles = (int)ntiles;
+    const long long nitems = tiles_xy * nzc;
+    if (nitems > INT_MAX) return fail(DCB_ERR_UNSUPPORTED, "too many work items (%lld)", nitems);
+    p.ntiles = (int)nitems;
 
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (staged) {
-        const int src_rows = p.ylast - p.yorg + 1;
         const cuuint64_t gdim[3] = {(cuuint64_t)p.W, (cuuint64_t)src_rows, (cuuint64_t)p.D};
         const cuuint64_t gstr[2] = {(cuuint64_t)src_pitch_bytes,
                                     (cuuint64_t)(p.D > 1 ? src_slice_bytes
@@ -240,7 +237,7 @@ static int plan_and_launch(TileKernel kern, int rpt, RemapParams &p, double gmai
                 return fail(DCB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
             staged = false;
             p.nstage = 0;
-            smem = kMaxStages * sizeof(uint64_t) + 2 * 4 * kWarps * sizeof(int);
+            smem = tail;
         }
     }
     if (smem > 48 * 1024)
@@ -249,7 +246,7 @@ static int plan_and_launch(TileKernel kern, int rpt, RemapParams &p, double gmai
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)kern, kThreads, smem));
     if (occ < 1) return fail(DCB_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
-    const int grid = (int)std::min<long long>(ntiles, (long long)occ * props.sm_count);
+    const int grid = (int)std::min<long long>(nitems, (long long)occ * props.sm_count);
 
     kern<<<grid, kThreads, smem, stream>>>(p, tmap);
     CUDA_TRY(cudaGetLastError());
@@ -407,16 +404,16 @@ static int check_options(const dcb_options *opt, dcb_options *o) {
     return DCB_OK;
 }
 
-template <int MAP, bool ROUND32, int RPT>
-static TileKernel pick_kernel(int order, int blend) {
-    if (order == 0) return remap_tile_kernel<MAP, 0, DCB_BLEND_EXACT, ROUND32, RPT>;
+template <bool ROUND32>
+static StackKernel pick_stack_kernel(int order, int blend) {
+    if (order == 0) return remap_stack_kernel<0, DCB_BLEND_EXACT, ROUND32>;
     switch (blend) {
         case DCB_BLEND_LERP64:
-            return remap_tile_kernel<MAP, 1, DCB_BLEND_LERP64, ROUND32, RPT>;
+            return remap_stack_kernel<1, DCB_BLEND_LERP64, ROUND32>;
         case DCB_BLEND_LERP32:
-            return remap_tile_kernel<MAP, 1, DCB_BLEND_LERP32, ROUND32, RPT>;
+            return remap_stack_kernel<1, DCB_BLEND_LERP32, ROUND32>;
         default:
-            return remap_tile_kernel<MAP, 1, DCB_BLEND_EXACT, ROUND32, RPT>;
+            return remap_stack_kernel<1, DCB_BLEND_EXACT, ROUND32>;
     }
 }
 
@@ -635,6 +632,9 @@ int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, in
     REQUIRE(D == 1 || (dst_slice_stride >= dst_pitch * (size_t)nrows && dst_slice_stride % 4 == 0),
             "bad destination slice stride %zu", dst_slice_stride);
     REQUIRE(coord_round == 0 || coord_round == 1, "coord_round must be 0 or 1");
+    REQUIRE((unsigned long long)(src_pitch / 4) * (unsigned long long)src_rows < (1ull << 31),
+            "source window of %d rows x %zu bytes exceeds 2^31 elements per slice", src_rows,
+            src_pitch);
     if (!coord_round) {
         REQUIRE(o.order == 1, "float64-coordinate (slice) sampling is order 1 only");
         if (o.blend == DCB_BLEND_LERP32) o.blend = DCB_BLEND_LERP64;
@@ -676,13 +676,11 @@ int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, in
         const ImageKernelSel k = pick_image_kernel<MAP_RADIAL>(o.order, o.blend, model->n, o.flags);
         return plan_and_launch_image(k, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
     }
-    if (coord_round) {
-        const int rpt = 4;
-        return plan_and_launch(pick_kernel<MAP_RADIAL, true, 4>(o.order, o.blend), rpt, p, gm, gc,
-                               o.path, src_pitch, src_slice_stride, (cudaStream_t)stream);
-    }
-    return plan_and_launch(pick_kernel<MAP_RADIAL, false, 1>(1, o.blend), 1, p, gm, gc, o.path,
-                           src_pitch, src_slice_stride, (cudaStream_t)stream);
+    if (coord_round)
+        return plan_and_launch_stack(pick_stack_kernel<true>(o.order, o.blend), p, gm, gc, o.path,
+                                     src_pitch, src_slice_stride, (cudaStream_t)stream);
+    return plan_and_launch_stack(pick_stack_kernel<false>(1, o.blend), p, gm, gc, o.path, src_pitch,
+                                 src_slice_stride, (cudaStream_t)stream);
 }
 
 int dcb_unwarp_image_backward_f32(const float *src, float *dst, int H, int W, size_t src_pitch,

@@ -1,27 +1,11 @@
-// remap.cuh -- the backward-remap kernels of libdiscorpy_b200 (sm_100a).
-//
-// One kernel template serves every entry of the hot path:
-//   a1 unwarp_image_backward          MAP_RADIAL, ROUND32, D = 1
-//   a2 unwarp_slice_backward          MAP_RADIAL, !ROUND32 (fp64 coordinates), nrows = 1
-//   a3 unwarp_chunk_slices_backward   MAP_RADIAL, ROUND32, rows start..stop, D slices
-//   a4 correct_perspective_image      MAP_PERSP,  ROUND32, D = 1
-// It restates, per output pixel, discorpy/post/postprocessing.py:138-147 /
-// :214-228 / :302-312 / :448-457 plus the order-0/1 arithmetic of
-// scipy.ndimage.map_coordinates -- see DESIGN.md "Numerics" for the exact
-// operation order that is kept and why.
-//
-// Work decomposition (B200-first, nothing like it in the reference):
-//   * a CTA of 256 threads owns an output tile of 128 x (8*RPT) pixels for a
-//     chunk of Z slices; lane l of warp w owns columns x0+l+32k (k<4) of rows
-//     w*RPT..w*RPT+RPT-1, so every global store is one full 128-byte line.
-//   * the fp64 coordinate evaluation happens once per tile and stays in
-//     registers for all slices of the chunk.
-//   * the tile's source bounding box is reduced with redux.sync + one smem
-//     exchange; if it fits the staged box, one elected thread issues a 3-D
-//     TMA load (cp.async.bulk.tensor) per slice into an mbarrier-guarded
-//     shared-memory ring and the four taps are read from shared memory;
-//     otherwise (strong magnification, e.g. BASELINE config 1) that tile
-//     gathers straight from global memory through the read-only path.
+// remap.cuh -- shared pieces of the backward-remap kernels of libdiscorpy_b200
+// (sm_100a): parameter blocks, tap fetchers, the per-pixel order-0/1 arithmetic
+// of scipy.ndimage.map_coordinates for pre-clipped coordinates (used by the
+// direct-gather paths), the caller-supplied-coordinates kernel and the
+// synthetic input generator.  The tiled kernels live in remap_image.cuh (one
+// image: a1, a4 of SURVEY.md section 8a) and remap_stack.cuh (Z-stacks: a2, a3).
+// Numerics restate discorpy/post/postprocessing.py:138-147 / :214-228 /
+// :302-312 / :448-457 -- see DESIGN.md "Numerics".
 #pragma once
 #include <type_traits>
 #include <limits.h>
@@ -34,7 +18,6 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kCols = 4;            // columns per thread
 constexpr int kTileW = 32 * kCols;  // 128 output pixels per tile row
-constexpr int kMaxStages = 4;
 
 enum { MAP_RADIAL = 0, MAP_PERSP = 1 };
 
@@ -142,213 +125,6 @@ __device__ __forceinline__ float clamp_coord<float>(double v, int vmax) {
 template <>
 __device__ __forceinline__ double clamp_coord<double>(double v, int vmax) {
     return fmin(fmax(v, 0.0), (double)vmax);
-}
-
-// ---------------------------------------------------------------------------
-// the tile kernel
-// ---------------------------------------------------------------------------
-template <int MAP, int ORDER, int BLEND, bool ROUND32, int RPT>
-__global__ void __launch_bounds__(kThreads, (RPT >= 4 ? 2 : 3))
-    remap_tile_kernel(const __grid_constant__ RemapParams p,
-                      const __grid_constant__ CUtensorMap tmap) {
-    using CT = typename std::conditional<ROUND32, float, double>::type;
-    constexpr int TH = kWarps * RPT;
-
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)p.nstage * p.stage_bytes);
-    int *red = reinterpret_cast<int *>(full + kMaxStages);  // [2][4][kWarps]
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const bool staged = p.nstage > 0;
-    if (staged && threadIdx.x == 0) {
-        for (int s = 0; s < p.nstage; ++s) mbar_init(&full[s], 1);
-        fence_mbar_init();
-        tma_prefetch_desc(&tmap);
-    }
-    __syncthreads();
-
-    uint32_t fills = 0;  // slices that went through the ring so far (CTA-uniform)
-    int tile_par = 0;
-    const int wmax = p.W - 1;
-    const int y_end = p.row0 + p.nrows;
-
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, tile_par ^= 1) {
-        const int txi = t % p.tiles_x;
-        const int rest = t / p.tiles_x;
-        const int tyi = rest % p.tiles_y;
-        const int zci = rest / p.tiles_y;
-        const int x_base = txi * kTileW + lane;
-        const int y_base = p.row0 + tyi * TH + warp * RPT;
-        const int z0 = zci * p.zchunk;
-        const int nz = min(p.zchunk, p.D - z0);
-
-        // ---- coordinates: fp64, once per tile --------------------------------
-        CT cx[RPT][kCols], cy[RPT][kCols];
-        if (MAP == MAP_RADIAL) {
-            double xu[kCols], xu2[kCols];
-#pragma unroll
-            for (int k = 0; k < kCols; ++k) {
-                xu[k] = (double)(x_base + 32 * k) - p.rad.xc;  // :138
-                xu2[k] = __dmul_rn(xu[k], xu[k]);
-            }
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                const double yu = (double)(y_base + j) - p.rad.yc;  // :139
-                const double yu2 = __dmul_rn(yu, yu);
-                double r[kCols], f[kCols];
-#pragma unroll
-                for (int k = 0; k < kCols; ++k) r[k] = dsqrt_pos(__dadd_rn(xu2[k], yu2));  // :141
-                radial_factor<kCols>(p.rad.a, p.rad.n, r, f);  // :142-143
-#pragma unroll
-                for (int k = 0; k < kCols; ++k) {  // :144-145
-                    cx[j][k] = clamp_coord<CT>(fma(f[k], xu[k], p.rad.xc), wmax);
-                    cy[j][k] = clamp_coord<CT>(fma(f[k], yu, p.rad.yc), p.H - 1);
-                }
-            }
-        } else {
-            // projective map, postprocessing.py:450-457, same operation order
-            double c1x[kCols], c4x[kCols], c7x[kCols];
-#pragma unroll
-            for (int k = 0; k < kCols; ++k) {
-                const double x = (double)(x_base + 32 * k);
-                c1x[k] = __dmul_rn(p.per.c[0], x);
-                c4x[k] = __dmul_rn(p.per.c[3], x);
-                c7x[k] = __dmul_rn(p.per.c[6], x);
-            }
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                const double y = (double)(y_base + j);
-                const double c2y = __dmul_rn(p.per.c[1], y);
-                const double c5y = __dmul_rn(p.per.c[4], y);
-                const double c8y = __dmul_rn(p.per.c[7], y);
-#pragma unroll
-                for (int k = 0; k < kCols; ++k) {
-                    const double den = __dadd_rn(__dadd_rn(c7x[k], c8y), 1.0);
-                    const double nx = __dadd_rn(__dadd_rn(c1x[k], c2y), p.per.c[2]);
-                    const double ny = __dadd_rn(__dadd_rn(c4x[k], c5y), p.per.c[5]);
-                    cx[j][k] = clamp_coord<CT>(__ddiv_rn(nx, den), wmax);
-                    cy[j][k] = clamp_coord<CT>(__ddiv_rn(ny, den), p.H - 1);
-                }
-            }
-        }
-
-        // ---- source bounding box of the tile ---------------------------------
-        bool fits = false;
-        int bx0 = 0, by0 = 0;
-        if (staged) {
-            CT fmnx = (CT)3.0e9, fmny = (CT)3.0e9, fmxx = (CT)-1, fmxy = (CT)-1;
-#pragma unroll
-            for (int j = 0; j < RPT; ++j)
-#pragma unroll
-                for (int k = 0; k < kCols; ++k) {
-                    const bool valid = (x_base + 32 * k < p.W) && (y_base + j < y_end);
-                    if (valid) {
-                        fmnx = cx[j][k] < fmnx ? cx[j][k] : fmnx;
-                        fmxx = cx[j][k] > fmxx ? cx[j][k] : fmxx;
-                        fmny = cy[j][k] < fmny ? cy[j][k] : fmny;
-                        fmxy = cy[j][k] > fmxy ? cy[j][k] : fmxy;
-                    }
-                }
-            // cvt.rzi saturates: 3e9 -> INT_MAX, -1 -> -1
-            int mnx = __reduce_min_sync(0xffffffffu, (int)fmnx);
-            int mny = __reduce_min_sync(0xffffffffu, (int)fmny);
-            int mxx = __reduce_max_sync(0xffffffffu, (int)fmxx);
-            int mxy = __reduce_max_sync(0xffffffffu, (int)fmxy);
-            int *rd = red + tile_par * 4 * kWarps;
-            if (lane == 0) {
-                rd[0 * kWarps + warp] = mnx;
-                rd[1 * kWarps + warp] = mny;
-                rd[2 * kWarps + warp] = mxx;
-                rd[3 * kWarps + warp] = mxy;
-            }
-            __syncthreads();
-            mnx = mny = INT_MAX;
-            mxx = mxy = -1;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                mnx = min(mnx, rd[0 * kWarps + w]);
-                mny = min(mny, rd[1 * kWarps + w]);
-                mxx = max(mxx, rd[2 * kWarps + w]);
-                mxy = max(mxy, rd[3 * kWarps + w]);
-            }
-            const int bx1 = min(mxx + 1, wmax);
-            const int by1 = min(max(mxy + 1, p.yorg), p.ylast);
-            // measured on B200: the box's innermost start coordinate must be a
-            // multiple of 16 bytes, otherwise UTMALDG raises "illegal instruction"
-            bx0 = mnx & ~3;
-            by0 = min(max(mny, p.yorg), p.ylast);
-            fits = (bx1 - bx0 + 1 <= p.bw) && (by1 - by0 + 1 <= p.bh);
-        }
-
-        if (fits && threadIdx.x == 0) {
-            const int npre = min(nz, p.nstage);
-            for (int s = 0; s < npre; ++s) {
-                const uint32_t st = (fills + s) % p.nstage;
-                mbar_expect_tx(&full[st], p.box_bytes);
-                tma_load_3d(smem + (size_t)st * p.stage_bytes, &tmap, bx0, by0 - p.yorg, z0 + s,
-                            &full[st]);
-            }
-        }
-
-        // ---- slices of the chunk ----------------------------------------------
-        for (int iz = 0; iz < nz; ++iz) {
-            const int z = z0 + iz;
-            float *out = p.dst + (long long)z * p.dst_slice;
-            if (fits) {
-                const uint32_t st = fills % p.nstage;
-                mbar_wait(&full[st], (fills / p.nstage) & 1u);
-                SmemFetch fetch{reinterpret_cast<const float *>(smem + (size_t)st * p.stage_bytes),
-                                p.bw, -(by0 * p.bw + bx0)};
-#pragma unroll
-                for (int j = 0; j < RPT; ++j) {
-                    const int y = y_base + j;
-                    if (y < y_end) {
-                        float *orow = out + (long long)(y - p.row0) * p.dst_pitch;
-                        float v[kCols];
-#pragma unroll
-                        for (int k = 0; k < kCols; ++k)
-                            v[k] = (x_base + 32 * k < p.W)
-                                       ? sample_px<ORDER, BLEND, CT>(fetch, cx[j][k], cy[j][k], wmax,
-                                                                     p.yorg, p.ylast)
-                                       : 0.0f;
-#pragma unroll
-                        for (int k = 0; k < kCols; ++k)
-                            if (x_base + 32 * k < p.W) __stcs(orow + x_base + 32 * k, v[k]);
-                    }
-                }
-                ++fills;
-                if (iz + p.nstage < nz) {  // CTA-uniform: refill the stage just drained
-                    __syncthreads();
-                    if (threadIdx.x == 0) {
-                        mbar_expect_tx(&full[st], p.box_bytes);
-                        tma_load_3d(smem + (size_t)st * p.stage_bytes, &tmap, bx0, by0 - p.yorg,
-                                    z + p.nstage, &full[st]);
-                    }
-                }
-            } else {
-                GlobalFetch fetch{p.src + (long long)z * p.src_slice - (long long)p.yorg * p.src_pitch,
-                                  p.src_pitch};
-#pragma unroll
-                for (int j = 0; j < RPT; ++j) {
-                    const int y = y_base + j;
-                    if (y < y_end) {
-                        float *orow = out + (long long)(y - p.row0) * p.dst_pitch;
-                        float v[kCols];
-#pragma unroll
-                        for (int k = 0; k < kCols; ++k)
-                            v[k] = (x_base + 32 * k < p.W)
-                                       ? sample_px<ORDER, BLEND, CT>(fetch, cx[j][k], cy[j][k], wmax,
-                                                                     p.yorg, p.ylast)
-                                       : 0.0f;
-#pragma unroll
-                        for (int k = 0; k < kCols; ++k)
-                            if (x_base + 32 * k < p.W) __stcs(orow + x_base + 32 * k, v[k]);
-                    }
-                }
-            }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------
