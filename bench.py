@@ -14,10 +14,15 @@ Step   : one pass of the hot path over one batch of IMAGES_PER_STEP distinct
          every launch reads its source from HBM.
 value  : device-timed, inputs already resident in HBM.
 e2e    : the same metric through the public Python API
-         (discorpy_b200.post.postprocessing.unwarp_image_backward) with host
-         buffers: per image a 64 MiB host->device copy from pinned memory, the
-         kernel, and a 64 MiB device->host copy of the result, all inside the
-         timed region.
+         (discorpy_b200.post.postprocessing.unwarp_image_backward -> C ABI
+         dcb_unwarp_image_backward_host_f32) with host buffers: per image a
+         64 MiB host->device copy from pinned memory, the kernel, and a 64 MiB
+         device->host copy of the result, all inside the timed region (the
+         library pipelines the three in row bands).
+extras : secondary device-timed figures that explain the headline: the other
+         blend modes of the single-image kernel and the Z-stack kernel on the
+         same 4096^2 geometry (geometry evaluated once per tile and reused for
+         every slice -- the path unwarp_chunk_slices_backward takes).
 --impl reference : the reference's own CPU code path (NumPy float64
          coordinate temporaries + scipy.ndimage.map_coordinates, restated in
          oracle/oracle_np.py because /root/reference does not travel to the GPU
@@ -314,6 +319,58 @@ def run_gpu_arm(args, rank, local_rank, world):
     clocks = sampler.stop() if sampler else None
     barrier()
 
+    # ---- secondary device-timed figures (explain the headline, do not replace it) ----
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        def time_images(blend, order=1, reps=2):
+            o = _cabi.make_options(order, blend, post.config["path"])
+            def once():
+                for s_, d_ in zip(srcs, dsts):
+                    _cabi.check(fn(ctypes.c_void_p(s_.ptr), ctypes.c_void_p(d_.ptr), H, W, s_.pitch,
+                                   d_.pitch, ctypes.byref(model), ctypes.byref(o), sh))
+            once()
+            a, b = dcb.Event(), dcb.Event()
+            a.record(stream)
+            for _ in range(reps):
+                once()
+            b.record(stream)
+            b.sync()
+            return a.elapsed_ms(b) * 1e3 / (reps * nimg)        # us per image
+        extras["single_image_kernel_us"] = {
+            "exact": time_images(dcb.BLEND_EXACT), "lerp64": time_images(dcb.BLEND_LERP64),
+            "lerp32": time_images(dcb.BLEND_LERP32), "order0": time_images(dcb.BLEND_EXACT, 0)}
+        # the same 4096^2 geometry as a Z-stack of slices sharing the model (a3, the path
+        # unwarp_chunk_slices_backward takes): geometry evaluated once per tile
+        depth = args.stack_depth
+        stack = dcb.DeviceArray((depth, H, W)).fill_synthetic(seed=2)
+        sout = dcb.DeviceArray((depth, H, W))
+        sfn = _cabi.load().dcb_unwarp_stack_backward_f32
+        stack_us = {}
+        for name, blend, order in (("exact", dcb.BLEND_EXACT, 1), ("lerp32", dcb.BLEND_LERP32, 1),
+                                   ("order0", dcb.BLEND_EXACT, 0)):
+            o = _cabi.make_options(order, blend, post.config["path"])
+            def once():
+                _cabi.check(sfn(ctypes.c_void_p(stack.ptr), ctypes.c_void_p(sout.ptr), depth, H, W, 0,
+                                H, stack.pitch, stack.slice_stride, sout.pitch, sout.slice_stride, 0,
+                                H, 1, ctypes.byref(model), ctypes.byref(o), sh))
+            once()
+            a, b = dcb.Event(), dcb.Event()
+            a.record(stream)
+            for _ in range(3):
+                once()
+            b.record(stream)
+            b.sync()
+            stack_us[name] = a.elapsed_ms(b) * 1e3 / (3 * depth)  # us per 4096^2 slice
+        extras["stack_kernel_us_per_slice"] = stack_us
+        extras["stack_depth"] = depth
+        peak_, _ = measured_peak()
+        extras["roofline_frac"] = {
+            "single_image": {k: ALGO_BYTES_PER_PX * H * W / (v * 1e-6) / 1e9 / peak_
+                             for k, v in extras["single_image_kernel_us"].items()},
+            "stack": {k: ALGO_BYTES_PER_PX * H * W / (v * 1e-6) / 1e9 / peak_
+                      for k, v in stack_us.items()}}
+        del stack, sout
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -343,10 +400,14 @@ def run_gpu_arm(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
-                     "peak_kind": peak_kind, "kernel": "remap_tile_kernel<RADIAL,order1>",
+                     "traffic_source": TRAFFIC_SOURCE,
+                     "peak_kind": peak_kind,
+                     "kernel": "remap_image_kernel<RADIAL, order 1, blend %s, 5 terms>" % args.blend,
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * H * W,
                      "kernel_us": kernel_s * 1e6},
     }
+    if extras:
+        line["extras"] = extras
     if world == 1 and not args.no_cpu_baseline:
         ref = CpuReference()
         ref.run_once()
@@ -369,7 +430,10 @@ def run_gpu_arm(args, rank, local_rank, world):
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant
 # kernel, from the committed `ncu --set full` capture (profiles/); None until
 # a capture exists for the current kernel.
-TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_BYTES_PER_LAUNCH = 69375488 + 18262528
+TRAFFIC_SOURCE = ("profiles/r1/ncu_summary_v5.txt: dram__bytes_read.sum 69.4 MB + "
+                  "dram__bytes_write.sum 18.3 MB of one launch (most of the 64 MiB output is "
+                  "still dirty in the 126 MB L2 when the profiled launch ends)")
 
 
 def main():
@@ -384,6 +448,9 @@ def main():
     ap.add_argument("--e2e-images-per-step", type=int, default=E2E_IMAGES_PER_STEP)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary figures (blend variants, Z-stack kernel)")
+    ap.add_argument("--stack-depth", type=int, default=32)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

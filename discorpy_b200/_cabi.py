@@ -85,6 +85,9 @@ SIGNATURES = {
     "dcb_unwarp_image_backward_f32": [_vp, _vp, _i, _i, _sz, _sz,
                                       ctypes.POINTER(Radial),
                                       ctypes.POINTER(Options), _vp],
+    "dcb_unwarp_image_backward_host_f32": [_vp, _vp, _i, _i, _sz, _sz,
+                                           ctypes.POINTER(Radial),
+                                           ctypes.POINTER(Options), _i],
     "dcb_unwarp_stack_backward_f32": [_vp, _vp, _i, _i, _i, _i, _i, _sz, _sz,
                                       _sz, _sz, _i, _i, _i,
                                       ctypes.POINTER(Radial),

@@ -691,6 +691,159 @@ int dcb_unwarp_image_backward_f32(const float *src, float *dst, int H, int W, si
                                          stream);
 }
 
+// ---- host-buffer entry: banded upload / compute / download pipeline -------------
+namespace {
+
+constexpr int kMaxBands = 32;
+
+struct HostPipe {
+    cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+    cudaEvent_t ev_up[kMaxBands], ev_run[kMaxBands], ev_free = nullptr;
+    void *dsrc = nullptr, *ddst = nullptr;
+    size_t src_cap = 0, dst_cap = 0;
+    int device = -1;
+    bool ok = false;
+};
+thread_local HostPipe g_pipe;
+
+int pipe_prepare(size_t src_bytes, size_t dst_bytes) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    HostPipe &hp = g_pipe;
+    if (hp.ok && hp.device != dev) {  // the thread moved to another GPU: start over
+        cudaFree(hp.dsrc);
+        cudaFree(hp.ddst);
+        hp = HostPipe();
+    }
+    if (!hp.ok) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp.up, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp.run, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp.down, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxBands; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&hp.ev_up[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&hp.ev_run[i], cudaEventDisableTiming));
+        }
+        hp.device = dev;
+        hp.ok = true;
+    }
+    if (hp.src_cap < src_bytes) {
+        if (hp.dsrc) CUDA_TRY(cudaFree(hp.dsrc));
+        hp.dsrc = nullptr;
+        hp.src_cap = 0;
+        CUDA_TRY(cudaMalloc(&hp.dsrc, src_bytes));
+        hp.src_cap = src_bytes;
+    }
+    if (hp.dst_cap < dst_bytes) {
+        if (hp.ddst) CUDA_TRY(cudaFree(hp.ddst));
+        hp.ddst = nullptr;
+        hp.dst_cap = 0;
+        CUDA_TRY(cudaMalloc(&hp.ddst, dst_bytes));
+        hp.dst_cap = dst_bytes;
+    }
+    return DCB_OK;
+}
+
+// Conservative range of source rows that output rows [r0, r1) of the radial map
+// can sample: interval product of F over the radii the band reaches and yu over
+// the band, padded for the sampling step of F and for the bilinear footprint.
+void radial_row_range(const dcb_radial &m, int H, int W, int r0, int r1, int *lo, int *hi) {
+    const double ya = (double)r0 - m.yc, yb = (double)(r1 - 1) - m.yc;
+    const double xa = 0.0 - m.xc, xb = (double)(W - 1) - m.xc;
+    auto nearest0 = [](double a, double b) { return (a <= 0.0 && b >= 0.0) ? 0.0 : std::min(std::fabs(a), std::fabs(b)); };
+    const double ymin = nearest0(ya, yb), xmin = nearest0(xa, xb);
+    const double ymax = std::max(std::fabs(ya), std::fabs(yb)), xmax = std::max(std::fabs(xa), std::fabs(xb));
+    const double rmin = std::sqrt(xmin * xmin + ymin * ymin), rmax = std::sqrt(xmax * xmax + ymax * ymax);
+    const int S = 2048;
+    const double step = (rmax - rmin) / S;
+    double fmin = 1e300, fmax = -1e300, dmax = 0.0;
+    for (int i = 0; i <= S; ++i) {
+        const double r = rmin + step * i;
+        double f = 0.0, fp = 0.0;
+        for (int k = m.n - 1; k >= 0; --k) {
+            fp = fp * r + f;
+            f = f * r + m.a[k];
+        }
+        fmin = std::min(fmin, f);
+        fmax = std::max(fmax, f);
+        dmax = std::max(dmax, std::fabs(fp));
+    }
+    const double pad = 2.0 * dmax * step;  // F between two samples (generous for a polynomial)
+    fmin -= pad;
+    fmax += pad;
+    const double c[4] = {fmin * ya, fmin * yb, fmax * ya, fmax * yb};
+    double vmin = c[0], vmax = c[0];
+    for (double v : c) {
+        vmin = std::min(vmin, v);
+        vmax = std::max(vmax, v);
+    }
+    vmin += m.yc;
+    vmax += m.yc;
+    if (!(vmin == vmin) || !(vmax == vmax) || !(std::fabs(vmin) < 1e15) || !(std::fabs(vmax) < 1e15)) {
+        *lo = 0;
+        *hi = H - 1;
+        return;
+    }
+    *lo = (int)std::max(0.0, std::min((double)(H - 1), std::floor(vmin) - 1.0));
+    *hi = (int)std::max(0.0, std::min((double)(H - 1), std::ceil(vmax) + 2.0));
+}
+
+}  // namespace
+
+int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, int H, int W,
+                                       size_t src_pitch_host, size_t dst_pitch_host,
+                                       const dcb_radial *model, const dcb_options *opt, int nbands) {
+    REQUIRE(src_host != nullptr && dst_host != nullptr, "null image pointer");
+    REQUIRE(model != nullptr, "radial model is NULL");
+    REQUIRE(H >= 1 && W >= 1, "image must be at least 1x1 (got %dx%d)", H, W);
+    REQUIRE(src_pitch_host >= (size_t)W * 4 && dst_pitch_host >= (size_t)W * 4, "bad host pitch");
+    const size_t pitch = ((size_t)W * 4 + 15) / 16 * 16;  // device rows: 16-byte pitch for TMA
+    int rc = pipe_prepare(pitch * (size_t)H, pitch * (size_t)H);
+    if (rc) return rc;
+    HostPipe &hp = g_pipe;
+    if (nbands <= 0)  // one band per 8 MiB, at most 8 (a 4096^2 image: 8 bands of 512 rows)
+        nbands = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)W * 4 * (size_t)H) >> 23));
+    nbands = std::min(std::min(nbands, kMaxBands), H);
+    const int rows_per = (H + nbands - 1) / nbands;
+    nbands = (H + rows_per - 1) / rows_per;
+    char *dsrc = (char *)hp.dsrc, *ddst = (char *)hp.ddst;
+    // uploads, in row order
+    for (int b = 0; b < nbands; ++b) {
+        const int r0 = b * rows_per, nr = std::min(rows_per, H - r0);
+        CUDA_TRY(cudaMemcpy2DAsync(dsrc + (size_t)r0 * pitch, pitch,
+                                   (const char *)src_host + (size_t)r0 * src_pitch_host,
+                                   src_pitch_host, (size_t)W * 4, nr, cudaMemcpyHostToDevice, hp.up));
+        CUDA_TRY(cudaEventRecord(hp.ev_up[b], hp.up));
+    }
+    // per band: wait for the last source row it can touch, unwarp its rows, download them
+    int waited = -1;
+    for (int b = 0; b < nbands; ++b) {
+        const int r0 = b * rows_per, nr = std::min(rows_per, H - r0);
+        int lo, hi;
+        radial_row_range(*model, H, W, r0, r0 + nr, &lo, &hi);
+        const int need = std::min(nbands - 1, hi / rows_per);
+        if (need > waited) {
+            CUDA_TRY(cudaStreamWaitEvent(hp.run, hp.ev_up[need], 0));
+            waited = need;
+        }
+        rc = dcb_unwarp_stack_backward_f32((const float *)dsrc, (float *)(ddst + (size_t)r0 * pitch), 1,
+                                           H, W, 0, H, pitch, pitch * (size_t)H, pitch,
+                                           pitch * (size_t)nr, r0, nr, 1, model, opt, hp.run);
+        if (rc) {
+            cudaDeviceSynchronize();
+            return rc;
+        }
+        CUDA_TRY(cudaEventRecord(hp.ev_run[b], hp.run));
+        CUDA_TRY(cudaStreamWaitEvent(hp.down, hp.ev_run[b], 0));
+        CUDA_TRY(cudaMemcpy2DAsync((char *)dst_host + (size_t)r0 * dst_pitch_host, dst_pitch_host,
+                                   ddst + (size_t)r0 * pitch, pitch, (size_t)W * 4, nr,
+                                   cudaMemcpyDeviceToHost, hp.down));
+    }
+    CUDA_TRY(cudaStreamSynchronize(hp.down));
+    CUDA_TRY(cudaStreamSynchronize(hp.run));
+    CUDA_TRY(cudaStreamSynchronize(hp.up));
+    return DCB_OK;
+}
+
 int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W, size_t src_pitch,
                                       size_t dst_pitch, const dcb_persp *model,
                                       const dcb_options *opt, void *stream) {

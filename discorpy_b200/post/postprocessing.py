@@ -36,7 +36,7 @@ _MODES = ("reflect", "grid-mirror", "constant", "grid-constant", "nearest",
           "mirror", "grid-wrap", "wrap")
 
 #: blend / path used by the hot functions; see include/discorpy_b200.h
-config = {"blend": _cabi.BLEND_EXACT, "path": _cabi.PATH_AUTO}
+config = {"blend": _cabi.BLEND_EXACT, "path": _cabi.PATH_AUTO, "bands": 0}
 
 
 # ---------------------------------------------------------------------------
@@ -145,15 +145,22 @@ def unwarp_image_backward(mat, xcenter, ycenter, list_fact, order=1,
     (height, width) = mat.shape          # ValueError for non-2D, like :137
     order = _check_order_mode(order, mode)
     model = _cabi.make_radial(xcenter, ycenter, list_fact)
-    stream = _dev.current_stream()
-    src = mat if on_device else DeviceArray.from_host(_as_f32_image(mat),
-                                                      stream)
-    dst = DeviceArray((height, width))
     opt = _opts(order)
-    _cabi.call("dcb_unwarp_image_backward_f32", _vp(src.ptr), _vp(dst.ptr),
-               height, width, src.pitch, dst.pitch, ctypes.byref(model),
+    if not on_device:
+        # host in, host out: banded upload / compute / download pipeline
+        src = _as_f32_image(mat)
+        _dev.ensure_init()
+        out = _dev.pinned_empty((height, width), np.float32)
+        _cabi.call("dcb_unwarp_image_backward_host_f32", _vp(src.ctypes.data),
+                   _vp(out.ctypes.data), height, width, width * 4, width * 4,
+                   ctypes.byref(model), ctypes.byref(opt), config["bands"])
+        return out
+    stream = _dev.current_stream()
+    dst = DeviceArray((height, width))
+    _cabi.call("dcb_unwarp_image_backward_f32", _vp(mat.ptr), _vp(dst.ptr),
+               height, width, mat.pitch, dst.pitch, ctypes.byref(model),
                ctypes.byref(opt), _vp(stream.handle))
-    return dst if on_device else dst.to_host(stream=stream)
+    return dst
 
 
 def unwarp_image_forward(mat, xcenter, ycenter, list_fact):

@@ -125,6 +125,18 @@ int dcb_unwarp_image_backward_f32(const float *src, float *dst, int H, int W,
                                   const dcb_radial *model_host,
                                   const dcb_options *opt_host, void *stream);
 
+/* Same function for HOST buffers (what a NumPy caller holds): the image is
+ * uploaded in `nbands` row bands (0 = library default), each band of output rows
+ * is unwarped as soon as the last source row it can sample has arrived, and is
+ * downloaded while the next one computes -- three streams, so for a pinned
+ * 4096^2 image the call costs about one PCIe transfer instead of two plus the
+ * kernel.  Synchronous: returns when dst_host is complete.  Pitches in bytes.
+ * Device scratch and streams are cached per host thread. */
+int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, int H, int W,
+                                       size_t src_pitch_host, size_t dst_pitch_host,
+                                       const dcb_radial *model_host,
+                                       const dcb_options *opt_host, int nbands);
+
 /* Replaces the per-slice Python loops of
  *   postprocessing.py:188-229 `unwarp_slice_backward`        (coord_round = 0,
  *       row0 = index, nrows = 1: float64 coordinates, never rounded), and

@@ -244,6 +244,34 @@ def test_device_resident_api_and_sharding_gives_same_bytes():
     assert np.array_equal(res.to_host(), whole[0])
 
 
+def test_banded_host_pipeline_gives_the_same_bytes():
+    """dcb_unwarp_image_backward_host_f32: upload / compute / download in row
+    bands must not change a single byte, whatever the band count, also when a
+    band's source rows lie far from its output rows (strong distortion)."""
+    rng = np.random.default_rng(77)
+    mat = rng.random((1500, 1100), dtype=np.float32)
+    pinned = dcb.pinned_copy(mat)
+    for xc, yc, fact in ((551.3, 760.2, FACT5),
+                         (300.0, 1400.5, [0.7, 6e-4, -2e-7]),      # strong, off-centre
+                         (551.3, 760.2, [1.9, -1.5e-3, 6e-7])):    # folds rows back
+        want = orc.unwarp_image_backward(mat, xc, yc, fact, 1)
+        outs = []
+        for bands in (1, 2, 5, 13):
+            post.config["bands"] = bands
+            try:
+                outs.append(post.unwarp_image_backward(pinned if bands != 5 else mat, xc, yc, fact))
+            finally:
+                post.config["bands"] = 0
+        for o in outs[1:]:
+            assert np.array_equal(o, outs[0])
+        _compare(outs[0], want, mat, 1, flips_allowed=1)
+    # the default band count on a 32 MiB image (4 bands)
+    big = rng.random((2048, 4096), dtype=np.float32)
+    got = post.unwarp_image_backward(big, 2050.4, 1000.6, FACT5)
+    dev = post.unwarp_image_backward(dcb.DeviceArray.from_host(big), 2050.4, 1000.6, FACT5)
+    assert np.array_equal(got, dev.to_host())
+
+
 def test_edge_shapes_and_values():
     for shape in ((1, 1), (1, 300), (300, 1), (2, 2), (33, 129), (7, 4097)):
         rng = np.random.default_rng(shape[0] * 31 + shape[1])

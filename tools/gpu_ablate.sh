@@ -16,7 +16,7 @@ for w in (6, 7, 8, 9):
 PY
 rm -f gpurun_out/bench_variants_$tag.jsonl
 for f in $flags; do for blend in $blends; do
-  DCB_FLAGS=$f timeout 300 python bench.py --steps 20 --warmup 3 --blend $blend --no-cpu-baseline --e2e-steps 0 2>&1 | tail -1 | sed "s/^{/{\"flags\": $f, /" >> gpurun_out/bench_variants_$tag.jsonl
+  DCB_FLAGS=$f timeout 300 python bench.py --steps 20 --warmup 3 --blend $blend --no-cpu-baseline --no-extras --e2e-steps 0 2>&1 | tail -1 | sed "s/^{/{\"flags\": $f, /" >> gpurun_out/bench_variants_$tag.jsonl
 done; done
 python - <<PY
 import json

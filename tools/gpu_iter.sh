@@ -8,7 +8,7 @@ echo "== smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3
 echo "== pytest gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
 rm -f gpurun_out/bench_variants_$tag.jsonl
 for f in $flags; do for blend in $blends; do
-  DCB_FLAGS=$f timeout 300 python bench.py --steps 20 --warmup 3 --blend $blend --no-cpu-baseline --e2e-steps 0 2>&1 | tail -1 | sed "s/^{/{\"flags\": $f, /" >> gpurun_out/bench_variants_$tag.jsonl
+  DCB_FLAGS=$f timeout 300 python bench.py --steps 20 --warmup 3 --blend $blend --no-cpu-baseline --no-extras --e2e-steps 0 2>&1 | tail -1 | sed "s/^{/{\"flags\": $f, /" >> gpurun_out/bench_variants_$tag.jsonl
 done; done
 python - <<PY
 import json
