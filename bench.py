@@ -295,6 +295,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     ms_local = e0.elapsed_ms(e1)
     ms = max_over_ranks(ms_local)
     plan = dcb.last_plan()
+    clocks = sampler.stop() if sampler else None     # NVML polling must not sit in the e2e loop
 
     # ---- end to end through the public API, host buffers ----------------------
     e2e_n = args.e2e_images_per_step
@@ -316,7 +317,6 @@ def run_gpu_arm(args, rank, local_rank, world):
     dcb.synchronize()
     e2e_s_local = time.perf_counter() - t0
     e2e_s = max_over_ranks(e2e_s_local)
-    clocks = sampler.stop() if sampler else None
     barrier()
 
     # ---- secondary device-timed figures (explain the headline, do not replace it) ----

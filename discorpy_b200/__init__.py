@@ -52,4 +52,10 @@ def install_as_discorpy():
     proc = sys.modules.get("discorpy.proc.processing")
     if proc is not None and hasattr(proc, "post"):
         proc.post = ours
+    try:        # the colour-frame entry lives in discorpy.util.utility
+        ref_util = importlib.import_module("discorpy.util.utility")
+        from .util import utility as our_util
+        ref_util.unwarp_color_image_backward = our_util.unwarp_color_image_backward
+    except ImportError:
+        pass
     return pkg

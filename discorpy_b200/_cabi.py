@@ -22,6 +22,7 @@ DCB_ERR_NO_DEVICE = -4
 
 BLEND_EXACT, BLEND_LERP64, BLEND_LERP32 = 0, 1, 2
 PATH_AUTO, PATH_DIRECT, PATH_TMA = 0, 1, 2
+FLAG_ROUND_INT = 0x100      # DCB_FLAG_ROUND_INT
 
 
 class DcbError(RuntimeError):
@@ -175,8 +176,8 @@ def make_persp(list_coef):
 
 
 def make_options(order=1, blend=BLEND_EXACT, path=PATH_AUTO, flags=None):
-    """``flags`` is reserved (0); A/B builds of the library (-DDCB_AB) read an
-    experimental kernel variant from it, settable through ``DCB_FLAGS``."""
-    if flags is None:
-        flags = int(os.environ.get("DCB_FLAGS", "0") or 0)
-    return Options(int(order), int(blend), int(path), int(flags))
+    """``flags``: ``FLAG_ROUND_INT`` for integer images.  A/B builds of the
+    library (-DDCB_AB) also read an experimental kernel variant from the low
+    byte, settable through ``DCB_FLAGS``."""
+    env = int(os.environ.get("DCB_FLAGS", "0") or 0) & 0xff
+    return Options(int(order), int(blend), int(path), int(flags or 0) | env)

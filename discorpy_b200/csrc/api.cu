@@ -149,7 +149,8 @@ static void persp_slopes(const dcb_persp &m, int H, int W, double *gmain, double
 typedef void (*StackKernel)(const RemapParams, const CUtensorMap);
 
 // Launch planning for the Z-stack kernel (remap_stack.cuh).
-static int plan_and_launch_stack(StackKernel kern, RemapParams &p, double gmain, double gcross,
+static int plan_and_launch_stack(StackKernel kern, bool widen, RemapParams &p, double gmain,
+                                 double gcross,
                                  int path_req, size_t src_pitch_bytes, size_t src_slice_bytes,
                                  cudaStream_t stream) {
     DevProps props;
@@ -193,7 +194,9 @@ static int plan_and_launch_stack(StackKernel kern, RemapParams &p, double gmain,
         bh = std::max(bh, 1);
         // ring depth: as many slices in flight as ~96 KB per CTA hold (two CTAs per SM)
         const long long stage = ((long long)bw * bh * 4 + 127) / 128 * 128;
-        nstage = (int)std::max<long long>(2, std::min<long long>(kStkMaxStages, (96 * 1024) / stage));
+        // (the fp64 blends keep two float64 copies of a box = 4 stages' worth next to the ring)
+        nstage = (int)std::max<long long>(
+            2, std::min<long long>(kStkMaxStages, (100 * 1024) / stage - (widen ? 4 : 0)));
     }
     p.bw = bw;
     p.bh = bh;
@@ -201,7 +204,7 @@ static int plan_and_launch_stack(StackKernel kern, RemapParams &p, double gmain,
     p.box_bytes = (unsigned)(bw * bh * 4);
     p.stage_bytes = (p.box_bytes + 127u) / 128u * 128u;
     const size_t tail = 2 * kStkMaxStages * sizeof(uint64_t) + 2 * 4 * kWarps * sizeof(int);
-    size_t smem = (size_t)nstage * p.stage_bytes + tail;
+    size_t smem = (size_t)(nstage + (widen && nstage > 0 ? 4 : 0)) * p.stage_bytes + tail;
 
     // --- z chunking: enough items to balance the machine, long enough chunks to
     //     amortise the per-tile geometry ----------------------------------------------
@@ -401,6 +404,7 @@ static int check_options(const dcb_options *opt, dcb_options *o) {
             "order %d not supported by the CUDA path (0 and 1 are)", o->order);
     REQUIRE(o->blend >= 0 && o->blend <= 2, "unknown blend %d", o->blend);
     REQUIRE(o->path >= 0 && o->path <= 2, "unknown path %d", o->path);
+    REQUIRE((o->flags & ~(DCB_FLAG_ROUND_INT | 0xff)) == 0, "unknown flags 0x%x", o->flags);
     return DCB_OK;
 }
 
@@ -656,6 +660,7 @@ int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, in
     p.nrows = nrows;
     p.yorg = src_row0;
     p.ylast = src_row0 + src_rows - 1;
+    p.rint = (o.flags & DCB_FLAG_ROUND_INT) ? 1 : 0;
     double gm, gc;
     radial_slopes(*model, W, row0, nrows, &gm, &gc);
     if (coord_round && D == 1) {
@@ -673,14 +678,17 @@ int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, in
         q.yorg = p.yorg;
         q.ylast = p.ylast;
         q.dbg = (o.flags >> 4) & 0xf;
+        q.rint = p.rint;
         const ImageKernelSel k = pick_image_kernel<MAP_RADIAL>(o.order, o.blend, model->n, o.flags);
         return plan_and_launch_image(k, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
     }
+    const bool widen = StackWeights<1, DCB_BLEND_EXACT, true>::kWiden && (o.order == 1) &&
+                       (o.blend != DCB_BLEND_LERP32);
     if (coord_round)
-        return plan_and_launch_stack(pick_stack_kernel<true>(o.order, o.blend), p, gm, gc, o.path,
-                                     src_pitch, src_slice_stride, (cudaStream_t)stream);
-    return plan_and_launch_stack(pick_stack_kernel<false>(1, o.blend), p, gm, gc, o.path, src_pitch,
-                                 src_slice_stride, (cudaStream_t)stream);
+        return plan_and_launch_stack(pick_stack_kernel<true>(o.order, o.blend), widen, p, gm, gc,
+                                     o.path, src_pitch, src_slice_stride, (cudaStream_t)stream);
+    return plan_and_launch_stack(pick_stack_kernel<false>(1, o.blend), widen, p, gm, gc, o.path,
+                                 src_pitch, src_slice_stride, (cudaStream_t)stream);
 }
 
 int dcb_unwarp_image_backward_f32(const float *src, float *dst, int H, int W, size_t src_pitch,
@@ -884,6 +892,7 @@ int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W
     q.nrows = H;
     q.yorg = 0;
     q.ylast = H - 1;
+    q.rint = (o.flags & DCB_FLAG_ROUND_INT) ? 1 : 0;
     const ImageKernelSel k = pick_image_kernel<MAP_PERSP>(o.order, o.blend, 0, o.flags);
     return plan_and_launch_image(k, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
 }
@@ -914,18 +923,19 @@ static int launch_map_coords(const float *src, float *dst, int H, int W, long lo
     const size_t want = (n + 255) / 256;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)props.sm_count * 16));
     const CT *y = (const CT *)yd, *x = (const CT *)xd;
+    const int rint = (o.flags & DCB_FLAG_ROUND_INT) ? 1 : 0;
     if (o.order == 0)
         map_coords_kernel<0, DCB_BLEND_EXACT, CT><<<grid, 256, 0, stream>>>(src, dst, H, W, pitch, y,
-                                                                           x, n, oob);
+                                                                           x, n, oob, 0);
     else if (o.blend == DCB_BLEND_LERP64)
         map_coords_kernel<1, DCB_BLEND_LERP64, CT><<<grid, 256, 0, stream>>>(src, dst, H, W, pitch,
-                                                                            y, x, n, oob);
+                                                                            y, x, n, oob, rint);
     else if (o.blend == DCB_BLEND_LERP32 && sizeof(CT) == 4)
         map_coords_kernel<1, DCB_BLEND_LERP32, CT><<<grid, 256, 0, stream>>>(src, dst, H, W, pitch,
-                                                                            y, x, n, oob);
+                                                                            y, x, n, oob, rint);
     else
         map_coords_kernel<1, DCB_BLEND_EXACT, CT><<<grid, 256, 0, stream>>>(src, dst, H, W, pitch, y,
-                                                                           x, n, oob);
+                                                                           x, n, oob, rint);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     g_last_plan = {DCB_PATH_DIRECT, 0, 0, grid, 0};

@@ -40,6 +40,7 @@ struct RemapParams {
     int tiles_x, tiles_y, zchunk, ntiles;
     int bw, bh, nstage;  // staged box; nstage == 0 => direct gathers only
     unsigned stage_bytes, box_bytes;
+    int rint, pad;       // 1: integer image, round half away from zero (see finish_f64)
     RadialDev rad;
     PerspDev per;
 };
@@ -64,12 +65,29 @@ struct GlobalFetch {
 };
 
 // ---------------------------------------------------------------------------
+// output conversion.  float32 images: one IEEE rounding of the fp64 sum.
+// Integer images (uint8/16, int8/16 travel as float32, exactly): SciPy adds
+// +-0.5 to the fp64 sum and truncates ("round half away from zero"); doing it
+// here, before the value ever becomes a float32, avoids a double rounding.
+// `rint` is a kernel parameter (warp-uniform).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double round_half_away(double s) {
+    return trunc(s + (s >= 0.0 ? 0.5 : -0.5));
+}
+__device__ __forceinline__ float finish_f64(double s, int rint) {
+    return __double2float_rn(rint ? round_half_away(s) : s);
+}
+__device__ __forceinline__ float finish_f32(float v, int rint) {
+    return rint ? truncf(v + (v >= 0.0f ? 0.5f : -0.5f)) : v;
+}
+
+// ---------------------------------------------------------------------------
 // one output pixel: the arithmetic of scipy.ndimage.map_coordinates(order 0|1)
 // for a coordinate that already lies in [0, W-1] x [0, H-1]
 // ---------------------------------------------------------------------------
 template <int ORDER, int BLEND, class CT, class Fetch>
 __device__ __forceinline__ float sample_px(const Fetch &fetch, CT x, CT y, int wmax, int ylo,
-                                           int yhi) {
+                                           int yhi, int rint = 0) {
     int x0 = (int)x;  // truncation == floor, coordinates are >= 0
     int y0 = (int)y;
     const CT tx = x - (CT)x0;  // exact
@@ -94,13 +112,13 @@ __device__ __forceinline__ float sample_px(const Fetch &fetch, CT x, CT y, int w
         const float ftx = (float)tx, fty = (float)ty;
         const float top = fmaf(b - a, ftx, a);
         const float bot = fmaf(d - c, ftx, c);
-        return fmaf(bot - top, fty, top);
+        return finish_f32(fmaf(bot - top, fty, top), rint);
     } else if (BLEND == DCB_BLEND_LERP64) {
         const double dtx = (double)tx, dty = (double)ty;
         const double da = a, db = b, dc = c, dd = d;
         const double top = fma(db - da, dtx, da);
         const double bot = fma(dd - dc, dtx, dc);
-        return (float)fma(bot - top, dty, top);
+        return finish_f64(fma(bot - top, dty, top), rint);
     } else {
         // SciPy's order: each tap times its y weight, then its x weight, the
         // four products summed first to last, every step rounded (no FMA).
@@ -110,7 +128,7 @@ __device__ __forceinline__ float sample_px(const Fetch &fetch, CT x, CT y, int w
         t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)b, wy0), wx1));
         t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)c, wy1), wx0));
         t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)d, wy1), wx1));
-        return __double2float_rn(t);
+        return finish_f64(t, rint);
     }
 }
 
@@ -134,7 +152,7 @@ template <int ORDER, int BLEND, class CT>
 __global__ void __launch_bounds__(256)
     map_coords_kernel(const float *__restrict__ src, float *__restrict__ dst, int H, int W,
                       long long pitch, const CT *__restrict__ yd, const CT *__restrict__ xd,
-                      size_t n, unsigned *oob_count) {
+                      size_t n, unsigned *oob_count, int rint) {
     unsigned oob = 0;
     GlobalFetch fetch{src, pitch};
     const CT xmax = (CT)(W - 1), ymax = (CT)(H - 1);
@@ -146,7 +164,7 @@ __global__ void __launch_bounds__(256)
         y = y > (CT)0 ? y : (CT)0;
         x = x < xmax ? x : xmax;
         y = y < ymax ? y : ymax;
-        dst[i] = sample_px<ORDER, BLEND, CT>(fetch, x, y, W - 1, 0, H - 1);
+        dst[i] = sample_px<ORDER, BLEND, CT>(fetch, x, y, W - 1, 0, H - 1, rint);
     }
     if (oob_count != nullptr && oob != 0) atomicAdd(oob_count, oob);
 }

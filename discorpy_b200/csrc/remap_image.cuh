@@ -44,7 +44,8 @@ struct ImageParams {
     int tiles_y, ntiles;  // tiles are numbered column-major: t = txi * tiles_y + tyi
     int bw, bh;        // staged box, bw % 4 == 0; bw == 0 => never stage
     unsigned box_bytes, stage_bytes;
-    int dbg, pad;      // A/B builds (-DDCB_AB): ablation switches, 0 otherwise
+    int dbg;           // A/B builds (-DDCB_AB): ablation switches, 0 otherwise
+    int rint;          // 1: integer image, round half away from zero (finish_f64 in remap.cuh)
     RadialDev rad;
     PerspDev per;
 };
@@ -90,8 +91,8 @@ __device__ __forceinline__ double dsqrt_nz(double s) {
 //     products ty(1-tx), (1-ty)tx, (1-ty)(1-tx).
 // 5 + 4 + 3 = 12 fp64 operations instead of 13, every one of them rounding
 // exactly where SciPy's does.
-__device__ __forceinline__ float blend_exact(double a, double b, double c, double d, double tx,
-                                             double ty) {
+__device__ __forceinline__ double blend_exact(double a, double b, double c, double d, double tx,
+                                              double ty) {
     const double w11 = __dmul_rn(ty, tx);
     const double w10 = __dsub_rn(ty, w11);
     const double w01 = __dsub_rn(tx, w11);
@@ -100,7 +101,7 @@ __device__ __forceinline__ float blend_exact(double a, double b, double c, doubl
     s = __dadd_rn(s, __dmul_rn(b, w01));
     s = __dadd_rn(s, __dmul_rn(c, w10));
     s = __dadd_rn(s, __dmul_rn(d, w11));
-    return __double2float_rn(s);
+    return s;
 }
 
 // Per-thread column terms of the map (constant down a tile) and the row
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
                 }
                 float v[kCols];
                 if (__all_sync(0xffffffffu, ok)) {
+                    double sd[WIDE ? kCols : 1];
 #pragma unroll
                     for (int k = 0; k < kCols; ++k) {
                         const float tx = xf[k] - (tfx[k] - 8388608.0f);  // exact
@@ -423,11 +425,22 @@ __global__ void __launch_bounds__(kThreads, MINB)
                             if (BLEND == DCB_BLEND_LERP64) {
                                 const double top = fma(b - a, wx1, a);
                                 const double bot = fma(d - c, wx1, c);
-                                v[k] = (float)fma(bot - top, wy1, top);
+                                sd[WIDE ? k : 0] = fma(bot - top, wy1, top);
                             } else {
-                                v[k] = blend_exact(a, b, c, d, wx1, wy1);
+                                sd[WIDE ? k : 0] = blend_exact(a, b, c, d, wx1, wy1);
                             }
                         }
+                    }
+                    if (WIDE) {
+                        if (p.rint) {  // integer image: SciPy's +-0.5 and truncate, still in fp64
+#pragma unroll
+                            for (int k = 0; k < kCols; ++k) sd[WIDE ? k : 0] = round_half_away(sd[WIDE ? k : 0]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < kCols; ++k) v[k] = __double2float_rn(sd[WIDE ? k : 0]);
+                    } else if (ORDER == 1 && p.rint) {
+#pragma unroll
+                        for (int k = 0; k < kCols; ++k) v[k] = finish_f32(v[k], 1);
                     }
                 } else {
                     const GlobalFetch gfetch{p.src - (long long)p.yorg * p.src_pitch, p.src_pitch};
@@ -437,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
                     for (int k = 0; k < kCols; ++k)
                         v[k] = sample_px<ORDER, BLEND, float>(gfetch, clamp_bits(xf[k], wbits),
                                                               clamp_bits(yf[k], hbits), wmax,
-                                                              p.yorg, p.ylast);
+                                                              p.yorg, p.ylast, p.rint);
                 }
                 if (full_w) {
 #pragma unroll

@@ -54,6 +54,12 @@ struct StackWeights {
     // everything else keeps the two fractions as doubles
     static constexpr bool kT64 = (ORDER == 1 && !kF32 && !kW4);
     static constexpr int kDoubles = kW4 ? 4 : (kT64 ? 2 : 0);
+    // Sampling the fp64 blends from a float64 copy of the staged box (one
+    // conversion per source pixel instead of one per tap) was measured and
+    // rejected: the CTA barrier it needs per slice costs more than the XU
+    // conversions it saves (64 x 4096^2, exact: 48 % vs 56 % of the HBM peak).
+    // The code path is kept behind this switch for the record.
+    static constexpr bool kWiden = false;
 };
 
 template <int ORDER, int BLEND, bool ROUND32>
@@ -64,7 +70,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     using SW = StackWeights<ORDER, BLEND, ROUND32>;
 
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)p.nstage * p.stage_bytes);
+    // layout: [nstage raw boxes][two float64 tiles (fp64 blends only)][full][empty][red]
+    unsigned char *wide_base = smem + (size_t)p.nstage * p.stage_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(wide_base + (SW::kWiden ? 4 : 0) * (size_t)p.stage_bytes);
     uint64_t *empty = full + kStkMaxStages;
     int *red = reinterpret_cast<int *>(empty + kStkMaxStages);  // [2][4][kWarps]
 
@@ -233,57 +241,84 @@ __global__ void __launch_bounds__(kThreads, 2)
                 const uint32_t g = base + iz, st = g % S;
                 mbar_wait(&full[st], (g / S) & 1u);
                 const float *tile = reinterpret_cast<const float *>(smem + (size_t)st * p.stage_bytes);
+                const double *wtile = reinterpret_cast<const double *>(
+                    wide_base + (size_t)(2 * (iz & 1)) * p.stage_bytes);
+                if (SW::kWiden) {
+                    // float32 box -> float64 tile (exact), then the raw stage can be refilled;
+                    // the tile written here was last read two slices ago, behind the barrier
+                    // of the previous slice
+                    const float4 *src4 = reinterpret_cast<const float4 *>(tile);
+                    double2 *dst2 = reinterpret_cast<double2 *>(
+                        wide_base + (size_t)(2 * (iz & 1)) * p.stage_bytes);
+                    const int n4 = (bw * p.bh) >> 2;  // bw % 4 == 0
+                    int e = threadIdx.x;
+                    for (; e + kThreads < n4; e += 2 * kThreads) {
+                        const float4 u = src4[e], w = src4[e + kThreads];
+                        dst2[2 * e] = make_double2((double)u.x, (double)u.y);
+                        dst2[2 * e + 1] = make_double2((double)u.z, (double)u.w);
+                        dst2[2 * (e + kThreads)] = make_double2((double)w.x, (double)w.y);
+                        dst2[2 * (e + kThreads) + 1] = make_double2((double)w.z, (double)w.w);
+                    }
+                    if (e < n4) {
+                        const float4 u = src4[e];
+                        dst2[2 * e] = make_double2((double)u.x, (double)u.y);
+                        dst2[2 * e + 1] = make_double2((double)u.z, (double)u.w);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[st]);
+                    __syncthreads();
+                }
                 float v[kStkPx];
 #pragma unroll
                 for (int i = 0; i < kStkPx; ++i) {
-                    const float *q = tile + off[i];
                     if (ORDER == 0) {
-                        v[i] = q[0];
+                        v[i] = tile[off[i]];
                         continue;
                     }
-                    float a, b, c, d;
-                    if (!edge) {
-                        a = q[0];
-                        b = q[1];
-                        c = q[bw];
-                        d = q[bw + 1];
-                    } else {
-                        const int ox = (int)((dxm >> i) & 1u);
-                        const int oy = ((dym >> i) & 1u) ? bw : 0;
-                        a = q[0];
-                        b = q[ox];
-                        c = q[oy];
-                        d = q[oy + ox];
-                    }
+                    const int ox = edge ? (int)((dxm >> i) & 1u) : 1;
+                    const int oy = edge ? (((dym >> i) & 1u) ? bw : 0) : bw;
                     if (SW::kF32) {
+                        const float *q = tile + off[i];
+                        const float a = q[0], b = q[ox], c = q[oy], d = q[oy + ox];
                         const float top = fmaf(b - a, wf[i][0], a);
                         const float bot = fmaf(d - c, wf[i][0], c);
-                        v[i] = fmaf(bot - top, wf[i][1], top);
-                    } else if (SW::kW4) {
-                        double s = __dmul_rn((double)a, wd[i][0]);
-                        s = __dadd_rn(s, __dmul_rn((double)b, wd[i][1]));
-                        s = __dadd_rn(s, __dmul_rn((double)c, wd[i][2]));
-                        s = __dadd_rn(s, __dmul_rn((double)d, wd[i][3]));
-                        v[i] = __double2float_rn(s);
+                        v[i] = finish_f32(fmaf(bot - top, wf[i][1], top), p.rint);
+                        continue;
+                    }
+                    double a, b, c, d;
+                    if (SW::kWiden) {
+                        const double *q = wtile + off[i];
+                        a = q[0], b = q[ox], c = q[oy], d = q[oy + ox];
+                    } else {
+                        const float *q = tile + off[i];
+                        a = (double)q[0], b = (double)q[ox], c = (double)q[oy], d = (double)q[oy + ox];
+                    }
+                    if (SW::kW4) {
+                        double s = __dmul_rn(a, wd[i][0]);
+                        s = __dadd_rn(s, __dmul_rn(b, wd[i][1]));
+                        s = __dadd_rn(s, __dmul_rn(c, wd[i][2]));
+                        s = __dadd_rn(s, __dmul_rn(d, wd[i][3]));
+                        v[i] = finish_f64(s, p.rint);
                     } else if (BLEND == DCB_BLEND_LERP64) {
-                        const double da = a, db = b, dc = c, dd = d;
-                        const double top = fma(db - da, wd[i][0], da);
-                        const double bot = fma(dd - dc, wd[i][0], dc);
-                        v[i] = (float)fma(bot - top, wd[i][1], top);
+                        const double top = fma(b - a, wd[i][0], a);
+                        const double bot = fma(d - c, wd[i][0], c);
+                        v[i] = finish_f64(fma(bot - top, wd[i][1], top), p.rint);
                     } else {
                         // float64 coordinates: SciPy's two-step products, every step rounded
                         const double wx1 = wd[i][0], wy1 = wd[i][1];
                         const double wx0 = __dsub_rn(1.0, wx1), wy0 = __dsub_rn(1.0, wy1);
-                        double s = __dmul_rn(__dmul_rn((double)a, wy0), wx0);
-                        s = __dadd_rn(s, __dmul_rn(__dmul_rn((double)b, wy0), wx1));
-                        s = __dadd_rn(s, __dmul_rn(__dmul_rn((double)c, wy1), wx0));
-                        s = __dadd_rn(s, __dmul_rn(__dmul_rn((double)d, wy1), wx1));
-                        v[i] = __double2float_rn(s);
+                        double s = __dmul_rn(__dmul_rn(a, wy0), wx0);
+                        s = __dadd_rn(s, __dmul_rn(__dmul_rn(b, wy0), wx1));
+                        s = __dadd_rn(s, __dmul_rn(__dmul_rn(c, wy1), wx0));
+                        s = __dadd_rn(s, __dmul_rn(__dmul_rn(d, wy1), wx1));
+                        v[i] = finish_f64(s, p.rint);
                     }
                 }
-                // this warp is done with the stage: let the producer refill it
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[st]);
+                if (!SW::kWiden) {
+                    // this warp is done with the stage: let the producer refill it
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[st]);
+                }
 #pragma unroll
                 for (int j = 0; j < kStkRows; ++j) {
                     if (y_base + j < y_end) {
@@ -348,18 +383,18 @@ __global__ void __launch_bounds__(kThreads, 2)
                     if (SW::kF32) {
                         const float top = fmaf(b - a, wf[i][0], a);
                         const float bot = fmaf(d - c, wf[i][0], c);
-                        v[i] = fmaf(bot - top, wf[i][1], top);
+                        v[i] = finish_f32(fmaf(bot - top, wf[i][1], top), p.rint);
                     } else if (SW::kW4) {
                         double s = __dmul_rn((double)a, wd[i][0]);
                         s = __dadd_rn(s, __dmul_rn((double)b, wd[i][1]));
                         s = __dadd_rn(s, __dmul_rn((double)c, wd[i][2]));
                         s = __dadd_rn(s, __dmul_rn((double)d, wd[i][3]));
-                        v[i] = __double2float_rn(s);
+                        v[i] = finish_f64(s, p.rint);
                     } else if (BLEND == DCB_BLEND_LERP64) {
                         const double da = a, db = b, dc = c, dd = d;
                         const double top = fma(db - da, wd[i][0], da);
                         const double bot = fma(dd - dc, wd[i][0], dc);
-                        v[i] = (float)fma(bot - top, wd[i][1], top);
+                        v[i] = finish_f64(fma(bot - top, wd[i][1], top), p.rint);
                     } else {
                         const double wx1 = wd[i][0], wy1 = wd[i][1];
                         const double wx0 = __dsub_rn(1.0, wx1), wy0 = __dsub_rn(1.0, wy1);
@@ -367,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                         s = __dadd_rn(s, __dmul_rn(__dmul_rn((double)b, wy0), wx1));
                         s = __dadd_rn(s, __dmul_rn(__dmul_rn((double)c, wy1), wx0));
                         s = __dadd_rn(s, __dmul_rn(__dmul_rn((double)d, wy1), wx1));
-                        v[i] = __double2float_rn(s);
+                        v[i] = finish_f64(s, p.rint);
                     }
                 }
 #pragma unroll

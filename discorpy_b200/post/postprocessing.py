@@ -56,35 +56,38 @@ def _check_order_mode(order, mode):
     return int(order)
 
 
+#: integer dtypes that embed exactly in float32; images of these types travel
+#: as float32 and come back rounded the way SciPy rounds integer outputs
+_INT_IMAGE_DTYPES = (np.dtype(np.uint8), np.dtype(np.int8),
+                     np.dtype(np.uint16), np.dtype(np.int16))
+
+
 def _as_f32_image(mat):
-    """float32 images go to the GPU as they are.  Other dtypes would need the
-    reference's 'same dtype out' rule (round-half-away for integers) inside
-    the kernel and are refused loudly instead of silently going to the CPU."""
-    if mat.dtype != np.float32:
-        raise NotImplementedError(
-            "dtype %s is not implemented on the CUDA path yet (float32 is); "
-            "there is no CPU fallback" % mat.dtype)
-    return np.ascontiguousarray(mat)
+    """Returns ``(float32 C-contiguous array, flags, output dtype)``.
+
+    float32 images go to the GPU as they are.  uint8 / int8 / uint16 / int16
+    images are widened exactly on the host and flagged so that the kernels
+    round order-1 results half away from zero while still in float64 -- the
+    reference's 'same dtype out' rule (``scipy/ndimage/_ni_support.py:83``).
+    Anything else (float64, float16, 32/64-bit integers) is refused loudly
+    instead of silently going to the CPU."""
+    if mat.dtype == np.float32:
+        return np.ascontiguousarray(mat), 0, None
+    if mat.dtype in _INT_IMAGE_DTYPES:
+        return (np.ascontiguousarray(mat, dtype=np.float32),
+                _cabi.FLAG_ROUND_INT, mat.dtype)
+    raise NotImplementedError(
+        "dtype %s is not implemented on the CUDA path yet (float32, uint8, "
+        "int8, uint16 and int16 are); there is no CPU fallback" % mat.dtype)
 
 
-_EXACT_IN_F32 = (np.dtype(np.float32), np.dtype(np.float16), np.dtype(np.uint8),
-                 np.dtype(np.int8), np.dtype(np.uint16), np.dtype(np.int16),
-                 np.dtype(np.bool_))
+def _narrow(out, dtype):
+    """float32 result -> the input's integer dtype (values are integers)."""
+    return out if dtype is None else out.astype(dtype)
 
 
-def _to_f32_exact(arr):
-    """For the functions whose output is float32 whatever the input
-    (``unwarp_slice_backward``): dtypes that embed exactly in float32 are
-    widened on the host; the result is then what the reference computes."""
-    if arr.dtype not in _EXACT_IN_F32:
-        raise NotImplementedError(
-            "dtype %s does not embed exactly in float32; not implemented on "
-            "the CUDA path (no CPU fallback)" % arr.dtype)
-    return np.ascontiguousarray(arr, dtype=np.float32)
-
-
-def _opts(order=1):
-    return _cabi.make_options(order, config["blend"], config["path"])
+def _opts(order=1, flags=0):
+    return _cabi.make_options(order, config["blend"], config["path"], flags)
 
 
 def _vp(ptr):
@@ -145,16 +148,17 @@ def unwarp_image_backward(mat, xcenter, ycenter, list_fact, order=1,
     (height, width) = mat.shape          # ValueError for non-2D, like :137
     order = _check_order_mode(order, mode)
     model = _cabi.make_radial(xcenter, ycenter, list_fact)
-    opt = _opts(order)
     if not on_device:
         # host in, host out: banded upload / compute / download pipeline
-        src = _as_f32_image(mat)
+        src, flags, out_dtype = _as_f32_image(mat)
+        opt = _opts(order, flags)
         _dev.ensure_init()
         out = _dev.pinned_empty((height, width), np.float32)
         _cabi.call("dcb_unwarp_image_backward_host_f32", _vp(src.ctypes.data),
                    _vp(out.ctypes.data), height, width, width * 4, width * 4,
                    ctypes.byref(model), ctypes.byref(opt), config["bands"])
-        return out
+        return _narrow(out, out_dtype)
+    opt = _opts(order)
     stream = _dev.current_stream()
     dst = DeviceArray((height, width))
     _cabi.call("dcb_unwarp_image_backward_f32", _vp(mat.ptr), _vp(dst.ptr),
@@ -186,18 +190,13 @@ def unwarp_image_forward(mat, xcenter, ycenter, list_fact):
 
 
 def _stack_call(src, dst, depth, height, width, src_row0, src_rows, src_pitch,
-                src_slice, row0, nrows, coord_round, model, stream):
-    opt = _opts(1)
+                src_slice, row0, nrows, coord_round, model, stream, order=1,
+                flags=0):
+    opt = _opts(order, flags)
     _cabi.call("dcb_unwarp_stack_backward_f32", _vp(src), _vp(dst.ptr), depth,
                height, width, src_row0, src_rows, src_pitch, src_slice,
                dst.pitch, dst.slice_stride, row0, nrows, coord_round,
                ctypes.byref(model), ctypes.byref(opt), _vp(stream.handle))
-
-
-def _upload_row_window(mat3d, row_lo, row_hi, stream):
-    """Rows [row_lo, row_hi) of every slice -> DeviceArray (D, rows, W)."""
-    win = _to_f32_exact(np.asarray(mat3d[:, row_lo:row_hi, :]))
-    return DeviceArray.from_host(win, stream)
 
 
 def unwarp_slice_backward(mat3D, xcenter, ycenter, list_fact, index):
@@ -238,9 +237,13 @@ def unwarp_slice_backward(mat3D, xcenter, ycenter, list_fact, index):
                     0, model, stream)
         dst.shape = (depth, width)
         return dst
-    win = _upload_row_window(mat3D, yd_min, yd_max, stream)
+    # integer stacks: SciPy rounds each slice to the stack's dtype before the
+    # reference stores it into the float32 sinogram (:227-228)
+    win_np, flags, _ = _as_f32_image(np.asarray(mat3D[:, yd_min:yd_max, :]))
+    win = DeviceArray.from_host(win_np, stream)
     _stack_call(win.ptr, dst, depth, height, width, yd_min, yd_max - yd_min,
-                win.pitch, win.slice_stride, index, 1, 0, model, stream)
+                win.pitch, win.slice_stride, index, 1, 0, model, stream,
+                flags=flags)
     return dst.to_host(stream=stream).reshape(depth, width)
 
 
@@ -261,7 +264,7 @@ def _mapping(mat, xmat, ymat):
 
 def _map_coordinates(mat, yd, xd, order, mode):
     (height, width) = mat.shape
-    src_np = _as_f32_image(mat)
+    src_np, flags, out_dtype = _as_f32_image(mat)
     kind = np.result_type(yd.dtype, xd.dtype)
     ctype = np.float32 if kind == np.float32 else np.float64
     yd = np.ascontiguousarray(yd, dtype=ctype).ravel()
@@ -279,7 +282,7 @@ def _map_coordinates(mat, yd, xd, order, mode):
         _cabi.call("dcb_h2d", _vp(dy.ptr), _vp(yd.ctypes.data), n * itemsize, sh)
         _cabi.call("dcb_h2d", _vp(dx.ptr), _vp(xd.ctypes.data), n * itemsize, sh)
         _cabi.call("dcb_memset", _vp(dflag.ptr), 0, 16, sh)
-        opt = _opts(order)
+        opt = _opts(order, flags)
         _cabi.call("dcb_map_coordinates_f32", _vp(src.ptr), _vp(dout.ptr),
                    height, width, src.pitch, _vp(dy.ptr), _vp(dx.ptr),
                    int(ctype is np.float64), n, _vp(dflag.ptr),
@@ -294,7 +297,7 @@ def _map_coordinates(mat, yd, xd, order, mode):
             "%d coordinates lie outside the image; the CUDA path clamps them, "
             "which equals SciPy only for mode='nearest' (got %r)"
             % (int(flag[0]), mode))
-    return out
+    return _narrow(out, out_dtype)
 
 
 def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
@@ -326,10 +329,6 @@ def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
     yd2 = _row_yd(height, width, xcenter, ycenter, list_fact, stop_index)
     yd_min = int(np.int16(np.floor(np.amin(yd1))))
     yd_max = int(np.int16(np.ceil(np.amax(yd2)))) + 1
-    if not on_device and np.asarray(mat3D[:0]).dtype != np.float32:
-        raise NotImplementedError(
-            "dtype %s is not implemented on the CUDA path yet (float32 is)"
-            % np.asarray(mat3D[:0]).dtype)
     nrows = stop_index - start_index + 1
     model = _cabi.make_radial(xcenter, ycenter, list_fact)
     stream = _dev.current_stream()
@@ -340,11 +339,29 @@ def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
                     yd_max - yd_min, mat3D.pitch, mat3D.slice_stride,
                     start_index, nrows, 1, model, stream)
         return dst
-    win = _upload_row_window(mat3D, yd_min, yd_max, stream)
+    win_np, flags, out_dtype = _as_f32_image(
+        np.asarray(mat3D[:, yd_min:yd_max, :]))
+    win = DeviceArray.from_host(win_np, stream)
     _stack_call(win.ptr, dst, depth, height, width, yd_min, yd_max - yd_min,
                 win.pitch, win.slice_stride, start_index, nrows, 1, model,
-                stream)
-    return dst.to_host(stream=stream)
+                stream, flags=flags)
+    return _narrow(dst.to_host(stream=stream), out_dtype)
+
+
+def _unwarp_planes(planes, xcenter, ycenter, list_fact, order):
+    """All rows of every plane of a host (C, H, W) array through the Z-stack
+    kernel with the image numerics (fp32-rounded coordinates): the geometry is
+    evaluated once and reused for every plane.  Used for colour images."""
+    (depth, height, width) = planes.shape
+    src_np, flags, out_dtype = _as_f32_image(planes)
+    model = _cabi.make_radial(xcenter, ycenter, list_fact)
+    stream = _dev.current_stream()
+    src = DeviceArray.from_host(src_np, stream)
+    dst = DeviceArray((depth, height, width))
+    _stack_call(src.ptr, dst, depth, height, width, 0, height, src.pitch,
+                src.slice_stride, 0, height, 1, model, stream, order=order,
+                flags=flags)
+    return _narrow(dst.to_host(stream=stream), out_dtype)
 
 
 def _generate_perspective_map(mat, list_coef):
@@ -400,14 +417,18 @@ def correct_perspective_image(mat, list_coef, order=1, mode="reflect",
         return out.reshape((height, width))
     model = _cabi.make_persp(list_coef)
     stream = _dev.current_stream()
-    src = mat if on_device else DeviceArray.from_host(_as_f32_image(mat),
-                                                      stream)
+    flags, out_dtype = 0, None
+    if on_device:
+        src = mat
+    else:
+        src_np, flags, out_dtype = _as_f32_image(mat)
+        src = DeviceArray.from_host(src_np, stream)
     dst = DeviceArray((height, width))
-    opt = _opts(order)
+    opt = _opts(order, flags)
     _cabi.call("dcb_correct_perspective_image_f32", _vp(src.ptr),
                _vp(dst.ptr), height, width, src.pitch, dst.pitch,
                ctypes.byref(model), ctypes.byref(opt), _vp(stream.handle))
-    return dst if on_device else dst.to_host(stream=stream)
+    return dst if on_device else _narrow(dst.to_host(stream=stream), out_dtype)
 
 
 def unwarp_image_backward_perspective(mat, xcenter, ycenter, list_fact,
@@ -417,8 +438,8 @@ def unwarp_image_backward_perspective(mat, xcenter, ycenter, list_fact,
     entry BASELINE.json names.  The reference has no such function; the result
     is defined as ``correct_perspective_image(unwarp_image_backward(mat, ...),
     list_coef)`` (``examples/readthedocs_demo/demo_05.py:127,147``) with the
-    intermediate image rounded to float32 -- both passes run back to back on
-    the GPU, the intermediate never leaves HBM.
+    intermediate image rounded to the image dtype -- both passes run back to
+    back on the GPU, the intermediate never leaves HBM.
     """
     if len(list_coef) != 8:
         raise ValueError("!!! Eight coefficients are required !!!")
@@ -430,11 +451,15 @@ def unwarp_image_backward_perspective(mat, xcenter, ycenter, list_fact,
     radial = _cabi.make_radial(xcenter, ycenter, list_fact)
     persp = _cabi.make_persp(list_coef)
     stream = _dev.current_stream()
-    src = mat if on_device else DeviceArray.from_host(_as_f32_image(mat),
-                                                      stream)
+    flags, out_dtype = 0, None
+    if on_device:
+        src = mat
+    else:
+        src_np, flags, out_dtype = _as_f32_image(mat)
+        src = DeviceArray.from_host(src_np, stream)
     tmp = DeviceArray((height, width))
     dst = DeviceArray((height, width))
-    opt = _opts(order)
+    opt = _opts(order, flags)
     _cabi.call("dcb_unwarp_image_backward_perspective_f32", _vp(src.ptr),
                _vp(dst.ptr), _vp(tmp.ptr), height, width, src.pitch, dst.pitch,
                tmp.pitch, ctypes.byref(radial), ctypes.byref(persp),
@@ -442,7 +467,7 @@ def unwarp_image_backward_perspective(mat, xcenter, ycenter, list_fact,
     if on_device:
         dst._keepalive = tmp      # until the stream has consumed it
         return dst
-    return dst.to_host(stream=stream)
+    return _narrow(dst.to_host(stream=stream), out_dtype)
 
 
 # ---------------------------------------------------------------------------

@@ -72,11 +72,20 @@ typedef struct dcb_persp {
     double c[8];
 } dcb_persp;
 
+/* dcb_options.flags.  DCB_FLAG_ROUND_INT: the image holds integer pixel values
+ * (uint8/uint16/int8/int16 widened exactly to float32 by the host); order-1
+ * results are then rounded half away from zero to an integer while still in
+ * fp64 -- what scipy.ndimage.map_coordinates does for integer outputs
+ * (output dtype = input dtype, scipy/ndimage/_ni_support.py:83) -- and stored as
+ * that integer in float32, which the host narrows back without loss.  Bits 0-7
+ * select experimental kernel variants in -DDCB_AB builds and are ignored otherwise. */
+#define DCB_FLAG_ROUND_INT 0x100
+
 typedef struct dcb_options {
     int32_t order; /* 0 nearest, 1 bilinear */
     int32_t blend; /* enum dcb_blend */
     int32_t path;  /* enum dcb_path */
-    int32_t flags; /* reserved, 0 */
+    int32_t flags; /* DCB_FLAG_* */
 } dcb_options;
 
 /* ---- library / device ---------------------------------------------------- */

@@ -146,10 +146,58 @@ def persp_cases():
     return cases
 
 
+def dtype_and_color_cases():
+    """Rows SURVEY.md 8(f) ranks 1 and 2: colour frames (H, W, C) through
+    ``util.unwarp_color_image_backward`` and integer images through the other
+    functions of the path (output dtype = input dtype)."""
+    f2 = [1.0, 3.0e-3]
+    f5 = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]
+    coef = [1.02, 0.01, -1.5, 0.005, 1.01, -0.8, 8e-5, -5e-5]
+    cases = []
+    n = 0
+    for shape, dtype, kind in (((40, 56, 3), "uint8", "noise"),
+                               ((33, 47, 4), "float32", "noise"),
+                               ((64, 50, 3), "uint16", "noise"),
+                               ((29, 31), "uint8", "noise"),
+                               ((36, 44, 2), "int16", "signed")):
+        for pad, pad_mode in ((0, "constant"), (3, "edge"),
+                              ((1, 2, 3, 4), "reflect")):
+            for order in (0, 1):
+                cases.append(dict(id="col%03d" % n, fn="color",
+                                  shape=list(shape), kind=kind, seed=1300 + n,
+                                  dtype=dtype, xc=shape[1] / 2 + 0.6,
+                                  yc=shape[0] / 2 - 1.3, fact=f5 if n % 2 else f2,
+                                  order=order,
+                                  pad=list(pad) if isinstance(pad, tuple) else pad,
+                                  pad_mode=pad_mode))
+                n += 1
+    for dtype, kind in (("uint8", "noise"), ("uint16", "noise"),
+                        ("int16", "signed"), ("int8", "signed")):
+        cases.append(dict(id="dty%03d" % n, fn="chunk", shape=[3, 52, 71],
+                          kind=kind, seed=1300 + n, dtype=dtype, xc=36.2,
+                          yc=25.4, fact=f2, start=5, stop=40))
+        n += 1
+        for order in (0, 1):
+            cases.append(dict(id="dty%03d" % n, fn="persp", shape=[57, 63],
+                              kind=kind, seed=1300 + n, dtype=dtype, coef=coef,
+                              order=order))
+            n += 1
+        cases.append(dict(id="dty%03d" % n, fn="combined", shape=[57, 63],
+                          kind=kind, seed=1300 + n, dtype=dtype, coef=coef,
+                          order=1, xc=31.9, yc=27.6, fact=f5))
+        n += 1
+        cases.append(dict(id="dty%03d" % n, fn="slice", shape=[3, 52, 71],
+                          kind=kind, seed=1300 + n, dtype=dtype, xc=36.2,
+                          yc=25.4, fact=f2, index=17))
+        n += 1
+    return cases
+
+
 def main():
     sys.path.insert(0, "/root/reference")
     sys.path.insert(0, ROOT)
     import discorpy.post.postprocessing as ref   # the real reference
+    import discorpy.util.utility as ref_util
     from oracle import oracle_np as orc
     os.makedirs(GOLDEN, exist_ok=True)
 
@@ -207,6 +255,38 @@ def main():
                 mat, c["xc"], c["yc"], c["fact"], c["coef"])
         check(r, o, c["id"])
         out[c["id"]] = r
+        meta.append(c)
+    for c in dtype_and_color_cases():
+        mat = make_input(c["kind"], tuple(c["shape"]), c["seed"], c["dtype"])
+        fn = c["fn"]
+        if fn == "color":
+            pad = tuple(c["pad"]) if isinstance(c["pad"], list) else c["pad"]
+            r = ref_util.unwarp_color_image_backward(
+                mat, c["xc"], c["yc"], c["fact"], order=c["order"], pad=pad,
+                pad_mode=c["pad_mode"])
+            o = orc.unwarp_color_image_backward(
+                mat, c["xc"], c["yc"], c["fact"], order=c["order"], pad=pad,
+                pad_mode=c["pad_mode"])
+        elif fn == "chunk":
+            r = ref.unwarp_chunk_slices_backward(mat, c["xc"], c["yc"], c["fact"],
+                                                 c["start"], c["stop"])
+            o = orc.unwarp_chunk_slices_backward(mat, c["xc"], c["yc"], c["fact"],
+                                                 c["start"], c["stop"])
+        elif fn == "slice":
+            r = ref.unwarp_slice_backward(mat, c["xc"], c["yc"], c["fact"],
+                                          c["index"])
+            o = orc.unwarp_slice_backward(mat, c["xc"], c["yc"], c["fact"],
+                                          c["index"])
+        elif fn == "persp":
+            r = ref.correct_perspective_image(mat, c["coef"], order=c["order"])
+            o = orc.correct_perspective_image(mat, c["coef"], order=c["order"])
+        else:
+            t = ref.unwarp_image_backward(mat, c["xc"], c["yc"], c["fact"])
+            r = ref.correct_perspective_image(t, c["coef"])
+            o = orc.unwarp_image_backward_perspective(
+                mat, c["xc"], c["yc"], c["fact"], c["coef"])
+        check(np.ascontiguousarray(r), np.ascontiguousarray(o), c["id"])
+        out[c["id"]] = np.ascontiguousarray(r)
         meta.append(c)
     np.savez_compressed(os.path.join(GOLDEN, "reference_outputs.npz"), **out)
     with open(os.path.join(GOLDEN, "cases.json"), "w") as f:

@@ -27,6 +27,7 @@ __all__ = [
     "sample", "unwarp_image_backward", "unwarp_slice_backward",
     "unwarp_chunk_slices_backward", "correct_perspective_image",
     "unwarp_image_backward_perspective", "mapping", "chunk_row_window",
+    "unwarp_color_image_backward",
 ]
 
 
@@ -187,7 +188,9 @@ def unwarp_slice_backward(mat3D, xcenter, ycenter, list_fact, index):
                                index)
     sino = np.zeros((depth, width), dtype=np.float32)
     for i in range(depth):
-        sino[i] = sample(mat3D[i], yd, xd, 1, out_dtype=np.float32)
+        # map_coordinates returns the slice's own dtype (:227-228), i.e. integer
+        # stacks are rounded to integers BEFORE the store into the float32 sinogram
+        sino[i] = sample(mat3D[i], yd, xd, 1)
     return sino
 
 
@@ -277,3 +280,36 @@ def unwarp_rows_scipy(mat, xcenter, ycenter, list_fact, row0, nrows, order=1,
     indices = np.reshape(yd, (-1, 1)), np.reshape(xd, (-1, 1))
     out = map_coordinates(mat, indices, order=order, mode=mode)
     return out.reshape((nrows, width))
+
+
+def unwarp_color_image_backward(mat, xcenter, ycenter, list_fact, order=1,
+                                mode="reflect", pad=0, pad_mode="constant"):
+    """``discorpy/util/utility.py:278-342`` for ``pad`` given as an int or a
+    (top, bottom, left, right) tuple (``:267-275``; ``pad=True`` needs
+    ``discorpy.proc`` and is outside the oracle): ``np.pad`` (``:315-319``),
+    centre shifted by the pad (``:321-322``), the image coordinate map
+    (``:323-330``, same expressions as ``postprocessing.py:138-145``) and one
+    ``map_coordinates`` per channel (``:332-341``).  The result keeps the
+    reference's layout: channels moved back to the last axis (a view)."""
+    mat = np.asarray(mat)
+    if isinstance(pad, bool):
+        if pad:
+            raise NotImplementedError("pad=True is outside the oracle")
+        t_pad = b_pad = l_pad = r_pad = 0
+    elif isinstance(pad, int):
+        t_pad = b_pad = l_pad = r_pad = pad
+    else:
+        t_pad, b_pad, l_pad, r_pad = pad
+    if mat.ndim == 2:
+        pad_width = [(t_pad, b_pad), (l_pad, r_pad)]
+    else:
+        pad_width = [(t_pad, b_pad), (l_pad, r_pad), (0, 0)]
+    mat_pad = np.pad(mat, pad_width, mode=pad_mode)
+    (height, width) = mat_pad.shape[:2]
+    yd, xd = radial_coords(height, width, xcenter + l_pad, ycenter + t_pad,
+                           list_fact)
+    if mat.ndim == 2:
+        return sample(mat_pad, yd, xd, order)
+    planes = [sample(mat_pad[:, :, i], yd, xd, order)
+              for i in range(mat_pad.shape[-1])]
+    return np.moveaxis(np.asarray(planes), 0, 2)

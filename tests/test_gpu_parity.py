@@ -24,7 +24,8 @@ import discorpy_b200.post.postprocessing as post
 
 pytestmark = pytest.mark.gpu
 
-CASES = [c for c in load_cases() if c.get("dtype", "float32") == "float32"]
+GPU_DTYPES = ("float32", "uint8", "int8", "uint16", "int16")
+CASES = [c for c in load_cases() if c.get("dtype", "float32") in GPU_DTYPES]
 FACT5 = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]
 COEF_DOT_05 = [1.00227490554, -2.99523692178e-05, 8.99519088e-08,
                -1.57066461911e-10, 8.08880211618e-14]
@@ -47,6 +48,12 @@ def _run_gpu(c, mat):
     if fn == "combined":
         return post.unwarp_image_backward_perspective(
             mat, c["xc"], c["yc"], c["fact"], c["coef"])
+    if fn == "color":
+        from discorpy_b200.util import utility as util
+        pad = tuple(c["pad"]) if isinstance(c["pad"], list) else c["pad"]
+        return np.ascontiguousarray(util.unwarp_color_image_backward(
+            mat, c["xc"], c["yc"], c["fact"], order=c["order"], pad=pad,
+            pad_mode=c["pad_mode"]))
     raise AssertionError(fn)
 
 
@@ -64,7 +71,8 @@ def _default_config():
 @pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
 def test_golden_vectors_bit_exact(case, path):
     post.config["path"] = path
-    mat = make_input(case["kind"], tuple(case["shape"]), case["seed"])
+    mat = make_input(case["kind"], tuple(case["shape"]), case["seed"],
+                     case.get("dtype", "float32"))
     got = _run_gpu(case, mat)
     want = golden_output(case["id"])
     assert got.dtype == want.dtype and got.shape == want.shape
@@ -216,11 +224,12 @@ def test_stack_paths_against_oracle():
     full = post.unwarp_chunk_slices_backward(stack, xc, yc, FACT5, 0, 639)
     for z in (0, 5):
         assert np.array_equal(full[z], post.unwarp_image_backward(stack[z], xc, yc, FACT5))
-    # uint16 stacks are widened exactly (output is float32 in the reference too)
+    # uint16 stacks: SciPy rounds every slice to uint16 before the reference stores it
+    # into the float32 sinogram (:227-228); the kernel rounds in fp64 the same way
     st16 = (stack[:2] * 60000).astype(np.uint16)
     got = post.unwarp_slice_backward(st16, xc, yc, FACT5, 300)
     want = orc.unwarp_slice_backward(st16, xc, yc, FACT5, 300)
-    assert int(np.count_nonzero(np.abs(got - want) > 1e-5 * 60000)) == 0
+    assert got.dtype == np.float32 and int(np.count_nonzero(got != want)) <= 1
 
 
 def test_device_resident_api_and_sharding_gives_same_bytes():
@@ -295,6 +304,28 @@ def test_edge_shapes_and_values():
     assert np.array_equal(got, want)
     with pytest.raises(NotImplementedError, match="dtype"):
         post.unwarp_image_backward(np.zeros((8, 8), np.float64), 4, 4, [1.0])
+
+
+def test_integer_frames_full_compare():
+    """uint8 camera frame (BASELINE config 1 geometry) and a uint16 colour frame:
+    output dtype = input dtype, SciPy's integer rounding, bit-exact."""
+    rng = np.random.default_rng(31)
+    frame = rng.integers(0, 256, (2160, 2560), dtype=np.uint8)
+    for order in (0, 1):
+        want = orc.unwarp_image_backward(frame, 588.692801577, 462.092631791,
+                                         COEF_DOT_05, order)
+        got = post.unwarp_image_backward(frame, 588.692801577, 462.092631791,
+                                         COEF_DOT_05, order=order)
+        assert got.dtype == np.uint8
+        assert int(np.count_nonzero(got != want)) <= 1
+    from discorpy_b200.util import utility as util
+    rgb = rng.integers(0, 65536, (600, 800, 3), dtype=np.uint16)
+    want = orc.unwarp_color_image_backward(rgb, 402.3, 297.8, FACT5, pad=16, pad_mode="edge")
+    before = dcb.launch_count()
+    got = util.unwarp_color_image_backward(rgb, 402.3, 297.8, FACT5, pad=16, pad_mode="edge")
+    assert dcb.launch_count() == before + 1          # all channels in one launch
+    assert got.dtype == np.uint16 and got.shape == want.shape == (632, 832, 3)
+    assert int(np.count_nonzero(got != want)) <= 1
 
 
 def test_tma_path_is_actually_taken_and_launches_counted():
