@@ -23,6 +23,7 @@ DCB_ERR_NO_DEVICE = -4
 BLEND_EXACT, BLEND_LERP64, BLEND_LERP32 = 0, 1, 2
 PATH_AUTO, PATH_DIRECT, PATH_TMA = 0, 1, 2
 FLAG_ROUND_INT = 0x100      # DCB_FLAG_ROUND_INT
+DTYPE_F32, DTYPE_U8, DTYPE_I8, DTYPE_U16, DTYPE_I16 = 0, 1, 2, 3, 4
 
 
 class DcbError(RuntimeError):
@@ -101,6 +102,8 @@ SIGNATURES = {
     "dcb_unwarp_image_backward_perspective_f32": [
         _vp, _vp, _vp, _i, _i, _sz, _sz, _sz, ctypes.POINTER(Radial),
         ctypes.POINTER(Persp), ctypes.POINTER(Options), _vp],
+    "dcb_unpack_hwc_to_planes_f32": [_vp, _i, _vp, _i, _i, _i, _sz, _sz, _vp],
+    "dcb_pack_planes_f32_to_hwc": [_vp, _vp, _i, _i, _i, _i, _sz, _sz, _vp],
     "dcb_fill_synthetic_f32": [_vp, _sz, _u64, _u64, _vp],
     "dcb_launch_count": [ctypes.POINTER(_u64)],
     "dcb_launch_count_reset": [],

@@ -12,6 +12,7 @@
 #include "remap.cuh"
 #include "remap_image.cuh"
 #include "remap_stack.cuh"
+#include "convert.cuh"
 #include "microbench.cuh"
 
 using namespace dcb;
@@ -959,6 +960,73 @@ int dcb_map_coordinates_f32(const float *src, float *dst, int H, int W, size_t s
                                          oob_count, o, (cudaStream_t)stream);
     return launch_map_coords<float>(src, dst, H, W, (long long)(src_pitch / 4), yd, xd, n_out,
                                     oob_count, o, (cudaStream_t)stream);
+}
+
+static size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case DCB_DTYPE_F32: return 4;
+        case DCB_DTYPE_U8:
+        case DCB_DTYPE_I8: return 1;
+        case DCB_DTYPE_U16:
+        case DCB_DTYPE_I16: return 2;
+        default: return 0;
+    }
+}
+
+static int check_hwc_args(const void *a, const void *b, int dtype, int H, int W, int C, size_t pitch,
+                          size_t plane) {
+    REQUIRE(a != nullptr && b != nullptr, "null pointer");
+    REQUIRE(dtype_size(dtype) != 0, "unknown dtype %d", dtype);
+    REQUIRE(H >= 1 && W >= 1 && C >= 1 && C <= 64, "bad shape (%d, %d, %d)", H, W, C);
+    REQUIRE(pitch >= (size_t)W * 4 && pitch % 4 == 0, "bad plane pitch %zu", pitch);
+    REQUIRE(plane >= pitch * (size_t)H && plane % 4 == 0, "bad plane stride %zu", plane);
+    return DCB_OK;
+}
+
+int dcb_unpack_hwc_to_planes_f32(const void *src_hwc, int dtype, float *dst_planes, int H, int W,
+                                 int C, size_t dst_pitch, size_t dst_plane_stride, void *stream) {
+    int rc = check_hwc_args(src_hwc, dst_planes, dtype, H, W, C, dst_pitch, dst_plane_stride);
+    if (rc) return rc;
+    DevProps props;
+    rc = device_props(&props);
+    if (rc != DCB_OK) return rc;
+    const long long npx = (long long)H * W;
+    const int grid = (int)std::min<long long>((npx + 255) / 256, (long long)props.sm_count * 16);
+    const long long pitch = (long long)(dst_pitch / 4), plane = (long long)(dst_plane_stride / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case DCB_DTYPE_U8: unpack_hwc_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)src_hwc, dst_planes, H, W, C, pitch, plane); break;
+        case DCB_DTYPE_I8: unpack_hwc_kernel<int8_t><<<grid, 256, 0, st>>>((const int8_t *)src_hwc, dst_planes, H, W, C, pitch, plane); break;
+        case DCB_DTYPE_U16: unpack_hwc_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)src_hwc, dst_planes, H, W, C, pitch, plane); break;
+        case DCB_DTYPE_I16: unpack_hwc_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t *)src_hwc, dst_planes, H, W, C, pitch, plane); break;
+        default: unpack_hwc_kernel<float><<<grid, 256, 0, st>>>((const float *)src_hwc, dst_planes, H, W, C, pitch, plane); break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return DCB_OK;
+}
+
+int dcb_pack_planes_f32_to_hwc(const float *src_planes, void *dst_hwc, int dtype, int H, int W, int C,
+                               size_t src_pitch, size_t src_plane_stride, void *stream) {
+    int rc = check_hwc_args(src_planes, dst_hwc, dtype, H, W, C, src_pitch, src_plane_stride);
+    if (rc) return rc;
+    DevProps props;
+    rc = device_props(&props);
+    if (rc != DCB_OK) return rc;
+    const long long npx = (long long)H * W;
+    const int grid = (int)std::min<long long>((npx + 255) / 256, (long long)props.sm_count * 16);
+    const long long pitch = (long long)(src_pitch / 4), plane = (long long)(src_plane_stride / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case DCB_DTYPE_U8: pack_hwc_kernel<uint8_t><<<grid, 256, 0, st>>>(src_planes, (uint8_t *)dst_hwc, H, W, C, pitch, plane); break;
+        case DCB_DTYPE_I8: pack_hwc_kernel<int8_t><<<grid, 256, 0, st>>>(src_planes, (int8_t *)dst_hwc, H, W, C, pitch, plane); break;
+        case DCB_DTYPE_U16: pack_hwc_kernel<uint16_t><<<grid, 256, 0, st>>>(src_planes, (uint16_t *)dst_hwc, H, W, C, pitch, plane); break;
+        case DCB_DTYPE_I16: pack_hwc_kernel<int16_t><<<grid, 256, 0, st>>>(src_planes, (int16_t *)dst_hwc, H, W, C, pitch, plane); break;
+        default: pack_hwc_kernel<float><<<grid, 256, 0, st>>>(src_planes, (float *)dst_hwc, H, W, C, pitch, plane); break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return DCB_OK;
 }
 
 int dcb_fill_synthetic_f32(float *dst, size_t n, uint64_t seed, uint64_t offset, void *stream) {

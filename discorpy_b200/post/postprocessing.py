@@ -348,20 +348,51 @@ def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
     return _narrow(dst.to_host(stream=stream), out_dtype)
 
 
-def _unwarp_planes(planes, xcenter, ycenter, list_fact, order):
-    """All rows of every plane of a host (C, H, W) array through the Z-stack
-    kernel with the image numerics (fp32-rounded coordinates): the geometry is
-    evaluated once and reused for every plane.  Used for colour images."""
-    (depth, height, width) = planes.shape
-    src_np, flags, out_dtype = _as_f32_image(planes)
+_DTYPE_CODES = {np.dtype(np.float32): _cabi.DTYPE_F32,
+                np.dtype(np.uint8): _cabi.DTYPE_U8,
+                np.dtype(np.int8): _cabi.DTYPE_I8,
+                np.dtype(np.uint16): _cabi.DTYPE_U16,
+                np.dtype(np.int16): _cabi.DTYPE_I16}
+
+
+def _unwarp_frame_hwc(frame, xcenter, ycenter, list_fact, order):
+    """A host (H, W, C) frame of any supported dtype through the Z-stack
+    kernel with the image numerics (fp32-rounded coordinates).  The frame
+    crosses PCIe in its own dtype; de-interleaving, widening and the way back
+    happen on the device, and all channels share ONE remap launch in which the
+    geometry is evaluated once per tile.  Used for colour images."""
+    (height, width, chan) = frame.shape
+    if frame.dtype not in _DTYPE_CODES:
+        raise NotImplementedError(
+            "dtype %s is not implemented on the CUDA path yet (float32, "
+            "uint8, int8, uint16 and int16 are); there is no CPU fallback"
+            % frame.dtype)
+    code = _DTYPE_CODES[frame.dtype]
+    flags = 0 if code == _cabi.DTYPE_F32 else _cabi.FLAG_ROUND_INT
+    raw = np.ascontiguousarray(frame)
     model = _cabi.make_radial(xcenter, ycenter, list_fact)
     stream = _dev.current_stream()
-    src = DeviceArray.from_host(src_np, stream)
-    dst = DeviceArray((depth, height, width))
-    _stack_call(src.ptr, dst, depth, height, width, 0, height, src.pitch,
-                src.slice_stride, 0, height, 1, model, stream, order=order,
-                flags=flags)
-    return _narrow(dst.to_host(stream=stream), out_dtype)
+    sh = _vp(stream.handle)
+    planes = DeviceArray((chan, height, width))
+    dst = DeviceArray((chan, height, width))
+    out = _dev.pinned_empty(raw.shape, raw.dtype)
+    with _dev.borrowed(max(raw.nbytes, 16)) as draw:
+        _cabi.call("dcb_h2d", _vp(draw.ptr), _vp(raw.ctypes.data), raw.nbytes,
+                   sh)
+        if not _dev.is_pinned(raw):
+            stream.sync()
+        _cabi.call("dcb_unpack_hwc_to_planes_f32", _vp(draw.ptr), code,
+                   _vp(planes.ptr), height, width, chan, planes.pitch,
+                   planes.slice_stride, sh)
+        _stack_call(planes.ptr, dst, chan, height, width, 0, height,
+                    planes.pitch, planes.slice_stride, 0, height, 1, model,
+                    stream, order=order, flags=flags)
+        _cabi.call("dcb_pack_planes_f32_to_hwc", _vp(dst.ptr), _vp(draw.ptr),
+                   code, height, width, chan, dst.pitch, dst.slice_stride, sh)
+        _cabi.call("dcb_d2h", _vp(out.ctypes.data), _vp(draw.ptr), raw.nbytes,
+                   sh)
+        stream.sync()
+    return out
 
 
 def _generate_perspective_map(mat, list_coef):

@@ -74,7 +74,8 @@ def unwarp_color_image_backward(mat, xcenter, ycenter, list_fact, order=1,
     Returns
     -------
     array_like
-        2D/3D array of the (padded) shape and the input dtype.
+        2D/3D array of the (padded) shape and the input dtype (C-contiguous;
+        the reference returns the same values as a moved-axis view).
     """
     mat = np.asarray(mat)
     (height, width) = mat.shape[:2]
@@ -95,6 +96,4 @@ def unwarp_color_image_backward(mat, xcenter, ycenter, list_fact, order=1,
                                            order=order, mode=mode)
     if num_dim != 3:
         raise ValueError("Input must be a 2D or 3D (H, W, C) array")
-    planes = np.ascontiguousarray(np.moveaxis(mat, 2, 0))
-    out = _post._unwarp_planes(planes, xcenter, ycenter, list_fact, order)
-    return np.moveaxis(out, 0, 2)
+    return _post._unwarp_frame_hwc(mat, xcenter, ycenter, list_fact, order)

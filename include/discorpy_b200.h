@@ -202,6 +202,19 @@ int dcb_unwarp_image_backward_perspective_f32(const float *src, float *dst, floa
                                               const dcb_persp *persp_host,
                                               const dcb_options *opt_host, void *stream);
 
+/* Pixel types of host frames; the remap kernels themselves work on float32. */
+enum dcb_dtype { DCB_DTYPE_F32 = 0, DCB_DTYPE_U8 = 1, DCB_DTYPE_I8 = 2, DCB_DTYPE_U16 = 3, DCB_DTYPE_I16 = 4 };
+
+/* Camera frames: dense interleaved (H, W, C) device array of `dtype` <-> C
+ * float32 planes (row pitch / plane stride in bytes).  Replaces the host-side
+ * per-channel slicing of discorpy/util/utility.py:337-341 (mat_pad[:, :, i])
+ * and the np.moveaxis at :341; integer samples widen exactly, and narrow back
+ * exactly after a DCB_FLAG_ROUND_INT remap.  C = 1 converts a 2-D image. */
+int dcb_unpack_hwc_to_planes_f32(const void *src_hwc, int dtype, float *dst_planes, int H, int W,
+                                 int C, size_t dst_pitch, size_t dst_plane_stride, void *stream);
+int dcb_pack_planes_f32_to_hwc(const float *src_planes, void *dst_hwc, int dtype, int H, int W,
+                               int C, size_t src_pitch, size_t src_plane_stride, void *stream);
+
 /* Benchmark input generator (no reference counterpart): dst[i] =
  * top24(splitmix64(seed ^ (offset + i))) / 2^24, float32 in [0,1).  Lets
  * multi-GB stacks be created in HBM without crossing PCIe. */
