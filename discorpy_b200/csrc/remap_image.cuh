@@ -81,6 +81,28 @@ __device__ __forceinline__ double dsqrt_nz(double s) {
     return fma(d, h, g);
 }
 
+// (nx / den, ny / den) with one reciprocal: MUFU.RCP64H seed (20 bits), two
+// Newton steps (-> ~2^-80 before rounding), then one Markstein correction per
+// quotient -- 10 fp64 operations + 1 MUFU for both quotients, correctly
+// rounded except in rare last-bit cases (like dsqrt: far below what can flip an
+// fp32-rounded coordinate).  A zero / non-finite / subnormal denominator takes
+// the IEEE division, so the projective singularity behaves like the reference.
+__device__ __forceinline__ void ddiv_pair(double nx, double ny, double den, double &qx, double &qy) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    double e = fma(-den, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-den, r, 1.0);
+    r = fma(r, e, r);
+    const double x0 = __dmul_rn(nx, r), y0 = __dmul_rn(ny, r);
+    qx = fma(fma(-den, x0, nx), r, x0);
+    qy = fma(fma(-den, y0, ny), r, y0);
+    if (!(fabs(r) < 1e300) || !(fabs(r) > 1e-300)) {  // den = 0, huge, tiny or NaN
+        qx = __ddiv_rn(nx, den);
+        qy = __ddiv_rn(ny, den);
+    }
+}
+
 // SciPy's order-1 value  sum_ij  rn(rn(m_ij * wy_i) * wx_j)  accumulated first
 // tap to last (DCB_BLEND_EXACT), with fewer operations but the same roundings:
 //   * wy_i and wx_j are fp32 fractions widened to fp64 (<= 24 significant
@@ -169,8 +191,10 @@ struct MapEval<MAP_PERSP, NT> {
             const double den = __dadd_rn(__dadd_rn(c7x[k], c8y), 1.0);
             const double nx = __dadd_rn(__dadd_rn(c1x[k], c2y), p.per.c[2]);
             const double ny = __dadd_rn(__dadd_rn(c4x[k], c5y), p.per.c[5]);
-            xf[k] = __double2float_rn(__ddiv_rn(nx, den));
-            yf[k] = __double2float_rn(__ddiv_rn(ny, den));
+            double qx, qy;
+            ddiv_pair(nx, ny, den, qx, qy);
+            xf[k] = __double2float_rn(qx);
+            yf[k] = __double2float_rn(qy);
         }
     }
 };
