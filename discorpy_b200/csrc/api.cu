@@ -301,7 +301,7 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
         need_h = std::min<long long>(need_h, src_rows);
         bw = (int)((need_w + 3) / 4 * 4);
         bh = (int)need_h;
-        const int max_stage = (TH >= 32 ? 24 : 14) * 1024;
+        const int max_stage = (TH >= 32 ? 22 : 14) * 1024;  // 5 stages x 2 CTAs within 227 KB
         if (bw > 256 || bh > 256 || (long long)bw * bh * 4 > max_stage) {
             // strong magnification somewhere: stage a modest box, tiles whose
             // probes do not fit are gathered straight from global memory
@@ -339,11 +339,11 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
         CUDA_TRY(cudaFuncSetAttribute((const void *)sel.kern,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)sel.kern, kThreads,
-                                                           smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)sel.kern,
+                                                           kImgThreads, smem));
     if (occ < 1) return fail(DCB_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
     const int grid = (int)std::min<long long>(ntiles, (long long)occ * props.sm_count);
-    sel.kern<<<grid, kThreads, smem, stream>>>(p, tmap);
+    sel.kern<<<grid, kImgThreads, smem, stream>>>(p, tmap);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     g_last_plan = {staged ? DCB_PATH_TMA : DCB_PATH_DIRECT, bw, bh, grid, (int)smem};
@@ -1108,10 +1108,10 @@ int dcb_selftest_tma(const float *src, int D, int H, int W, size_t pitch, size_t
 
 int dcb_microbench(int which, double *gops) {
     REQUIRE(gops != nullptr, "gops is NULL");
-    REQUIRE(which >= 0 && which <= 9, "which must be 0..9");
+    REQUIRE(which >= 0 && which <= 29, "which must be 0..29");
     double *sink = nullptr;
     CUDA_TRY(cudaMalloc(&sink, 2 * sizeof(double)));
-    if (which >= 6) {  // latency probes: cycles per dependent operation
+    if (which >= 6 && which <= 9) {  // latency probes: cycles per dependent operation
         switch (which) {
             case 6: microbench_latency_kernel<6><<<1, 32>>>(sink); break;
             case 7: microbench_latency_kernel<7><<<1, 32>>>(sink); break;
@@ -1137,6 +1137,26 @@ int dcb_microbench(int which, double *gops) {
             case 1: microbench_kernel<1><<<grid, block>>>(sink, 1.0); break;
             case 2: microbench_kernel<2><<<grid, block>>>(sink, 1.0); break;
             case 3: microbench_coords_kernel<<<grid, block>>>(sink, 2050.37, 2040.81); break;
+            case 10: microbench_kernel<10><<<grid, block>>>(sink, 1.0); break;
+            case 20: microbench_kernel<20><<<grid, block>>>(sink, 1.0); break;
+            case 21: microbench_kernel<21><<<grid, block>>>(sink, 1.0); break;
+            case 22: microbench_kernel<22><<<grid, block>>>(sink, 1.0); break;
+            case 23: microbench_kernel<23><<<grid, block>>>(sink, 1.0); break;
+            case 24: microbench_mix_kernel<24><<<grid, block>>>(sink, 1.0); break;
+            case 25: microbench_mix_kernel<25><<<grid, block>>>(sink, 1.0); break;
+            case 26: microbench_mix_kernel<26><<<grid, block>>>(sink, 1.0); break;
+            case 27: microbench_mix_kernel<27><<<grid, block>>>(sink, 1.0); break;
+            case 28: microbench_mix_kernel<28><<<grid, block>>>(sink, 1.0); break;
+            case 29: microbench_mix_kernel<29><<<grid, block>>>(sink, 1.0); break;
+            case 11: case 12: case 13: case 14: case 15: case 16: case 17: case 18: {
+                // the coordinate evaluation at 1..8 resident CTAs (8..64 warps) per SM
+                const int ctas = which - 10;
+                const size_t sm = (size_t)(220 * 1024) / ctas - 2048;
+                CUDA_TRY(cudaFuncSetAttribute((const void *)microbench_coords_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                microbench_coords_kernel<<<grid, block, sm>>>(sink, 2050.37, 2040.81);
+                break;
+            }
             case 4: microbench_kernel<4><<<grid, block>>>(sink, 1.0); break;
             case 5: microbench_kernel<5><<<grid, block>>>(sink, 1.0); break;
         }
@@ -1151,8 +1171,14 @@ int dcb_microbench(int which, double *gops) {
     cudaEventDestroy(e1);
     cudaFree(sink);
     if (which == 1) ops_per_thread *= 2;       // two conversions per step
-    if (which == 3) ops_per_thread = (double)kMbIters * 4;  // pixels
+    if (which == 3 || (which >= 11 && which <= 18)) ops_per_thread = (double)kMbIters * 4;  // pixels
     if (which == 5) ops_per_thread *= 3;       // DFMA + two conversions
+    if (which >= 24 && which <= 29) {  // mixes: cycles per warp-level group on one SM sub-partition
+        const double groups = (double)kMbIters * grid * block / 32.0;          // warp-groups issued
+        const double smsp_cycles = best * 1e-3 * 1.965e9 * 148 * 4;             // at 1965 MHz
+        *gops = smsp_cycles / groups;
+        return DCB_OK;
+    }
     *gops = ops_per_thread * grid * block / (best * 1e-3) / 1e9;
     return DCB_OK;
 }

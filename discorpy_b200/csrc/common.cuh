@@ -35,6 +35,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
                  : "memory");
 }
 
+// one arrival (release) on an mbarrier of this CTA
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // Blocking wait on a phase parity.  try_wait suspends in hardware for a
 // bounded time; the outer loop is bounded too so that a mis-programmed copy
 // traps instead of hanging the GPU.

@@ -31,6 +31,17 @@ __global__ void __launch_bounds__(256) microbench_kernel(double *sink, double se
                 asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(d[c]) : "d"(d[c]));
             } else if (WHICH == 4) {
                 f[c] = fmaf(f[c], 0.999999f, 1e-7f);
+            } else if (WHICH == 10) {
+                // DFMA with three register operands (what the kernels issue)
+                d[c] = fma(d[c], d[(c + 3) % kMbChains], d[(c + 5) % kMbChains]);
+            } else if (WHICH == 20) {   // DFMA, two registers + constant (Horner step)
+                d[c] = fma(d[c], d[(c + 3) % kMbChains], 1e-7);
+            } else if (WHICH == 21) {   // DMUL, two registers
+                d[c] = __dmul_rn(d[c], d[(c + 3) % kMbChains]);
+            } else if (WHICH == 22) {   // DADD, two registers
+                d[c] = __dadd_rn(d[c], d[(c + 3) % kMbChains]);
+            } else if (WHICH == 23) {   // DFMA, two distinct registers, one used twice
+                d[c] = fma(d[c], d[(c + 3) % kMbChains], d[c]);
             } else if (WHICH == 5) {
                 d[c] = fma(d[c], 0.999999, 1e-7);
                 double w;
@@ -42,6 +53,53 @@ __global__ void __launch_bounds__(256) microbench_kernel(double *sink, double se
     double acc = 0;
 #pragma unroll
     for (int c = 0; c < kMbChains; ++c) acc += d[c] + f[c];
+    if (acc == 123.456) sink[0] = acc;
+}
+
+// which 24..29: does a slow-pipe instruction block the issue port?  One group per
+// iteration, all operations independent across 8 chains; the host reports the
+// cycles one warp-level group costs an SM sub-partition.
+//   24: 16 FFMA                       25: 2 F2F (f32->f64->f32) + 16 FFMA
+//   26: 1 MUFU.RSQ64H + 8 FFMA        27: 4 DFMA + 8 FFMA
+//   28: 2 F2F + 8 DFMA                29: 2 F2F alone
+template <int WHICH>
+__global__ void __launch_bounds__(256) microbench_mix_kernel(double *sink, double seed) {
+    float f[16];
+    double d[8];
+    float g = (float)seed + threadIdx.x * 1e-3f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) f[c] = (float)seed + c + threadIdx.x * 1e-3f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) d[c] = seed + c + threadIdx.x * 1e-3;
+    for (int it = 0; it < kMbIters; ++it) {
+        if (WHICH == 24 || WHICH == 25) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) f[c] = fmaf(f[c], 0.999999f, 1e-7f);
+        }
+        if (WHICH == 26 || WHICH == 27) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) f[c] = fmaf(f[c], 0.999999f, 1e-7f);
+        }
+        if (WHICH == 25 || WHICH == 28 || WHICH == 29) {
+            double w;
+            asm volatile("cvt.f64.f32 %0, %1;" : "=d"(w) : "f"(g));
+            asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(g) : "d"(w));
+        }
+        if (WHICH == 26) asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(d[0]) : "d"(d[0]));
+        if (WHICH == 27) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) d[c] = fma(d[c], 0.999999, 1e-7);
+        }
+        if (WHICH == 28) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) d[c] = fma(d[c], 0.999999, 1e-7);
+        }
+    }
+    double acc = g;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc += f[c];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc += d[c];
     if (acc == 123.456) sink[0] = acc;
 }
 

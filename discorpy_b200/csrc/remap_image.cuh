@@ -225,28 +225,39 @@ struct ImageKernelTraits {
     static constexpr bool kWide = (ORDER == 1 && BLEND != DCB_BLEND_LERP32);
 };
 
-constexpr int kBoxRing = 16;  // tile boxes kept in shared memory (placed 8 tiles ahead)
+constexpr int kBoxRing = 4;       // tile boxes in flight between the producer and the samplers
+constexpr int kImgThreads = kThreads + 32;  // 8 sampling warps + 1 producer warp
 
-// Shared-memory layout (host side must agree, see image_smem_bytes in api.cu):
+// Shared-memory layout (host side must agree, see plan_and_launch_image in api.cu):
 //   WIDE : [raw][wide 0][wide 1][tail]      raw = stage_bytes, wide = 2 * stage_bytes
 //   !WIDE: [raw 0][raw 1][tail]
-//   tail : uint64_t full[2]; TileBox boxes[kBoxRing]
-__host__ __device__ constexpr size_t image_tail_bytes() { return 16 + kBoxRing * sizeof(TileBox); }
+//   tail : uint64_t raw_full[2], data_full[2], data_empty[2]; TileBox boxes[kBoxRing]
+__host__ __device__ constexpr size_t image_tail_bytes() { return 48 + kBoxRing * sizeof(TileBox); }
 
 // NT > 0: number of polynomial terms known at compile time (coefficients become
 // constant-bank operands of the DFMAs); NT == 0: any p.rad.n through a switch.
 // TH: tile height (16 or 32 rows); MINB: resident CTAs per SM the register
 // allocation is held to.
+//
+// Warp-specialised: warps 0..7 only evaluate coordinates and sample; warp 8 (the
+// producer) places the source boxes, issues the TMA loads and -- for the fp64
+// blends -- widens each landed float32 box into one of two float64 tiles.  The
+// hand-over is by mbarriers (data_full: producer -> samplers, data_empty: one
+// arrival per sampling warp -> producer), so there is no CTA-wide barrier in
+// the tile loop and the XU-bound widening runs concurrently with the
+// fp64-bound sampling instead of in lock-step phases.
 template <int MAP, int ORDER, int BLEND, int NT, int TH, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
+__global__ void __launch_bounds__(kImgThreads, MINB)
     remap_image_kernel(const __grid_constant__ ImageParams p,
                        const __grid_constant__ CUtensorMap tmap) {
     constexpr bool WIDE = ImageKernelTraits<ORDER, BLEND>::kWide;
-    constexpr int RPW = TH / kWarps;  // rows per warp and tile
+    constexpr int RPW = TH / kWarps;  // rows per sampling warp and tile
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *tail = smem + (WIDE ? 5 : 2) * (size_t)p.stage_bytes;
-    uint64_t *full = reinterpret_cast<uint64_t *>(tail);       // [2]
-    TileBox *boxes = reinterpret_cast<TileBox *>(tail + 16);   // [kBoxRing]
+    uint64_t *raw_full = reinterpret_cast<uint64_t *>(tail);         // [2] TMA bytes landed
+    uint64_t *data_full = raw_full + 2;                              // [2] WIDE: float64 tile ready
+    uint64_t *data_empty = raw_full + 4;                             // [2] tile buffer released
+    TileBox *boxes = reinterpret_cast<TileBox *>(tail + 48);         // [kBoxRing]
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -260,86 +271,112 @@ __global__ void __launch_bounds__(kThreads, MINB)
     const int n = (int)((long long)(blockIdx.x + 1) * p.ntiles / gridDim.x) - t0;
 
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&raw_full[b], 1);
+            mbar_init(&data_full[b], 1);
+            mbar_init(&data_empty[b], kWarps);
+        }
         fence_mbar_init();
         if (staged) tma_prefetch_desc(&tmap);
     }
+    __syncthreads();
 
-    // ---- one warp: place the source box of local tile k from 9 probe points ----
-    auto place_box = [&](int k) {
-        const int t = t0 + k;
-        const int txi = t / p.tiles_y, tyi = t - txi * p.tiles_y;
-        const int x_lo = txi * kTileW, y_lo = p.row0 + tyi * TH;
-        const int x_hi = min(x_lo + kTileW - 1, wmax), y_hi = min(y_lo + TH - 1, y_end - 1);
-        const int q = lane % 9;
-        const int px = x_lo + ((x_hi - x_lo) * (q % 3)) / 2;
-        const int py = y_lo + ((y_hi - y_lo) * (q / 3)) / 2;
-        float xf, yf;
-        map_point<MAP>(p, px, py, xf, yf);
-        const int mnx = __reduce_min_sync(0xffffffffu, (int)xf);
-        const int mny = __reduce_min_sync(0xffffffffu, (int)yf);
-        const int mxx = __reduce_max_sync(0xffffffffu, (int)xf);
-        const int mxy = __reduce_max_sync(0xffffffffu, (int)yf);
-        // one pixel of slack around the probes for curvature inside the tile
-        const int bx0 = max(mnx - 1, 0) & ~3;
-        const int by0 = min(max(mny - 1, p.yorg), p.ylast);
-        const bool use = staged && (mxx + 2 - bx0 < p.bw) && (mxy + 2 - by0 < p.bh);
-        if (lane == 0) boxes[k % kBoxRing] = TileBox{bx0, by0, use ? 1 : 0, 0};
-    };
-    // ---- one thread: start the copy of local tile k's box into a raw stage ------
-    auto issue_tma = [&](int k, int stage) {
-        const TileBox b = boxes[k % kBoxRing];
-        if (b.use) {
-            mbar_expect_tx(&full[stage], p.box_bytes);
-            tma_load_3d(smem + (size_t)stage * p.stage_bytes, &tmap, b.bx0, b.by0 - p.yorg, 0,
-                        &full[stage]);
-        }
-    };
-    // ---- all threads: float32 box in the raw stage -> float64 tile `buf` --------
-    auto widen = [&](int buf) {
-        const float4 *src4 = reinterpret_cast<const float4 *>(smem);
-        double2 *dst2 = reinterpret_cast<double2 *>(smem + (size_t)(1 + 2 * buf) * p.stage_bytes);
-        const int n4 = (p.bw * p.bh) >> 2;  // bw % 4 == 0
-        int i = threadIdx.x;
-        for (; i + kThreads < n4; i += 2 * kThreads) {
-            const float4 u = src4[i], v = src4[i + kThreads];
-            dst2[2 * i] = make_double2((double)u.x, (double)u.y);
-            dst2[2 * i + 1] = make_double2((double)u.z, (double)u.w);
-            dst2[2 * (i + kThreads)] = make_double2((double)v.x, (double)v.y);
-            dst2[2 * (i + kThreads) + 1] = make_double2((double)v.z, (double)v.w);
-        }
-        if (i < n4) {
-            const float4 u = src4[i];
-            dst2[2 * i] = make_double2((double)u.x, (double)u.y);
-            dst2[2 * i + 1] = make_double2((double)u.z, (double)u.w);
-        }
-    };
-
-    uint32_t cnt0 = 0, cnt1 = 0;  // fills consumed per raw stage (CTA-uniform)
-    for (int k = warp; k < min(n, 8); k += kWarps) place_box(k);
-    __syncthreads();  // mbarriers initialised, boxes 0..7 placed
-    if (WIDE) {
-        if (n > 0) {
-            if (threadIdx.x == 0) issue_tma(0, 0);
-            if (boxes[0].use) {
-                mbar_wait(&full[0], cnt0 & 1u);
-                ++cnt0;
-                widen(0);
+    if (warp == kWarps) {
+        // =========================== producer warp ===================================
+        // place the source box of local tile k from 9 probe points (all 32 lanes)
+        auto place_box = [&](int k) -> bool {
+            const int t = t0 + k;
+            const int txi = t / p.tiles_y, tyi = t - txi * p.tiles_y;
+            const int x_lo = txi * kTileW, y_lo = p.row0 + tyi * TH;
+            const int x_hi = min(x_lo + kTileW - 1, wmax), y_hi = min(y_lo + TH - 1, y_end - 1);
+            const int q = lane % 9;
+            const int px = x_lo + ((x_hi - x_lo) * (q % 3)) / 2;
+            const int py = y_lo + ((y_hi - y_lo) * (q / 3)) / 2;
+            float xf, yf;
+            map_point<MAP>(p, px, py, xf, yf);
+            const int mnx = __reduce_min_sync(0xffffffffu, (int)xf);
+            const int mny = __reduce_min_sync(0xffffffffu, (int)yf);
+            const int mxx = __reduce_max_sync(0xffffffffu, (int)xf);
+            const int mxy = __reduce_max_sync(0xffffffffu, (int)yf);
+            // one pixel of slack around the probes for curvature inside the tile
+            const int bx0 = max(mnx - 1, 0) & ~3;
+            const int by0 = min(max(mny - 1, p.yorg), p.ylast);
+            const bool use = staged && (mxx + 2 - bx0 < p.bw) && (mxy + 2 - by0 < p.bh);
+            if (lane == 0) boxes[k % kBoxRing] = TileBox{bx0, by0, use ? 1 : 0, 0};
+            __syncwarp();
+            return use;
+        };
+        // lane 0: start the copy of local tile k's box into raw stage `st`
+        auto issue_tma = [&](int k, int st) {
+            const TileBox b = boxes[k % kBoxRing];
+            mbar_expect_tx(&raw_full[st], p.box_bytes);
+            tma_load_3d(smem + (size_t)st * p.stage_bytes, &tmap, b.bx0, b.by0 - p.yorg, 0,
+                        &raw_full[st]);
+        };
+        if (WIDE) {
+            uint32_t nraw = 0;  // TMA fills consumed from the single raw stage
+            bool use_cur = n > 0 ? place_box(0) : false;
+            if (use_cur && lane == 0) issue_tma(0, 0);
+            for (int j = 0; j < n; ++j) {
+                const int b = j & 1;
+                // the next box is placed while this tile's copy is in flight
+                const bool use_next = (j + 1 < n) ? place_box(j + 1) : false;
+                if (use_cur) {
+                    mbar_wait(&raw_full[0], nraw & 1u);
+                    ++nraw;
+                }
+                if (j >= 2) mbar_wait(&data_empty[b], (uint32_t)((j >> 1) - 1) & 1u);
+                if (use_cur) {
+                    // float32 box -> float64 tile b (exact); bw % 4 == 0
+                    const float4 *src4 = reinterpret_cast<const float4 *>(smem);
+                    double2 *dst2 =
+                        reinterpret_cast<double2 *>(smem + (size_t)(1 + 2 * b) * p.stage_bytes);
+                    const int n4 = (p.bw * p.bh) >> 2;
+                    int e = lane;
+                    for (; e + 96 < n4; e += 128) {
+                        const float4 u0 = src4[e], u1 = src4[e + 32], u2 = src4[e + 64],
+                                     u3 = src4[e + 96];
+                        dst2[2 * e] = make_double2((double)u0.x, (double)u0.y);
+                        dst2[2 * e + 1] = make_double2((double)u0.z, (double)u0.w);
+                        dst2[2 * e + 64] = make_double2((double)u1.x, (double)u1.y);
+                        dst2[2 * e + 65] = make_double2((double)u1.z, (double)u1.w);
+                        dst2[2 * e + 128] = make_double2((double)u2.x, (double)u2.y);
+                        dst2[2 * e + 129] = make_double2((double)u2.z, (double)u2.w);
+                        dst2[2 * e + 192] = make_double2((double)u3.x, (double)u3.y);
+                        dst2[2 * e + 193] = make_double2((double)u3.z, (double)u3.w);
+                    }
+                    for (; e < n4; e += 32) {
+                        const float4 u = src4[e];
+                        dst2[2 * e] = make_double2((double)u.x, (double)u.y);
+                        dst2[2 * e + 1] = make_double2((double)u.z, (double)u.w);
+                    }
+                }
+                __syncwarp();  // every lane's stores precede the arrive; raw stage is free
+                if (lane == 0) {
+                    if (use_next) issue_tma(j + 1, 0);
+                    mbar_arrive(&data_full[b]);
+                }
+                use_cur = use_next;
+            }
+        } else {
+            // raw stage k&1 doubles as the data buffer: the samplers wait on raw_full[k&1];
+            // the producer runs at most two tiles ahead of the slowest sampling warp
+            for (int k = 0; k < n; ++k) {
+                const int b = k & 1;
+                const bool use = place_box(k);
+                if (k >= 2) mbar_wait(&data_empty[b], (uint32_t)((k >> 1) - 1) & 1u);
+                if (lane == 0) {
+                    if (use)
+                        issue_tma(k, b);
+                    else
+                        mbar_arrive(&raw_full[b]);
+                }
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0 && n > 1) issue_tma(1, 0);
-    } else {
-        if (threadIdx.x == 0) {
-            if (n > 0) issue_tma(0, 0);
-            if (n > 1) issue_tma(1, 1);
-        }
-#ifdef DCB_AB
-        if ((p.dbg & 4) && n > 0 && boxes[0].use) mbar_wait(&full[0], 0);
-#endif
+        return;
     }
 
+    // ============================== sampling warps ====================================
     int txi = t0 / p.tiles_y, tyi = t0 - txi * p.tiles_y;
     MapEval<MAP, NT> ev;
     {
@@ -350,22 +387,9 @@ __global__ void __launch_bounds__(kThreads, MINB)
     }
 
     for (int i = 0; i < n; ++i) {
-#ifdef DCB_AB
-        const bool compute_only = (p.dbg & 4) != 0;  // ablation: tile 0's box serves every tile
-        const TileBox box = boxes[compute_only ? 0 : i % kBoxRing];
-#else
-        constexpr bool compute_only = false;
+        // tile i is ready: WIDE -> float64 tile i&1 written by the producer; !WIDE -> raw stage landed
+        mbar_wait(WIDE ? &data_full[i & 1] : &raw_full[i & 1], (uint32_t)(i >> 1) & 1u);
         const TileBox box = boxes[i % kBoxRing];
-#endif
-        if (!WIDE && box.use && !compute_only) {  // raw stage i & 1 holds this tile's box
-            if (i & 1) {
-                mbar_wait(&full[1], cnt1 & 1u);
-                ++cnt1;
-            } else {
-                mbar_wait(&full[0], cnt0 & 1u);
-                ++cnt0;
-            }
-        }
         // ---- sample tile i ---------------------------------------------------------
         {
             const int x_base = txi * kTileW + lane;
@@ -377,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
             const int lim_x = box.use ? min(p.bw - 1, wmax - box.bx0) : 0;
             const int lim_y = box.use ? min(p.bh - 1, p.ylast - box.by0) : 0;
             const int bw = p.bw;
-            const int sb = compute_only ? 0 : (i & 1);
+            const int sb = i & 1;
             const float *rawt =
                 reinterpret_cast<const float *>(smem + (size_t)sb * p.stage_bytes);
             const double *widet = reinterpret_cast<const double *>(
@@ -388,23 +412,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
 #pragma unroll 1
             for (int j = 0; j < nrow; ++j, yd += 1.0, orow += p.dst_pitch) {
                 float xf[kCols], yf[kCols];
-#ifdef DCB_AB
-                if (p.dbg & 2) {  // ablation: no fp64 coordinate evaluation
-#pragma unroll
-                    for (int k = 0; k < kCols; ++k) {
-                        xf[k] = (float)(box.bx0 + 2 + lane + 32 * k) + 0.3f;
-                        yf[k] = (float)(box.by0 + 2 + warp * RPW + j) + 0.6f;
-                    }
-                } else
-#endif
-                    ev.row(p, yd, xf, yf);
-#ifdef DCB_AB
-                if (p.dbg & 1) {  // ablation: no sampling
-#pragma unroll
-                    for (int k = 0; k < kCols; ++k) __stcs(orow + 32 * k, xf[k] + yf[k]);
-                    continue;
-                }
-#endif
+                ev.row(p, yd, xf, yf);
                 float tfx[kCols], tfy[kCols];
                 int ix[kCols], iy[kCols];
                 bool ok = true;
@@ -414,12 +422,6 @@ __global__ void __launch_bounds__(kThreads, MINB)
                     tfy[k] = floor_magic(yf[k]);
                     ix[k] = __float_as_int(tfx[k]) - magic_x;  // x0 - bx0
                     iy[k] = __float_as_int(tfy[k]) - magic_y;  // y0 - by0
-#ifdef DCB_AB
-                    if (compute_only) {
-                        ix[k] = 2 + lane + 32 * k;
-                        iy[k] = 2 + warp * RPW + j;
-                    }
-#endif
                     ok = ok && ((unsigned)ix[k] < (unsigned)lim_x) &&
                          ((unsigned)iy[k] < (unsigned)lim_y);
                 }
@@ -445,6 +447,8 @@ __global__ void __launch_bounds__(kThreads, MINB)
                             const double *q = widet + idx;
                             const double a = q[0], b = q[1];
                             const double c = q[bw], d = q[bw + 1];
+                            // (an integer-pipe widening of tx, ty -- one IMAD.WIDE + a select for
+                            // zero -- was measured: 64.7 us instead of 61.7 us; F2F stays)
                             const double wx1 = (double)tx, wy1 = (double)ty;
                             if (BLEND == DCB_BLEND_LERP64) {
                                 const double top = fma(b - a, wx1, a);
@@ -486,26 +490,9 @@ __global__ void __launch_bounds__(kThreads, MINB)
                 }
             }
         }
-        // ---- while slower warps still sample: widen tile i+1, place boxes ahead ------
-        if (compute_only) {
-            if (++tyi == p.tiles_y) {
-                tyi = 0;
-                ++txi;
-                int xs[kCols];
-#pragma unroll
-                for (int k = 0; k < kCols; ++k) xs[k] = min(txi * kTileW + lane + 32 * k, wmax);
-                ev.set_columns(p, xs);
-            }
-            continue;
-        }
-        if (WIDE && i + 1 < n && boxes[(i + 1) % kBoxRing].use) {
-            mbar_wait(&full[0], cnt0 & 1u);
-            ++cnt0;
-            widen((i + 1) & 1);
-        }
-        if ((i & 7) == 0 && i + 8 + warp < n) place_box(i + 8 + warp);
-        __syncthreads();  // tile i sampled by all, wide[(i+1)&1] complete, raw stage free
-        if (threadIdx.x == 0 && i + 2 < n) issue_tma(i + 2, WIDE ? 0 : (i & 1));
+        // this warp is done with buffer i&1 (and with boxes[i % kBoxRing])
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&data_empty[i & 1]);
         // next tile of the column-major order
         if (++tyi == p.tiles_y) {
             tyi = 0;

@@ -39,10 +39,6 @@ constexpr int kStkRows = kStkTileH / kWarps;  // 2 rows per warp
 constexpr int kStkPx = kStkRows * kCols;      // 8 pixels per thread
 constexpr int kStkMaxStages = 8;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // How the per-pixel sampling state is kept across the slices of a chunk.
 template <int ORDER, int BLEND, bool ROUND32>
 struct StackWeights {
