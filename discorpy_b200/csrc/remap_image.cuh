@@ -225,8 +225,15 @@ struct ImageKernelTraits {
     static constexpr bool kWide = (ORDER == 1 && BLEND != DCB_BLEND_LERP32);
 };
 
+// float32 box in raw stage 0 -> float64 tile `buf` (exact); producer warp `part`
+// of kImgProducers converts every kImgProducers-th group of 32 float4.  bw % 4 == 0.
+struct ImageParams;
+__device__ __forceinline__ void widen_part(const ImageParams &p, unsigned char *smem, int buf,
+                                           int part, int lane);
+
 constexpr int kBoxRing = 4;       // tile boxes in flight between the producer and the samplers
-constexpr int kImgThreads = kThreads + 32;  // 8 sampling warps + 1 producer warp
+constexpr int kImgProducers = 2;                             // producer warps
+constexpr int kImgThreads = kThreads + 32 * kImgProducers;   // 8 sampling warps + the producers
 
 // Shared-memory layout (host side must agree, see plan_and_launch_image in api.cu):
 //   WIDE : [raw][wide 0][wide 1][tail]      raw = stage_bytes, wide = 2 * stage_bytes
@@ -241,7 +248,9 @@ __host__ __device__ constexpr size_t image_tail_bytes() { return 48 + kBoxRing *
 //
 // Warp-specialised: warps 0..7 only evaluate coordinates and sample; warp 8 (the
 // producer) places the source boxes, issues the TMA loads and -- for the fp64
-// blends -- widens each landed float32 box into one of two float64 tiles.  The
+// blends, together with warp 9 -- widens each landed float32 box into one of two
+// float64 tiles (one warp alone could not keep ahead of the samplers: with it
+// they spent 26 % of their time waiting, profiles/r1/ncu_summary_v6.txt).  The
 // hand-over is by mbarriers (data_full: producer -> samplers, data_empty: one
 // arrival per sampling warp -> producer), so there is no CTA-wide barrier in
 // the tile loop and the XU-bound widening runs concurrently with the
@@ -281,6 +290,26 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     }
     __syncthreads();
 
+    if (warp > kWarps) {
+        // ====================== second producer warp: widening only =====================
+        if (WIDE) {
+            uint32_t nraw = 0;
+            for (int j = 0; j < n; ++j) {
+                const int b = j & 1;
+                // tile j's box slot was published before its copy was started (see warp 8)
+                if (j >= 2) mbar_wait(&data_empty[b], (uint32_t)((j >> 1) - 1) & 1u);
+                // the leader tells through the named barrier whether this tile is staged
+                asm volatile("bar.sync 1, 64;" ::: "memory");   // (A) box j published / decided
+                if (boxes[j % kBoxRing].use) {
+                    mbar_wait(&raw_full[0], nraw & 1u);
+                    ++nraw;
+                    widen_part(p, smem, b, 1, lane);
+                }
+                asm volatile("bar.sync 1, 64;" ::: "memory");   // (B) both halves written, raw free
+            }
+        }
+        return;
+    }
     if (warp == kWarps) {
         // =========================== producer warp ===================================
         // place the source box of local tile k from 9 probe points (all 32 lanes)
@@ -321,37 +350,14 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                 const int b = j & 1;
                 // the next box is placed while this tile's copy is in flight
                 const bool use_next = (j + 1 < n) ? place_box(j + 1) : false;
+                if (j >= 2) mbar_wait(&data_empty[b], (uint32_t)((j >> 1) - 1) & 1u);
+                asm volatile("bar.sync 1, 64;" ::: "memory");   // (A)
                 if (use_cur) {
                     mbar_wait(&raw_full[0], nraw & 1u);
                     ++nraw;
+                    widen_part(p, smem, b, 0, lane);
                 }
-                if (j >= 2) mbar_wait(&data_empty[b], (uint32_t)((j >> 1) - 1) & 1u);
-                if (use_cur) {
-                    // float32 box -> float64 tile b (exact); bw % 4 == 0
-                    const float4 *src4 = reinterpret_cast<const float4 *>(smem);
-                    double2 *dst2 =
-                        reinterpret_cast<double2 *>(smem + (size_t)(1 + 2 * b) * p.stage_bytes);
-                    const int n4 = (p.bw * p.bh) >> 2;
-                    int e = lane;
-                    for (; e + 96 < n4; e += 128) {
-                        const float4 u0 = src4[e], u1 = src4[e + 32], u2 = src4[e + 64],
-                                     u3 = src4[e + 96];
-                        dst2[2 * e] = make_double2((double)u0.x, (double)u0.y);
-                        dst2[2 * e + 1] = make_double2((double)u0.z, (double)u0.w);
-                        dst2[2 * e + 64] = make_double2((double)u1.x, (double)u1.y);
-                        dst2[2 * e + 65] = make_double2((double)u1.z, (double)u1.w);
-                        dst2[2 * e + 128] = make_double2((double)u2.x, (double)u2.y);
-                        dst2[2 * e + 129] = make_double2((double)u2.z, (double)u2.w);
-                        dst2[2 * e + 192] = make_double2((double)u3.x, (double)u3.y);
-                        dst2[2 * e + 193] = make_double2((double)u3.z, (double)u3.w);
-                    }
-                    for (; e < n4; e += 32) {
-                        const float4 u = src4[e];
-                        dst2[2 * e] = make_double2((double)u.x, (double)u.y);
-                        dst2[2 * e + 1] = make_double2((double)u.z, (double)u.w);
-                    }
-                }
-                __syncwarp();  // every lane's stores precede the arrive; raw stage is free
+                asm volatile("bar.sync 1, 64;" ::: "memory");   // (B) float64 tile complete, raw free
                 if (lane == 0) {
                     if (use_next) issue_tma(j + 1, 0);
                     mbar_arrive(&data_full[b]);
@@ -502,6 +508,32 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             for (int k = 0; k < kCols; ++k) xs[k] = min(txi * kTileW + lane + 32 * k, wmax);
             ev.set_columns(p, xs);
         }
+    }
+}
+
+__device__ __forceinline__ void widen_part(const ImageParams &p, unsigned char *smem, int buf,
+                                           int part, int lane) {
+    const float4 *src4 = reinterpret_cast<const float4 *>(smem);
+    double2 *dst2 = reinterpret_cast<double2 *>(smem + (size_t)(1 + 2 * buf) * p.stage_bytes);
+    const int n4 = (p.bw * p.bh) >> 2;
+    constexpr int kStep = 32 * kImgProducers;
+    int e = lane + 32 * part;
+    for (; e + 3 * kStep < n4; e += 4 * kStep) {
+        const float4 u0 = src4[e], u1 = src4[e + kStep], u2 = src4[e + 2 * kStep],
+                     u3 = src4[e + 3 * kStep];
+        dst2[2 * e] = make_double2((double)u0.x, (double)u0.y);
+        dst2[2 * e + 1] = make_double2((double)u0.z, (double)u0.w);
+        dst2[2 * (e + kStep)] = make_double2((double)u1.x, (double)u1.y);
+        dst2[2 * (e + kStep) + 1] = make_double2((double)u1.z, (double)u1.w);
+        dst2[2 * (e + 2 * kStep)] = make_double2((double)u2.x, (double)u2.y);
+        dst2[2 * (e + 2 * kStep) + 1] = make_double2((double)u2.z, (double)u2.w);
+        dst2[2 * (e + 3 * kStep)] = make_double2((double)u3.x, (double)u3.y);
+        dst2[2 * (e + 3 * kStep) + 1] = make_double2((double)u3.z, (double)u3.w);
+    }
+    for (; e < n4; e += kStep) {
+        const float4 u = src4[e];
+        dst2[2 * e] = make_double2((double)u.x, (double)u.y);
+        dst2[2 * e + 1] = make_double2((double)u.z, (double)u.w);
     }
 }
 
