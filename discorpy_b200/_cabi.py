@@ -109,6 +109,7 @@ SIGNATURES = {
     "dcb_launch_count_reset": [],
     "dcb_last_plan": [ctypes.POINTER(_i)] * 5,
     "dcb_selftest_sqrt": [_sz, _u64, ctypes.POINTER(_u64)],
+    "dcb_selftest_sqrt_fast": [_sz, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_u64)],
     "dcb_selftest_tma": [_vp, _i, _i, _i, _sz, _sz, _i, _i, _i, _i, _i, _vp,
                          ctypes.POINTER(_i)],
     "dcb_microbench": [_i, ctypes.POINTER(ctypes.c_double)],

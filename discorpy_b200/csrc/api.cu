@@ -1076,6 +1076,22 @@ int dcb_selftest_sqrt(size_t n, uint64_t seed, uint64_t *mismatch) {
     return DCB_OK;
 }
 
+int dcb_selftest_sqrt_fast(size_t n, uint64_t seed, uint64_t *differ, uint64_t *beyond_one_ulp) {
+    REQUIRE(differ != nullptr && beyond_one_ulp != nullptr, "null pointer");
+    unsigned long long *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 2 * sizeof(*d)));
+    CUDA_TRY(cudaMemset(d, 0, 2 * sizeof(*d)));
+    selftest_sqrt_fast_kernel<<<148 * 8, 256>>>(n, seed, d);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    unsigned long long h[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
+    *differ = h[0];
+    *beyond_one_ulp = h[1];
+    return DCB_OK;
+}
+
 int dcb_selftest_tma(const float *src, int D, int H, int W, size_t pitch, size_t slice_stride,
                      int box_w, int box_h, int x0, int y0, int z0, float *out, int *status) {
     REQUIRE(src && out && status, "null pointer");

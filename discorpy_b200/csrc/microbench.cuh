@@ -186,6 +186,33 @@ __global__ void __launch_bounds__(256)
     if (bad) atomicAdd(mismatch, bad);
 }
 
+// the image kernel's 5-operation sqrt (dsqrt_nz, remap_image.cuh) on the same
+// inputs: out[0] = results that differ from IEEE sqrt, out[1] = results more
+// than one ulp away (must be 0)
+__global__ void __launch_bounds__(256)
+    selftest_sqrt_fast_kernel(size_t n, uint64_t seed, unsigned long long *out) {
+    unsigned long long diff = 0, bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t h = splitmix64(seed ^ i);
+        double s;
+        if ((i & 7) == 0) {
+            const double q = (double)(h >> 44) + 1.0;  // exact squares
+            s = q * q;
+        } else {
+            const double m = (double)(h >> 11) * (1.0 / 9007199254740992.0);  // [0,1)
+            const int e = (int)((h & 0x3f)) - 20;                             // 2^-20 .. 2^43
+            s = ldexp(1.0 + m, e);
+        }
+        const long long a = __double_as_longlong(dsqrt_nz(s));
+        const long long b = __double_as_longlong(sqrt(s));
+        if (a != b) ++diff;
+        if (a - b > 1 || b - a > 1) ++bad;
+    }
+    if (diff) atomicAdd(&out[0], diff);
+    if (bad) atomicAdd(&out[1], bad);
+}
+
 // TMA probe: load one (bw x bh) box at element coordinates (x0, y0, z0) of a
 // (D, H, W) float tensor into shared memory and copy it out.  status[0] = 0 ok,
 // 1 = the mbarrier never completed within ~0.2 s (no trap, so the context

@@ -68,17 +68,23 @@ __device__ __forceinline__ float clamp_bits(float v, int vmax_bits) {
     return __int_as_float(__vimin_s32_relu(__float_as_int(v), vmax_bits));
 }
 
-// sqrt for s > 0 (callers keep s away from 0, see MapEval<MAP_RADIAL>)
+// sqrt for s > 0 (callers keep s away from 0, see MapEval<MAP_RADIAL>), within
+// one ulp: with y0 = MUFU.RSQ64H(s) and e = 1 - s*y0^2 (|e| < 2^-19),
+// sqrt(s) = s*y0 * (1 - e)^(-1/2) = g * (1 + e/2 + 3e^2/8 + O(e^3)).  5 fp64
+// operations + 1 MUFU, every DFMA in a two-register form (the three-register
+// form issues at 70 % rate, profiles/r1/microbench_fp64_operand_forms.txt).
+// It need not be correctly rounded: the radius only enters F(r), whose
+// sensitivity F'(r) r is <= a few percent of F, so one ulp of r moves the
+// coordinate by far less than the rounding of the Horner steps themselves
+// (dcb_selftest_sqrt_fast bounds the error; the 4096^2 / 8192^2 parity runs
+// count the fp32 coordinates that differ from the reference: 0).
 __device__ __forceinline__ double dsqrt_nz(double s) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
-    double g = s * y;
-    double h = 0.5 * y;
-    const double r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    const double d = fma(-g, g, s);
-    return fma(d, h, g);
+    const double g = s * y;
+    const double e = fma(-g, y, 1.0);
+    const double q = fma(e, 0.375, 0.5) * e;
+    return fma(g, q, g);
 }
 
 // (nx / den, ny / den) with one reciprocal: MUFU.RCP64H seed (20 bits), two

@@ -234,9 +234,14 @@ int dcb_launch_count_reset(void);
 int dcb_last_plan(int *path, int *box_w, int *box_h, int *grid, int *smem_bytes);
 
 /* Device self-test of the custom fp64 square root used by the radial kernels
- * against IEEE sqrt on n pseudo-random inputs; *mismatch receives the number
+ * (probe points, Z-stack geometry) against IEEE sqrt on n pseudo-random inputs; *mismatch receives the number
  * of inputs whose result differs from the correctly rounded one. */
 int dcb_selftest_sqrt(size_t n, uint64_t seed, uint64_t *mismatch);
+
+/* Same inputs through the single-image kernel's 5-operation square root
+ * (one ulp, not correctly rounded): *differ = results that are not the IEEE
+ * value, *beyond_one_ulp = results more than one ulp away (expected 0). */
+int dcb_selftest_sqrt_fast(size_t n, uint64_t seed, uint64_t *differ, uint64_t *beyond_one_ulp);
 
 /* TMA probe (diagnostics): loads the (box_w x box_h) box whose first element is
  * (x0, y0, z0) of the (D, H, W) float32 tensor `src` (row pitch / slice stride

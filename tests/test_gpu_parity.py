@@ -350,6 +350,16 @@ def test_custom_sqrt_is_correctly_rounded():
     assert bad.value == 0, "%d of 2^26 inputs not correctly rounded" % bad.value
 
 
+def test_fast_sqrt_is_within_one_ulp():
+    """the 5-operation sqrt of the single-image kernel: never more than one ulp off"""
+    import ctypes
+    from discorpy_b200 import _cabi
+    differ, bad = ctypes.c_uint64(0), ctypes.c_uint64(123)
+    _cabi.call("dcb_selftest_sqrt_fast", 1 << 26, 12345, ctypes.byref(differ), ctypes.byref(bad))
+    assert bad.value == 0, "%d of 2^26 inputs more than one ulp off" % bad.value
+    assert differ.value < (1 << 26) // 4
+
+
 def test_synthetic_fill_matches_host_restatement():
     from discorpy_b200.device import synthetic_host
     arr = dcb.DeviceArray((64, 256)).fill_synthetic(seed=4, offset=1000)

@@ -50,7 +50,9 @@ params = dict(xcenter=1283.4, ycenter=1275.9,
               list_fact=[1.0, -2e-5, 6e-8, -1e-10, 5e-14]) if rank == 0 else None
 got = multigpu.broadcast_params(params, src=0)
 lo, hi = multigpu.shard_range(11, rank, world)
-print("RESULT " + json.dumps(dict(rank=rank, world=world, params=got, shard=[lo, hi])), flush=True)
+# one file per rank: two ranks writing to the shared stdout pipe can interleave
+with open(os.path.join(%(out)r, "rank%%d.json" %% rank), "w") as f:
+    json.dump(dict(rank=rank, world=world, params=got, shard=[lo, hi]), f)
 dist.barrier()
 dist.destroy_process_group()
 """
@@ -67,7 +69,7 @@ def _free_port():
 def test_two_gloo_ranks_broadcast_and_shard(tmp_path):
     import json
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % dict(root=ROOT))
+    script.write_text(WORKER % dict(root=ROOT, out=str(tmp_path)))
     env = dict(os.environ, OMP_NUM_THREADS="1")
     for attempt in range(3):            # a rendezvous port can be taken between probe and bind
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
@@ -77,8 +79,7 @@ def test_two_gloo_ranks_broadcast_and_shard(tmp_path):
         if res.returncode == 0:
             break
     assert res.returncode == 0, res.stderr[-2000:]
-    rows = [json.loads(l.split("RESULT ", 1)[1]) for l in res.stdout.splitlines()
-            if "RESULT " in l]
+    rows = [json.loads(f.read_text()) for f in sorted(tmp_path.glob("rank*.json"))]
     assert sorted(r["rank"] for r in rows) == [0, 1]
     want = dict(xcenter=1283.4, ycenter=1275.9,
                 list_fact=[1.0, -2e-5, 6e-8, -1e-10, 5e-14], list_coef=[])
