@@ -11,7 +11,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdiscorpy_b200.so")
+# DCB_LIB: load another build of the same library (A/B comparisons of kernel variants)
+LIB_PATH = os.environ.get("DCB_LIB") or os.path.join(_HERE, "lib", "libdiscorpy_b200.so")
 
 DCB_MAX_TERMS = 16
 DCB_OK = 0

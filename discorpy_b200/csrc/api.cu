@@ -409,17 +409,23 @@ static int check_options(const dcb_options *opt, dcb_options *o) {
     return DCB_OK;
 }
 
-template <bool ROUND32>
-static StackKernel pick_stack_kernel(int order, int blend) {
-    if (order == 0) return remap_stack_kernel<0, DCB_BLEND_EXACT, ROUND32>;
+template <bool ROUND32, bool RINT>
+static StackKernel pick_stack_kernel_r(int order, int blend) {
+    // order 0 copies pixels: nothing to round
+    if (order == 0) return remap_stack_kernel<0, DCB_BLEND_EXACT, ROUND32, false>;
     switch (blend) {
         case DCB_BLEND_LERP64:
-            return remap_stack_kernel<1, DCB_BLEND_LERP64, ROUND32>;
+            return remap_stack_kernel<1, DCB_BLEND_LERP64, ROUND32, RINT>;
         case DCB_BLEND_LERP32:
-            return remap_stack_kernel<1, DCB_BLEND_LERP32, ROUND32>;
+            return remap_stack_kernel<1, DCB_BLEND_LERP32, ROUND32, RINT>;
         default:
-            return remap_stack_kernel<1, DCB_BLEND_EXACT, ROUND32>;
+            return remap_stack_kernel<1, DCB_BLEND_EXACT, ROUND32, RINT>;
     }
+}
+template <bool ROUND32>
+static StackKernel pick_stack_kernel(int order, int blend, int rint) {
+    return rint ? pick_stack_kernel_r<ROUND32, true>(order, blend)
+                : pick_stack_kernel_r<ROUND32, false>(order, blend);
 }
 
 static int check_image_args(const void *src, const void *dst, int H, int W, size_t src_pitch,
@@ -683,12 +689,11 @@ int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, in
         const ImageKernelSel k = pick_image_kernel<MAP_RADIAL>(o.order, o.blend, model->n, o.flags);
         return plan_and_launch_image(k, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
     }
-    const bool widen = StackWeights<1, DCB_BLEND_EXACT, true>::kWiden && (o.order == 1) &&
-                       (o.blend != DCB_BLEND_LERP32);
+    const bool widen = false;  // no float64 copy of the staged box (see StackWeights)
     if (coord_round)
-        return plan_and_launch_stack(pick_stack_kernel<true>(o.order, o.blend), widen, p, gm, gc,
+        return plan_and_launch_stack(pick_stack_kernel<true>(o.order, o.blend, p.rint), widen, p, gm, gc,
                                      o.path, src_pitch, src_slice_stride, (cudaStream_t)stream);
-    return plan_and_launch_stack(pick_stack_kernel<false>(1, o.blend), widen, p, gm, gc, o.path,
+    return plan_and_launch_stack(pick_stack_kernel<false>(1, o.blend, p.rint), widen, p, gm, gc, o.path,
                                  src_pitch, src_slice_stride, (cudaStream_t)stream);
 }
 

@@ -43,18 +43,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // Blocking wait on a phase parity.  try_wait suspends in hardware for a
 // bounded time; the outer loop is bounded too so that a mis-programmed copy
 // traps instead of hanging the GPU.
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// (a __nanosleep back-off and try_wait's suspend-time hint were measured: no
+// difference on either kernel)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return;
+        if (mbar_try(addr, parity)) return;
     }
     __trap();
 }

@@ -50,25 +50,26 @@ struct StackWeights {
     // everything else keeps the two fractions as doubles
     static constexpr bool kT64 = (ORDER == 1 && !kF32 && !kW4);
     static constexpr int kDoubles = kW4 ? 4 : (kT64 ? 2 : 0);
-    // Sampling the fp64 blends from a float64 copy of the staged box (one
-    // conversion per source pixel instead of one per tap) was measured and
-    // rejected: the CTA barrier it needs per slice costs more than the XU
-    // conversions it saves (64 x 4096^2, exact: 48 % vs 56 % of the HBM peak).
-    // The code path is kept behind this switch for the record.
-    static constexpr bool kWiden = false;
+    // (Sampling the fp64 blends from a float64 copy of the staged box -- one
+    // conversion per source pixel instead of one per tap -- was measured with a
+    // CTA barrier per slice and rejected: 48 % vs 56 % of the HBM peak on
+    // 64 x 4096^2, exact blend.)
 };
 
-template <int ORDER, int BLEND, bool ROUND32>
+// RINT: integer image, SciPy's round-half-away-from-zero on the fp64 sum (a
+// template parameter: as a run-time flag it cost a DSETP, three FSEL and an
+// XU-pipe FRND per pixel and slice, profiles/r1/ncu_stack_v7.txt).
+template <int ORDER, int BLEND, bool ROUND32, bool RINT_>
 __global__ void __launch_bounds__(kThreads, 2)
     remap_stack_kernel(const __grid_constant__ RemapParams p,
                        const __grid_constant__ CUtensorMap tmap) {
     using CT = typename std::conditional<ROUND32, float, double>::type;
     using SW = StackWeights<ORDER, BLEND, ROUND32>;
+    constexpr int RINT = RINT_ ? 1 : 0;
 
     extern __shared__ __align__(128) unsigned char smem[];
-    // layout: [nstage raw boxes][two float64 tiles (fp64 blends only)][full][empty][red]
-    unsigned char *wide_base = smem + (size_t)p.nstage * p.stage_bytes;
-    uint64_t *full = reinterpret_cast<uint64_t *>(wide_base + (SW::kWiden ? 4 : 0) * (size_t)p.stage_bytes);
+    // layout: [nstage raw boxes][full][empty][red]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)p.nstage * p.stage_bytes);
     uint64_t *empty = full + kStkMaxStages;
     int *red = reinterpret_cast<int *>(empty + kStkMaxStages);  // [2][4][kWarps]
 
@@ -233,72 +234,80 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
             for (int k = 0; k < kCols; ++k) colok[k] = (x_base + 32 * k <= wmax);
 
+            // ONE slice loop for every tile.  (Measured, profiles/r1/stack_loop_ab.txt: as soon
+            // as the loop exists in several specialised copies under CTA-uniform branches the
+            // compiler can no longer prove the warp converged at __syncwarp -- BRA.DIV instead
+            // of WARPSYNC.ALL -- and the kernel runs 35-50 % slower although each copy executes
+            // fewer instructions.)  Only the tap loads differ between interior tiles (taps at
+            // +1 / +bw) and tiles where some +1 tap was folded back onto the last row / column
+            // (per-pixel offsets): a uniform branch around phase 1.
+            // ring position of slice iz: stage st, phase parity ph -- kept as counters (a
+            // division by the run-time stage count per slice costs three XU-pipe operations)
+            uint32_t st = base % S, ph = (base / S) & 1u;
             for (int iz = 0; iz < nz; ++iz, orow += p.dst_slice) {
-                const uint32_t g = base + iz, st = g % S;
-                mbar_wait(&full[st], (g / S) & 1u);
+                const uint32_t g = base + iz;
+                // Measured oddity (profiles/r1/stack_loop_ab.txt): the fp32 / nearest paths,
+                // which run at 85-90 % of the HBM peak, are 10-15 % FASTER when every warp
+                // re-derives the ring position with a division here (23.1 vs 27.0 us per
+                // 4096^2 slice) -- neither a plain delay before the wait nor keeping the
+                // counters out of the uniform datapath reproduces it; the fp64 blends
+                // (XU-bound) are 6 % faster with the counters.  Each takes what measured best.
+                if (SW::kF32 || SW::kNearest) st = g % S, ph = (g / S) & 1u;
+                mbar_wait(&full[st], ph);
                 const float *tile = reinterpret_cast<const float *>(smem + (size_t)st * p.stage_bytes);
-                const double *wtile = reinterpret_cast<const double *>(
-                    wide_base + (size_t)(2 * (iz & 1)) * p.stage_bytes);
-                if (SW::kWiden) {
-                    // float32 box -> float64 tile (exact), then the raw stage can be refilled;
-                    // the tile written here was last read two slices ago, behind the barrier
-                    // of the previous slice
-                    const float4 *src4 = reinterpret_cast<const float4 *>(tile);
-                    double2 *dst2 = reinterpret_cast<double2 *>(
-                        wide_base + (size_t)(2 * (iz & 1)) * p.stage_bytes);
-                    const int n4 = (bw * p.bh) >> 2;  // bw % 4 == 0
-                    int e = threadIdx.x;
-                    for (; e + kThreads < n4; e += 2 * kThreads) {
-                        const float4 u = src4[e], w = src4[e + kThreads];
-                        dst2[2 * e] = make_double2((double)u.x, (double)u.y);
-                        dst2[2 * e + 1] = make_double2((double)u.z, (double)u.w);
-                        dst2[2 * (e + kThreads)] = make_double2((double)w.x, (double)w.y);
-                        dst2[2 * (e + kThreads) + 1] = make_double2((double)w.z, (double)w.w);
+                const float *tile1 = tile + bw;  // the row below (interior tiles)
+                // phase 1: every tap of the thread's 8 pixels into registers, then the
+                // stage goes back to the producer BEFORE the arithmetic (the copy of a
+                // later slice overlaps the blend of this one)
+                float fa[kStkPx], fb[ORDER == 1 ? kStkPx : 1], fc[ORDER == 1 ? kStkPx : 1],
+                    fd[ORDER == 1 ? kStkPx : 1];
+                if (ORDER == 0) {
+#pragma unroll
+                    for (int i = 0; i < kStkPx; ++i) fa[i] = tile[off[i]];
+                } else if (edge) {
+#pragma unroll
+                    for (int i = 0; i < kStkPx; ++i) {
+                        const int ox = (int)((dxm >> i) & 1u);
+                        const int oy = ((dym >> i) & 1u) ? bw : 0;
+                        const float *q = tile + off[i];
+                        fa[i] = q[0], fb[ORDER == 1 ? i : 0] = q[ox];
+                        fc[ORDER == 1 ? i : 0] = q[oy], fd[ORDER == 1 ? i : 0] = q[oy + ox];
                     }
-                    if (e < n4) {
-                        const float4 u = src4[e];
-                        dst2[2 * e] = make_double2((double)u.x, (double)u.y);
-                        dst2[2 * e + 1] = make_double2((double)u.z, (double)u.w);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kStkPx; ++i) {
+                        fa[i] = tile[off[i]], fb[ORDER == 1 ? i : 0] = tile[off[i] + 1];
+                        fc[ORDER == 1 ? i : 0] = tile1[off[i]], fd[ORDER == 1 ? i : 0] = tile1[off[i] + 1];
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[st]);
-                    __syncthreads();
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);
+                // phase 2: the blend
                 float v[kStkPx];
 #pragma unroll
                 for (int i = 0; i < kStkPx; ++i) {
                     if (ORDER == 0) {
-                        v[i] = tile[off[i]];
+                        v[i] = fa[i];
                         continue;
                     }
-                    const int ox = edge ? (int)((dxm >> i) & 1u) : 1;
-                    const int oy = edge ? (((dym >> i) & 1u) ? bw : 0) : bw;
                     if (SW::kF32) {
-                        const float *q = tile + off[i];
-                        const float a = q[0], b = q[ox], c = q[oy], d = q[oy + ox];
-                        const float top = fmaf(b - a, wf[i][0], a);
-                        const float bot = fmaf(d - c, wf[i][0], c);
-                        v[i] = finish_f32(fmaf(bot - top, wf[i][1], top), p.rint);
+                        const float top = fmaf(fb[i] - fa[i], wf[i][0], fa[i]);
+                        const float bot = fmaf(fd[i] - fc[i], wf[i][0], fc[i]);
+                        v[i] = finish_f32(fmaf(bot - top, wf[i][1], top), RINT);
                         continue;
                     }
-                    double a, b, c, d;
-                    if (SW::kWiden) {
-                        const double *q = wtile + off[i];
-                        a = q[0], b = q[ox], c = q[oy], d = q[oy + ox];
-                    } else {
-                        const float *q = tile + off[i];
-                        a = (double)q[0], b = (double)q[ox], c = (double)q[oy], d = (double)q[oy + ox];
-                    }
+                    const double a = (double)fa[i], b = (double)fb[ORDER == 1 ? i : 0],
+                                 c = (double)fc[ORDER == 1 ? i : 0], d = (double)fd[ORDER == 1 ? i : 0];
                     if (SW::kW4) {
                         double s = __dmul_rn(a, wd[i][0]);
                         s = __dadd_rn(s, __dmul_rn(b, wd[i][1]));
                         s = __dadd_rn(s, __dmul_rn(c, wd[i][2]));
                         s = __dadd_rn(s, __dmul_rn(d, wd[i][3]));
-                        v[i] = finish_f64(s, p.rint);
+                        v[i] = finish_f64(s, RINT);
                     } else if (BLEND == DCB_BLEND_LERP64) {
                         const double top = fma(b - a, wd[i][0], a);
                         const double bot = fma(d - c, wd[i][0], c);
-                        v[i] = finish_f64(fma(bot - top, wd[i][1], top), p.rint);
+                        v[i] = finish_f64(fma(bot - top, wd[i][1], top), RINT);
                     } else {
                         // float64 coordinates: SciPy's two-step products, every step rounded
                         const double wx1 = wd[i][0], wy1 = wd[i][1];
@@ -307,13 +316,8 @@ __global__ void __launch_bounds__(kThreads, 2)
                         s = __dadd_rn(s, __dmul_rn(__dmul_rn(b, wy0), wx1));
                         s = __dadd_rn(s, __dmul_rn(__dmul_rn(c, wy1), wx0));
                         s = __dadd_rn(s, __dmul_rn(__dmul_rn(d, wy1), wx1));
-                        v[i] = finish_f64(s, p.rint);
+                        v[i] = finish_f64(s, RINT);
                     }
-                }
-                if (!SW::kWiden) {
-                    // this warp is done with the stage: let the producer refill it
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[st]);
                 }
 #pragma unroll
                 for (int j = 0; j < kStkRows; ++j) {
@@ -327,11 +331,17 @@ __global__ void __launch_bounds__(kThreads, 2)
                 if (threadIdx.x == 0 && iz + p.nstage - 1 < nz) {
                     // refill the stage consumed one iteration ago (all warps are past it or
                     // about to be): keeps nstage-1 slices in flight
-                    const uint32_t gn = g + S - 1u, sn = gn % S;
-                    if (gn >= S) mbar_wait(&empty[sn], ((gn / S) - 1u) & 1u);
+                    // global fill number g + S - 1 goes into the stage before st; it was last
+                    // used by fill g - 1, whose release is completion (g + S - 1) / S - 1 of `empty`
+                    const uint32_t sn = (st == 0u) ? S - 1u : st - 1u;
+                    if (g > 0u) mbar_wait(&empty[sn], (st == 0u) ? (ph ^ 1u) : ph);
                     mbar_expect_tx(&full[sn], p.box_bytes);
                     tma_load_3d(smem + (size_t)sn * p.stage_bytes, &tmap, bx0, by0 - p.yorg,
                                 z0 + iz + p.nstage - 1, &full[sn]);
+                }
+                if (++st == S) {
+                    st = 0u;
+                    ph ^= 1u;
                 }
             }
             fills += (uint32_t)nz;
@@ -379,18 +389,18 @@ __global__ void __launch_bounds__(kThreads, 2)
                     if (SW::kF32) {
                         const float top = fmaf(b - a, wf[i][0], a);
                         const float bot = fmaf(d - c, wf[i][0], c);
-                        v[i] = finish_f32(fmaf(bot - top, wf[i][1], top), p.rint);
+                        v[i] = finish_f32(fmaf(bot - top, wf[i][1], top), RINT);
                     } else if (SW::kW4) {
                         double s = __dmul_rn((double)a, wd[i][0]);
                         s = __dadd_rn(s, __dmul_rn((double)b, wd[i][1]));
                         s = __dadd_rn(s, __dmul_rn((double)c, wd[i][2]));
                         s = __dadd_rn(s, __dmul_rn((double)d, wd[i][3]));
-                        v[i] = finish_f64(s, p.rint);
+                        v[i] = finish_f64(s, RINT);
                     } else if (BLEND == DCB_BLEND_LERP64) {
                         const double da = a, db = b, dc = c, dd = d;
                         const double top = fma(db - da, wd[i][0], da);
                         const double bot = fma(dd - dc, wd[i][0], dc);
-                        v[i] = finish_f64(fma(bot - top, wd[i][1], top), p.rint);
+                        v[i] = finish_f64(fma(bot - top, wd[i][1], top), RINT);
                     } else {
                         const double wx1 = wd[i][0], wy1 = wd[i][1];
                         const double wx0 = __dsub_rn(1.0, wx1), wy0 = __dsub_rn(1.0, wy1);
@@ -398,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                         s = __dadd_rn(s, __dmul_rn(__dmul_rn((double)b, wy0), wx1));
                         s = __dadd_rn(s, __dmul_rn(__dmul_rn((double)c, wy1), wx0));
                         s = __dadd_rn(s, __dmul_rn(__dmul_rn((double)d, wy1), wx1));
-                        v[i] = finish_f64(s, p.rint);
+                        v[i] = finish_f64(s, RINT);
                     }
                 }
 #pragma unroll

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import discorpy_b200 as dcb                                    # noqa: E402
 from discorpy_b200 import _cabi                                # noqa: E402
+from bench import ClockSampler                                 # noqa: E402
 
 COEF_DOT_05 = [1.00227490554, -2.99523692178e-05, 8.99519088e-08,
                -1.57066461911e-10, 8.08880211618e-14]
@@ -61,6 +62,8 @@ def main():
                                    ctypes.byref(model), ctypes.byref(opt), sh))
                 for _ in range(2):
                     run()
+                sampler = ClockSampler(0)
+                sampler.start()
                 e0, e1 = dcb.Event(), dcb.Event()
                 e0.record(stream)
                 for _ in range(args.reps):
@@ -68,12 +71,14 @@ def main():
                 e1.record(stream)
                 e1.sync()
                 ms = e0.elapsed_ms(e1) / args.reps
+                clocks = sampler.stop()
                 px = D * H * W
                 gbs = 8.0 * px / (ms * 1e-3) / 1e9
                 print(json.dumps({"case": name, "order": order, "blend": bname, "coord_round": cr,
                                   "D": D, "H": H, "W": W, "ms": ms, "Mpix_s": px / 1e6 / (ms * 1e-3),
                                   "GBs": gbs, "frac": gbs / peak, "us_per_4096sq": ms * 1e3 * 4096 * 4096 / px,
-                                  "plan": dcb.last_plan()}), flush=True)
+                                  "plan": dcb.last_plan(), "clocks": clocks,
+                                  "lib": os.path.basename(_cabi.LIB_PATH)}), flush=True)
         del src, dst
         dcb.device.device_pool.clear()
 
