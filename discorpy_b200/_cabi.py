@@ -25,6 +25,10 @@ BLEND_EXACT, BLEND_LERP64, BLEND_LERP32 = 0, 1, 2
 PATH_AUTO, PATH_DIRECT, PATH_TMA = 0, 1, 2
 FLAG_ROUND_INT = 0x100      # DCB_FLAG_ROUND_INT
 DTYPE_F32, DTYPE_U8, DTYPE_I8, DTYPE_U16, DTYPE_I16 = 0, 1, 2, 3, 4
+#: enum dcb_mode, in the order the reference documents the modes (postprocessing.py:129-130)
+MODES = {"reflect": 0, "grid-mirror": 1, "constant": 2, "grid-constant": 3,
+         "nearest": 4, "mirror": 5, "grid-wrap": 6, "wrap": 7}
+MAP_RADIAL, MAP_PERSP, MAP_COORDS = 0, 1, 2
 
 
 class DcbError(RuntimeError):
@@ -114,6 +118,11 @@ SIGNATURES = {
     "dcb_selftest_tma": [_vp, _i, _i, _i, _sz, _sz, _i, _i, _i, _i, _i, _vp,
                          ctypes.POINTER(_i)],
     "dcb_microbench": [_i, ctypes.POINTER(ctypes.c_double)],
+    "dcb_spline_workspace_bytes": [_i, _i, _i, _i, ctypes.POINTER(_sz)],
+    "dcb_spline_prefilter": [_vp, _i, _i, _i, _sz, _i, _i, _vp, _sz, _vp],
+    "dcb_spline_remap": [_vp, _i, _i, _i, _i, _vp, _i, _sz, _i,
+                         ctypes.POINTER(Radial), ctypes.POINTER(Persp), _vp, _vp,
+                         _i, _sz, _vp, _i, ctypes.c_double, ctypes.c_double, _vp],
 }
 
 _lib = None

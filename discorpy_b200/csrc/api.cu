@@ -14,6 +14,7 @@
 #include "remap_stack.cuh"
 #include "convert.cuh"
 #include "microbench.cuh"
+#include "spline.cuh"
 
 using namespace dcb;
 
@@ -948,6 +949,71 @@ static int launch_map_coords(const float *src, float *dst, int H, int W, long lo
     return DCB_OK;
 }
 
+// ---- spline orders 2..5 / float64 images ------------------------------------------
+namespace {
+
+// correctly rounded doubles of sqrt(8)-3, sqrt(3)-2, ... (the literals SciPy holds;
+// evaluating the radicals in double loses bits to cancellation)
+const double kSplinePoles[6][2] = {
+    {0, 0}, {0, 0},
+    {-0x1.5f619980c4337p-3, 0},
+    {-0x1.126145e9ecd56p-2, 0},
+    {-0x1.72036f2fc0817p-2, -0x1.c1c13efa52247p-7},
+    {-0x1.b8e8be69086f0p-2, -0x1.610b778d2f346p-5}};
+
+struct SplinePlan {
+    int npad, pad_const, filt_kind, tap_kind;
+};
+
+bool spline_plan(int order, int mode, SplinePlan *pl) {
+    int filt, npad = 0, pad_const = 0, tap;
+    switch (mode) {
+        case DCB_MODE_REFLECT: case DCB_MODE_GRID_MIRROR: filt = SPL_REFLECT; tap = SPL_REFLECT; break;
+        case DCB_MODE_NEAREST: filt = SPL_REFLECT; tap = SPL_MIRROR; npad = 12; break;
+        case DCB_MODE_GRID_WRAP: filt = SPL_WRAP; tap = SPL_WRAP; break;
+        case DCB_MODE_GRID_CONSTANT: filt = SPL_MIRROR; tap = SPL_MIRROR; npad = 12; pad_const = 1; break;
+        case DCB_MODE_MIRROR: case DCB_MODE_CONSTANT: case DCB_MODE_WRAP: filt = SPL_MIRROR; tap = SPL_MIRROR; break;
+        default: return false;
+    }
+    if (order <= 1) npad = 0, pad_const = 0;   // no prefilter, no pre-padding
+    pl->npad = npad;
+    pl->pad_const = pad_const;
+    pl->filt_kind = filt;
+    pl->tap_kind = tap;
+    return true;
+}
+
+SplinePoles spline_poles(int order, int n, int kind, double *gain) {
+    SplinePoles pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.npoles = order / 2;
+    double g = 1.0;
+    for (int k = 0; k < pl.npoles; ++k) {
+        const double z = kSplinePoles[order][k];
+        pl.z[k] = z;
+        pl.zp[k] = std::pow(z, (double)(kind == SPL_MIRROR ? n - 1 : n));
+        volatile double a = 1.0 - 1.0 / z, b = 1.0 - z;   // SciPy's operation order, not folded
+        volatile double ab = a * b;
+        g = g * ab;
+    }
+    *gain = g;
+    return pl;
+}
+
+template <class OUT>
+void launch_spline(int order, const SplineParams &p, dim3 grid, cudaStream_t st) {
+    switch (order) {
+        case 0: spline_remap_kernel<0, OUT><<<grid, 256, 0, st>>>(p); break;
+        case 1: spline_remap_kernel<1, OUT><<<grid, 256, 0, st>>>(p); break;
+        case 2: spline_remap_kernel<2, OUT><<<grid, 256, 0, st>>>(p); break;
+        case 3: spline_remap_kernel<3, OUT><<<grid, 256, 0, st>>>(p); break;
+        case 4: spline_remap_kernel<4, OUT><<<grid, 256, 0, st>>>(p); break;
+        default: spline_remap_kernel<5, OUT><<<grid, 256, 0, st>>>(p); break;
+    }
+}
+
+}  // namespace
+
 extern "C" {
 
 int dcb_map_coordinates_f32(const float *src, float *dst, int H, int W, size_t src_pitch,
@@ -1063,6 +1129,127 @@ int dcb_last_plan(int *path, int *box_w, int *box_h, int *grid, int *smem_bytes)
     if (box_h) *box_h = g_last_plan.bh;
     if (grid) *grid = g_last_plan.grid;
     if (smem_bytes) *smem_bytes = g_last_plan.smem;
+    return DCB_OK;
+}
+
+// ---- spline orders 2..5 / float64 images (helpers above the second extern "C") ----
+int dcb_spline_workspace_bytes(int H, int W, int order, int mode, size_t *bytes) {
+    REQUIRE(bytes != nullptr, "bytes is NULL");
+    REQUIRE(H >= 1 && W >= 1, "empty image");
+    REQUIRE(order >= 0 && order <= 5, "spline order not supported");
+    SplinePlan pl;
+    REQUIRE(spline_plan(order, mode, &pl), "boundary mode not supported");
+    const size_t n = (size_t)(H + 2 * pl.npad) * (size_t)(W + 2 * pl.npad) * sizeof(double);
+    *bytes = order > 1 ? 2 * n : n;   // coefficients (+ the transposed scratch copy)
+    return DCB_OK;
+}
+
+int dcb_spline_prefilter(const void *src, int src_is_f64, int H, int W, size_t src_pitch,
+                         int order, int mode, void *workspace, size_t workspace_bytes,
+                         void *stream) {
+    REQUIRE(src != nullptr && workspace != nullptr, "null pointer");
+    size_t need = 0;
+    int rc = dcb_spline_workspace_bytes(H, W, order, mode, &need);
+    if (rc) return rc;
+    REQUIRE(workspace_bytes >= need, "workspace of %zu bytes, %zu needed", workspace_bytes, need);
+    const size_t esz = src_is_f64 ? 8 : 4;
+    REQUIRE(src_pitch % esz == 0 && src_pitch >= (size_t)W * esz, "bad source pitch %zu", src_pitch);
+    SplinePlan pl;
+    spline_plan(order, mode, &pl);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Hc = H + 2 * pl.npad, Wc = W + 2 * pl.npad;
+    double *coef = reinterpret_cast<double *>(workspace);
+    double *scratch = coef + (size_t)Hc * Wc;
+    // axis 0: lines of Hc samples (SciPy filters axis 0 first, _interpolation.py:185-188);
+    // a line of length 1 is left alone, gain included
+    double gain0 = 1.0, gain1 = 1.0;
+    SplinePoles p0 = spline_poles(order > 1 ? order : 0, Hc, pl.filt_kind, &gain0);
+    SplinePoles p1 = spline_poles(order > 1 ? order : 0, Wc, pl.filt_kind, &gain1);
+    if (order <= 1 || Hc < 2) gain0 = 1.0;
+    if (order <= 1 || Wc < 2) gain1 = 1.0;
+    const dim3 pgrid((Wc + 31) / 32, std::min((Hc + 7) / 8, 4096));
+    if (src_is_f64)
+        spline_pad_kernel<double><<<pgrid, 256, 0, st>>>(reinterpret_cast<const double *>(src),
+                                                        (long long)(src_pitch / 8), H, W, coef, Wc,
+                                                        pl.npad, pl.pad_const, gain0);
+    else
+        spline_pad_kernel<float><<<pgrid, 256, 0, st>>>(reinterpret_cast<const float *>(src),
+                                                       (long long)(src_pitch / 4), H, W, coef, Wc,
+                                                       pl.npad, pl.pad_const, gain0);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (order > 1) {
+        if (Hc >= 2) {
+            spline_filter_cols_kernel<<<(Wc + 31) / 32, 32, 0, st>>>(coef, Wc, Hc, Wc, p0, pl.filt_kind);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        if (Wc >= 2) {
+            // axis 1: transpose (with the gain), filter the columns of the transposed image, transpose back
+            const dim3 tg((Wc + 31) / 32, (Hc + 31) / 32), tb((Hc + 31) / 32, (Wc + 31) / 32);
+            spline_transpose_kernel<<<tg, 256, 0, st>>>(coef, Wc, Hc, Wc, scratch, Hc, gain1);
+            spline_filter_cols_kernel<<<(Hc + 31) / 32, 32, 0, st>>>(scratch, Hc, Wc, Hc, p1, pl.filt_kind);
+            spline_transpose_kernel<<<tb, 256, 0, st>>>(scratch, Hc, Wc, Hc, coef, Wc, 1.0);
+            g_launches.fetch_add(3, std::memory_order_relaxed);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return DCB_OK;
+}
+
+int dcb_spline_remap(const void *workspace, int H, int W, int order, int mode, void *dst,
+                     int dst_is_f64, size_t dst_pitch, int map_kind, const dcb_radial *radial_host,
+                     const dcb_persp *persp_host, const void *yd, const void *xd, int coord_is_f64,
+                     size_t n_out, uint32_t *oob_count, int flags, double sat_lo, double sat_hi,
+                     void *stream) {
+    REQUIRE(workspace != nullptr && dst != nullptr, "null pointer");
+    REQUIRE(H >= 1 && W >= 1, "empty image");
+    REQUIRE(order >= 0 && order <= 5, "spline order not supported");
+    SplinePlan pl;
+    REQUIRE(spline_plan(order, mode, &pl), "boundary mode not supported");
+    const size_t esz = dst_is_f64 ? 8 : 4;
+    SplineParams p;
+    memset(&p, 0, sizeof(p));
+    p.coef = reinterpret_cast<const double *>(workspace);
+    p.Hc = H + 2 * pl.npad;
+    p.Wc = W + 2 * pl.npad;
+    p.cpitch = p.Wc;
+    p.npad = pl.npad;
+    p.dst = dst;
+    p.H = H;
+    p.W = W;
+    p.tap_kind = pl.tap_kind;
+    p.rint = (flags & DCB_FLAG_ROUND_INT) ? 1 : 0;
+    p.lo = sat_lo;
+    p.hi = sat_hi;
+    p.map = map_kind;
+    dim3 grid;
+    if (map_kind == DCB_MAP_COORDS) {
+        REQUIRE(yd != nullptr && xd != nullptr, "null coordinate pointer");
+        p.yd = yd;
+        p.xd = xd;
+        p.coord_f64 = coord_is_f64 ? 1 : 0;
+        p.n = n_out;
+        p.oob_count = oob_count;
+        if (n_out == 0) return DCB_OK;
+        grid = dim3((unsigned)std::min<size_t>((n_out + 255) / 256, 148 * 16));
+    } else {
+        REQUIRE(dst_pitch % esz == 0 && dst_pitch >= (size_t)W * esz, "bad destination pitch %zu", dst_pitch);
+        p.dst_pitch = (long long)(dst_pitch / esz);
+        if (map_kind == DCB_MAP_RADIAL) {
+            REQUIRE(radial_host != nullptr, "radial model is NULL");
+            int rc = radial_to_dev(radial_host, &p.rad);
+            if (rc) return rc;
+        } else {
+            REQUIRE(map_kind == DCB_MAP_PERSP && persp_host != nullptr, "bad map kind / NULL model");
+            for (int i = 0; i < 8; ++i) p.per.c[i] = persp_host->c[i];
+        }
+        grid = dim3((W + 31) / 32, (H + 7) / 8);
+    }
+    if (dst_is_f64)
+        launch_spline<double>(order, p, grid, (cudaStream_t)stream);
+    else
+        launch_spline<float>(order, p, grid, (cudaStream_t)stream);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
     return DCB_OK;
 }
 

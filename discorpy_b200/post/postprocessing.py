@@ -31,6 +31,7 @@ from scipy import optimize
 from .. import _cabi
 from .. import device as _dev
 from ..device import DeviceArray
+from . import _spline
 
 _MODES = ("reflect", "grid-mirror", "constant", "grid-constant", "nearest",
           "mirror", "grid-wrap", "wrap")
@@ -49,11 +50,16 @@ def _check_order_mode(order, mode):
         raise RuntimeError("boundary mode not supported")
     if order is None or order < 0 or order > 5:
         raise RuntimeError("spline order not supported")
-    if order > 1:
-        raise NotImplementedError(
-            "spline order %d is not implemented on the CUDA path yet (orders "
-            "0 and 1 are); there is no CPU fallback" % order)
     return int(order)
+
+
+def _wants_spline(mat, order):
+    """Orders 2..5 need SciPy's float64 B-spline prefilter, and float64 images
+    need float64 input / output: both take the general spline path
+    (``_spline.py`` / ``csrc/spline.cuh``) instead of the float32 order-0/1
+    kernels."""
+    return order > 1 or (not isinstance(mat, DeviceArray)
+                         and np.asarray(mat).dtype == np.float64)
 
 
 #: integer dtypes that embed exactly in float32; images of these types travel
@@ -124,18 +130,22 @@ def unwarp_image_backward(mat, xcenter, ycenter, list_fact, order=1,
     Parameters
     ----------
     mat : array_like or DeviceArray
-        2D float32 array.
+        2D array: float32, float64, uint8, int8, uint16 or int16 (the result
+        has the same dtype, rounded like SciPy rounds it).
     xcenter, ycenter : float
         Center of distortion.
     list_fact : list of float
         Polynomial coefficients of the backward model.
     order : int, optional
-        0 (nearest) or 1 (bilinear) run on the GPU; 2..5 raise
-        ``NotImplementedError``.
+        Spline order 0..5.  0 (nearest) and 1 (bilinear) take the tuned
+        float32 kernels; 2..5 run SciPy's float64 B-spline prefilter and
+        (order+1)^2-tap interpolation on the GPU (``csrc/spline.cuh``).
     mode : str, optional
-        Accepted for signature parity.  The coordinates are clipped to the
-        image before sampling, so for order 0/1 all eight SciPy modes give the
-        same result.
+        One of SciPy's eight boundary modes.  The coordinates are clipped to
+        the image before sampling, so for order 0/1 all modes give the same
+        result; for order >= 2 the mode selects the prefilter's boundary
+        condition (and the 12-pixel pre-padding of 'nearest' /
+        'grid-constant'), as in SciPy.
 
     Returns
     -------
@@ -148,6 +158,8 @@ def unwarp_image_backward(mat, xcenter, ycenter, list_fact, order=1,
     (height, width) = mat.shape          # ValueError for non-2D, like :137
     order = _check_order_mode(order, mode)
     model = _cabi.make_radial(xcenter, ycenter, list_fact)
+    if _wants_spline(mat, order):
+        return _spline.remap(mat, order, mode, _cabi.MAP_RADIAL, radial=model)[0]
     if not on_device:
         # host in, host out: banded upload / compute / download pipeline
         src, flags, out_dtype = _as_f32_image(mat)
@@ -264,6 +276,13 @@ def _mapping(mat, xmat, ymat):
 
 def _map_coordinates(mat, yd, xd, order, mode):
     (height, width) = mat.shape
+    if _wants_spline(mat, order):
+        out, n_oob = _spline.remap(mat, order, mode, _cabi.MAP_COORDS, yd=yd, xd=xd)
+        if n_oob and mode != "nearest":
+            raise NotImplementedError(
+                "%d coordinates lie outside the image; the CUDA path clamps them, "
+                "which equals SciPy only for mode='nearest' (got %r)" % (n_oob, mode))
+        return out
     src_np, flags, out_dtype = _as_f32_image(mat)
     kind = np.result_type(yd.dtype, xd.dtype)
     ctype = np.float32 if kind == np.float32 else np.float64
@@ -447,6 +466,8 @@ def correct_perspective_image(mat, list_coef, order=1, mode="reflect",
                                mode)
         return out.reshape((height, width))
     model = _cabi.make_persp(list_coef)
+    if _wants_spline(mat, order):
+        return _spline.remap(mat, order, mode, _cabi.MAP_PERSP, persp=model)[0]
     stream = _dev.current_stream()
     flags, out_dtype = 0, None
     if on_device:
@@ -481,6 +502,9 @@ def unwarp_image_backward_perspective(mat, xcenter, ycenter, list_fact,
     order = _check_order_mode(order, mode)
     radial = _cabi.make_radial(xcenter, ycenter, list_fact)
     persp = _cabi.make_persp(list_coef)
+    if _wants_spline(mat, order):
+        tmp = _spline.remap(mat, order, mode, _cabi.MAP_RADIAL, radial=radial)[0]
+        return _spline.remap(tmp, order, mode, _cabi.MAP_PERSP, persp=persp)[0]
     stream = _dev.current_stream()
     flags, out_dtype = 0, None
     if on_device:

@@ -96,4 +96,11 @@ def unwarp_color_image_backward(mat, xcenter, ycenter, list_fact, order=1,
                                            order=order, mode=mode)
     if num_dim != 3:
         raise ValueError("Input must be a 2D or 3D (H, W, C) array")
+    if _post._wants_spline(mat, order):
+        # spline orders >= 2 / float64 frames: one prefilter + remap per channel
+        # (the reference loops over the channels too, utility.py:337-341)
+        planes = [_post.unwarp_image_backward(mat[:, :, i], xcenter, ycenter,
+                                              list_fact, order=order, mode=mode)
+                  for i in range(mat.shape[-1])]
+        return np.ascontiguousarray(np.moveaxis(np.asarray(planes), 0, 2))
     return _post._unwarp_frame_hwc(mat, xcenter, ycenter, list_fact, order)

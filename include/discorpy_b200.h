@@ -223,6 +223,40 @@ int dcb_fill_synthetic_f32(float *dst, size_t n, uint64_t seed, uint64_t offset,
 
 /* ---- diagnostics --------------------------------------------------------- */
 
+/* ---- spline orders 2..5 and float64 images ------------
+ * `order=` / `mode=` of postprocessing.py:147, :491 and util/utility.py:333,
+ * :338 beyond bilinear: scipy.ndimage.map_coordinates' float64 B-spline
+ * prefilter (scipy/ndimage/_interpolation.py:467-469, pre-padding :212-227)
+ * and its (order+1)^2-tap interpolation, restated operation by operation
+ * (oracle/oracle_spline.py) so that results are bit-identical to SciPy for the
+ * same coordinates.  Two steps, so that one prefiltered image can serve several
+ * maps:
+ *   1. dcb_spline_prefilter: (H, W) float32 or float64 image -> float64
+ *      coefficients at the start of `workspace` (dense (H+2p) x (W+2p) doubles,
+ *      p = 12 for nearest / grid-constant, else 0; order <= 1: a widened copy);
+ *   2. dcb_spline_remap: samples them through the radial map, the projective
+ *      map or caller-supplied coordinates (clamped into the image; *oob_count
+ *      counts those that were outside) into a float32 or float64 destination.
+ * Integer images travel as float32: DCB_FLAG_ROUND_INT rounds half away from
+ * zero and saturates at [sat_lo, sat_hi] like SciPy's integer outputs. */
+enum dcb_mode {
+    DCB_MODE_REFLECT = 0, DCB_MODE_GRID_MIRROR = 1, DCB_MODE_CONSTANT = 2,
+    DCB_MODE_GRID_CONSTANT = 3, DCB_MODE_NEAREST = 4, DCB_MODE_MIRROR = 5,
+    DCB_MODE_GRID_WRAP = 6, DCB_MODE_WRAP = 7
+};
+enum dcb_map_kind { DCB_MAP_RADIAL = 0, DCB_MAP_PERSP = 1, DCB_MAP_COORDS = 2 };
+
+int dcb_spline_workspace_bytes(int H, int W, int order, int mode, size_t *bytes);
+int dcb_spline_prefilter(const void *src, int src_is_f64, int H, int W, size_t src_pitch,
+                         int order, int mode, void *workspace, size_t workspace_bytes,
+                         void *stream);
+int dcb_spline_remap(const void *workspace, int H, int W, int order, int mode,
+                     void *dst, int dst_is_f64, size_t dst_pitch,
+                     int map_kind, const dcb_radial *radial_host, const dcb_persp *persp_host,
+                     const void *yd, const void *xd, int coord_is_f64, size_t n_out,
+                     uint32_t *oob_count, int flags, double sat_lo, double sat_hi,
+                     void *stream);
+
 /* Number of kernel launches issued by this library in the calling process
  * (all threads) since load / since the last reset. */
 int dcb_launch_count(uint64_t *count);

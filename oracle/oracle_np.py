@@ -105,14 +105,17 @@ def _cast_like_scipy(val, dtype):
 
     Floating outputs: one IEEE round-to-nearest.  Integer outputs: round half
     away from zero (``val + 0.5`` / ``val - 0.5`` then truncate), as SURVEY.md
-    section 8(a1) records for u8/u16/i16.
+    section 8(a1) records for u8/u16/i16, saturating at the type's range
+    (measured against SciPy with overshooting cubic splines).
     """
     dtype = np.dtype(dtype)
     if dtype.kind == "f":
         return val.astype(dtype)
     if dtype.kind in "iu":
+        # (spline orders >= 2 overshoot: SciPy saturates at the type's range)
+        info = np.iinfo(dtype)
         shifted = np.where(val >= 0, val + 0.5, val - 0.5)
-        return np.trunc(shifted).astype(dtype)
+        return np.clip(np.trunc(shifted), info.min, info.max).astype(dtype)
     raise TypeError("unsupported dtype %s" % dtype)
 
 

@@ -64,8 +64,10 @@ def test_argument_errors_come_before_any_device_work():
         post.unwarp_image_backward(img, 1, 1, [1.0], mode="bogus")
     with pytest.raises(RuntimeError, match="spline order not supported"):
         post.unwarp_image_backward(img, 1, 1, [1.0], order=6)
-    with pytest.raises(NotImplementedError, match="order 3"):
-        post.unwarp_image_backward(img, 1, 1, [1.0], order=3)
+    with pytest.raises(NotImplementedError, match="float16"):
+        post.unwarp_image_backward(img.astype(np.float16), 1, 1, [1.0])
+    with pytest.raises(NotImplementedError, match="int32"):
+        post.unwarp_image_backward(img.astype(np.int32), 1, 1, [1.0], order=3)
 
 
 def test_no_silent_cpu_fallback_without_gpu():
