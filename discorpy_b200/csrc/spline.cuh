@@ -97,7 +97,19 @@ __global__ void __launch_bounds__(32)
         if (kind == SPL_MIRROR) {
             double acc = __dadd_rn(__dmul_rn(zp, C_(n - 1)), C_(0));
             double z_i = z;
-            for (int i = 1; i < n - 1; ++i) {
+            int i = 1;
+            for (; i + 7 < n - 1; i += 8) {   // loads first: they do not depend on the chain
+                double a[8], b[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] = C_(n - 1 - i - k), b[k] = C_(i + k);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const double t = __dadd_rn(__dmul_rn(a[k], zp), b[k]);
+                    acc = __dadd_rn(acc, __dmul_rn(t, z_i));
+                    z_i = __dmul_rn(z_i, z);
+                }
+            }
+            for (; i < n - 1; ++i) {
                 const double t = __dadd_rn(__dmul_rn(C_(n - 1 - i), zp), C_(i));
                 acc = __dadd_rn(acc, __dmul_rn(t, z_i));
                 z_i = __dmul_rn(z_i, z);
@@ -107,7 +119,19 @@ __global__ void __launch_bounds__(32)
             const double c0 = C_(0);
             double acc = __dadd_rn(__dmul_rn(C_(n - 1), zp), c0);
             double z_i = z;
-            for (int i = 1; i < n; ++i) {   // C_(0) is still the original value here
+            int i = 1;
+            for (; i + 7 < n; i += 8) {   // C_(0) is still the original value throughout
+                double a[8], b[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] = C_(n - 1 - i - k), b[k] = C_(i + k);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const double t = __dadd_rn(__dmul_rn(a[k], zp), b[k]);
+                    acc = __dadd_rn(acc, __dmul_rn(t, z_i));
+                    z_i = __dmul_rn(z_i, z);
+                }
+            }
+            for (; i < n; ++i) {
                 const double t = __dadd_rn(__dmul_rn(C_(n - 1 - i), zp), C_(i));
                 acc = __dadd_rn(acc, __dmul_rn(t, z_i));
                 z_i = __dmul_rn(z_i, z);
