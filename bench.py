@@ -304,8 +304,12 @@ def run_gpu_arm(args, rank, local_rank, world):
         a = dcb.pinned_empty((H, W), np.float32)
         srcs[i % nimg].to_host(out=a)
         host_in.append(a)
-    for _ in range(2):
-        post.unwarp_image_backward(host_in[0], xc, yc, fact)
+    # warm-up in the timed loop's own pattern: one result is still referenced while the next
+    # call runs, so BOTH pinned output blocks the loop alternates between exist before the
+    # clock starts (a cold cudaHostAlloc of 64 MiB takes ~28 ms, tools/e2e_probe.py)
+    out = None
+    for i in range(max(3, args.warmup)):
+        out = post.unwarp_image_backward(host_in[i % len(host_in)], xc, yc, fact)
     barrier()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     t0 = time.perf_counter()
