@@ -605,6 +605,10 @@ int dcb_event_sync(void *event) {
     CUDA_TRY(cudaEventSynchronize((cudaEvent_t)event));
     return DCB_OK;
 }
+int dcb_stream_wait_event(void *stream, void *event) {
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+    return DCB_OK;
+}
 int dcb_event_elapsed_ms(void *start, void *stop, float *ms) {
     REQUIRE(ms != nullptr, "ms is NULL");
     CUDA_TRY(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));

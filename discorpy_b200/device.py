@@ -224,6 +224,11 @@ class Stream:
     def sync(self):
         _cabi.call("dcb_stream_sync", ctypes.c_void_p(self.handle))
 
+    def wait(self, event):
+        """Work submitted to this stream from now on waits for ``event``."""
+        _cabi.call("dcb_stream_wait_event", ctypes.c_void_p(self.handle),
+                   ctypes.c_void_p(event.handle))
+
     def __del__(self):
         try:
             if self.handle:

@@ -121,6 +121,7 @@ int dcb_event_create(void **event);
 int dcb_event_destroy(void *event);
 int dcb_event_record(void *event, void *stream);
 int dcb_event_sync(void *event);
+int dcb_stream_wait_event(void *stream, void *event); /* later work on `stream` waits for `event` */
 int dcb_event_elapsed_ms(void *start, void *stop, float *ms);
 
 /* ---- the hot path -------------------------------------------------------- */

@@ -1,0 +1,71 @@
+"""GPU: the streaming Z-stack entry (discorpy_b200/post/streaming.py) returns exactly
+what unwarp_chunk_slices_backward returns (same kernel, same window) and what the
+oracle computes, for in-memory, memory-mapped and pinned sources."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as orc
+
+import discorpy_b200 as dcb
+import discorpy_b200.post.postprocessing as post
+from discorpy_b200.post import streaming
+
+pytestmark = pytest.mark.gpu
+FACT = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "uint16"])
+@pytest.mark.parametrize("spb", [1, 3, 7, 64])
+def test_stream_equals_chunk_call_and_oracle(dtype, spb):
+    rng = np.random.default_rng(7)
+    d, h, w = 11, 90, 133                      # W % 4 != 0: pitched device rows
+    if dtype == "float32":
+        stack = rng.random((d, h, w), dtype=np.float32)
+    else:
+        stack = rng.integers(0, 65535, (d, h, w), dtype=np.uint16)
+    xc, yc, start, stop = 66.3, 44.1, 10, 71
+    want = post.unwarp_chunk_slices_backward(stack, xc, yc, FACT, start, stop)
+    got = streaming.unwarp_chunk_slices_backward_stream(stack, xc, yc, FACT, start, stop,
+                                                        slices_per_block=spb)
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+    ref = orc.unwarp_chunk_slices_backward(stack, xc, yc, FACT, start, stop)
+    assert np.array_equal(got, ref)
+
+
+def test_stream_from_memmap_into_memmap(tmp_path):
+    rng = np.random.default_rng(8)
+    d, h, w = 9, 64, 128
+    src = np.lib.format.open_memmap(tmp_path / "in.npy", mode="w+", dtype=np.float32,
+                                    shape=(d, h, w))
+    src[:] = rng.random((d, h, w), dtype=np.float32)
+    src.flush()
+    src = np.load(tmp_path / "in.npy", mmap_mode="r")
+    dst = np.lib.format.open_memmap(tmp_path / "out.npy", mode="w+", dtype=np.float32,
+                                    shape=(d, h, w))
+    out = streaming.unwarp_chunk_slices_backward_stream(src, 63.7, 30.2, FACT, out=dst,
+                                                        slices_per_block=4)
+    assert out is dst
+    want = orc.unwarp_chunk_slices_backward(np.asarray(src), 63.7, 30.2, FACT, 0, h - 1)
+    assert np.array_equal(np.asarray(dst), want)
+
+
+def test_stream_pinned_direct_dma():
+    rng = np.random.default_rng(9)
+    d, h, w = 10, 72, 256
+    src = dcb.pinned_empty((d, h, w), np.float32)
+    src[:] = rng.random((d, h, w), dtype=np.float32)
+    dst = dcb.pinned_empty((d, 41, w), np.float32)
+    streaming.unwarp_chunk_slices_backward_stream(src, 120.5, 35.5, FACT, 20, 60, out=dst,
+                                                  slices_per_block=3)
+    want = orc.unwarp_chunk_slices_backward(np.asarray(src), 120.5, 35.5, FACT, 20, 60)
+    assert np.array_equal(np.asarray(dst), want)
+
+
+def test_stream_argument_errors():
+    with pytest.raises(ValueError, match="3D"):
+        streaming.unwarp_chunk_slices_backward_stream(np.zeros((4, 4), np.float32), 1, 1, [1.0])
+    st = np.zeros((2, 8, 8), np.float32)
+    with pytest.raises(ValueError, match="out of the range"):
+        streaming.unwarp_chunk_slices_backward_stream(st, 4, 4, [1.0], 0, 8)
+    with pytest.raises(NotImplementedError):
+        streaming.unwarp_chunk_slices_backward_stream(st.astype(np.float64), 4, 4, [1.0])
