@@ -192,6 +192,13 @@ static int plan_and_launch_stack(StackKernel kern, bool widen, RemapParams &p, d
             bw = std::min(256, (std::min(kTileW + 16, (p.W + 3) / 4 * 4 + 4)));
             bh = std::min(std::min(TH + 8, src_rows), max_stage / (bw * 4));
         }
+        if (const char *env = getenv("DCB_STK_BOX")) {   // diagnostics: "w,h" forces the staged box
+            int ew = 0, eh = 0;
+            if (sscanf(env, "%d,%d", &ew, &eh) == 2 && ew >= 4 && ew <= 256 && eh >= 1 && eh <= 256) {
+                bw = ew / 4 * 4;
+                bh = std::min(eh, src_rows);
+            }
+        }
         bw = std::max(bw, 4);
         bh = std::max(bh, 1);
         // ring depth: as many slices in flight as ~96 KB per CTA hold (two CTAs per SM)
