@@ -232,6 +232,48 @@ def test_stack_paths_against_oracle():
     assert got.dtype == np.float32 and int(np.count_nonzero(got != want)) <= 1
 
 
+def test_baseline_config4_full_frame_stack():
+    """BASELINE config 4 at its frame size: 2560 x 2560 slices with the config's own
+    centre and model (>= 4 slices, >= 3 indices through
+    unwarp_slice_backward, float64 coordinates) plus the chunk path over all rows."""
+    rng = np.random.default_rng(44)
+    stack = rng.random((4, 2560, 2560), dtype=np.float32)
+    xc, yc = 1283.4, 1275.9
+    for index in (0, 1275, 2559, 77):
+        want = orc.unwarp_slice_backward(stack, xc, yc, FACT5, index)
+        got = post.unwarp_slice_backward(stack, xc, yc, FACT5, index)
+        assert got.shape == (4, 2560)
+        diff = np.abs(got.astype(np.float64) - want)
+        assert int(np.count_nonzero(diff > 1e-5)) == 0
+        assert int(np.count_nonzero(got != want)) <= 2
+    full = post.unwarp_chunk_slices_backward(stack, xc, yc, FACT5, 0, 2559)
+    for z in range(4):
+        want = oracle_c.unwarp_image_backward(stack[z], xc, yc, FACT5, 1)
+        _compare(full[z], want, stack[z], 1, flips_allowed=2)
+    # linearity of the data path in the image (same geometry): T(2a) == 2 T(a) exactly
+    twice = post.unwarp_chunk_slices_backward(stack[:1] * 2.0, xc, yc, FACT5, 0, 2559)
+    assert np.array_equal(twice[0], full[0] * 2.0)
+
+
+def test_baseline_config5_fisheye_8192():
+    """BASELINE config 5 geometry at full size: one 8192 x 8192 image, 9-term
+    fisheye-strength model (parity on one image per GPU), through
+    the single-image kernel and through the Z-stack kernel (batch of 2)."""
+    fact = [1.0, -1e-5, 3e-8, -2e-11, 5e-15, -8e-19, 6e-23, -2e-27, 3e-32]
+    xc, yc = 4100.3, 4090.8
+    rng = np.random.default_rng(5)
+    mat = rng.random((8192, 8192), dtype=np.float32)
+    for order in (0, 1):
+        want = oracle_c.unwarp_image_backward(mat, xc, yc, fact, order)
+        got = post.unwarp_image_backward(mat, xc, yc, fact, order=order)
+        n_ne, n_tol = _compare(got, want, mat, order, flips_allowed=16)
+        print("cfg5 order %d: %d px not identical, %d above tol" % (order, n_ne, n_tol))
+    batch = np.stack([mat[:4096], mat[4096:]])          # two (4096, 8192) frames
+    out = post.unwarp_chunk_slices_backward(batch, xc, 2045.4, fact, 0, 4095)
+    for z in range(2):
+        assert np.array_equal(out[z], post.unwarp_image_backward(batch[z], xc, 2045.4, fact))
+
+
 def test_device_resident_api_and_sharding_gives_same_bytes():
     rng = np.random.default_rng(21)
     stack = rng.random((6, 256, 512), dtype=np.float32)
