@@ -119,6 +119,7 @@ SIGNATURES = {
     "dcb_selftest_tma": [_vp, _i, _i, _i, _sz, _sz, _i, _i, _i, _i, _i, _vp,
                          ctypes.POINTER(_i)],
     "dcb_microbench": [_i, ctypes.POINTER(ctypes.c_double)],
+    "dcb_unwarp_image_forward_f32": [_vp, _vp, _i, _i, _sz, _sz, ctypes.POINTER(Radial), _vp, _vp],
     "dcb_spline_workspace_bytes": [_i, _i, _i, _i, ctypes.POINTER(_sz)],
     "dcb_spline_prefilter": [_vp, _i, _i, _i, _sz, _i, _i, _vp, _sz, _vp],
     "dcb_spline_remap": [_vp, _i, _i, _i, _i, _vp, _i, _sz, _i,

@@ -15,6 +15,7 @@
 #include "convert.cuh"
 #include "microbench.cuh"
 #include "spline.cuh"
+#include "forward.cuh"
 
 using namespace dcb;
 
@@ -1260,6 +1261,27 @@ int dcb_spline_remap(const void *workspace, int H, int W, int order, int mode, v
     else
         launch_spline<float>(order, p, grid, (cudaStream_t)stream);
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return DCB_OK;
+}
+
+int dcb_unwarp_image_forward_f32(const float *src, float *dst, int H, int W, size_t src_pitch,
+                                 size_t dst_pitch, const dcb_radial *model, uint32_t *workspace,
+                                 void *stream) {
+    int rc = check_image_args(src, dst, H, W, src_pitch, dst_pitch);
+    if (rc) return rc;
+    REQUIRE(workspace != nullptr, "workspace is NULL (H*W uint32)");
+    REQUIRE((long long)H * W < 0xffffffffll, "image too large for 32-bit pixel indices");
+    RadialDev rad;
+    rc = radial_to_dev(model, &rad);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)H * W * sizeof(uint32_t), st));
+    const dim3 grid((W + 31) / 32, (H + 7) / 8);
+    forward_propose_kernel<<<grid, 256, 0, st>>>(H, W, rad, workspace);
+    forward_gather_kernel<<<grid, 256, 0, st>>>(src, (long long)(src_pitch / 4), dst,
+                                               (long long)(dst_pitch / 4), H, W, workspace);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return DCB_OK;
 }

@@ -182,9 +182,23 @@ def unwarp_image_backward(mat, xcenter, ycenter, list_fact, order=1,
 def unwarp_image_forward(mat, xcenter, ycenter, list_fact):
     """
     Unwarp an image using a forward model (reference ``:151-185``).  Scatter
-    with vacant pixels, "only for assessment"; host-side NumPy, not part of
-    the accelerated path.
+    with vacant pixels, "only for assessment": NumPy arrays are handled host-side
+    exactly like the reference does; a float32 :class:`DeviceArray` is scattered on
+    the GPU (same positions, same last-writer-wins rule) and stays on the device.
     """
+    if isinstance(mat, DeviceArray):
+        # device-resident image: deterministic two-pass scatter on the GPU (forward.cuh)
+        (height, width) = mat.shape
+        model = _cabi.make_radial(xcenter, ycenter, list_fact)
+        stream = _dev.current_stream()
+        dst = DeviceArray((height, width))
+        work = _dev.device_pool.take(max(height * width * 4, 16))
+        _cabi.call("dcb_unwarp_image_forward_f32", _vp(mat.ptr), _vp(dst.ptr), height,
+                   width, mat.pitch, dst.pitch, ctypes.byref(model), _vp(work.ptr),
+                   _vp(stream.handle))
+        import weakref
+        weakref.finalize(dst, _dev.device_pool.give, work)   # until the stream is done with it
+        return dst
     mat = np.asarray(mat)
     (height, width) = mat.shape
     xd = np.arange(width) - xcenter

@@ -18,6 +18,17 @@ import numpy as np
 from ..post import postprocessing as _post
 
 
+def find_point_to_point(points, xcenter, ycenter, list_fact, output_order="xy"):
+    """Corresponding point in the other space for one (row, column) point and a
+    forward / backward model -- reference ``utility.py:192-226``; host side (one point)."""
+    xi, yi = points[1] - xcenter, points[0] - ycenter
+    ri = np.sqrt(xi * xi + yi * yi)
+    factor = np.float64(np.sum(list_fact * np.power(ri, np.arange(len(list_fact)))))
+    xo = xcenter + factor * xi
+    yo = ycenter + factor * yi
+    return (xo, yo) if output_order == "xy" else (yo, xo)
+
+
 def _calc_pad(pad, height, width, xcenter, ycenter, list_fact):
     """Pad widths (top, bottom, left, right) -- reference ``utility.py:229-275``.
 

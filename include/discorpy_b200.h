@@ -258,6 +258,16 @@ int dcb_spline_remap(const void *workspace, int H, int W, int order, int mode,
                      uint32_t *oob_count, int flags, double sat_lo, double sat_hi,
                      void *stream);
 
+/* postprocessing.py:151-185 `unwarp_image_forward` for a device-resident float32
+ * image: every source pixel moves to
+ * round-half-even(clip(centre + F(rd) (p - centre))); unreached outputs are 0;
+ * collisions keep the source with the largest linear index (NumPy's
+ * last-assignment-wins), made deterministic with an atomicMax pass.
+ * `workspace`: H*W uint32 on the device. */
+int dcb_unwarp_image_forward_f32(const float *src, float *dst, int H, int W, size_t src_pitch,
+                                 size_t dst_pitch, const dcb_radial *model_host,
+                                 uint32_t *workspace, void *stream);
+
 /* Number of kernel launches issued by this library in the calling process
  * (all threads) since load / since the last reset. */
 int dcb_launch_count(uint64_t *count);

@@ -384,6 +384,21 @@ def test_tma_path_is_actually_taken_and_launches_counted():
     assert dcb.last_plan()["path"] == dcb.PATH_DIRECT
 
 
+def test_forward_unwarp_on_device_matches_numpy_scatter():
+    """unwarp_image_forward for a DeviceArray == the host (reference-style NumPy) result,
+    including vacant pixels and collisions (last writer in C order wins)."""
+    rng = np.random.default_rng(21)
+    for shape, xc, yc, fact in (((300, 421), 200.3, 140.8, [1.0, 4.0e-4]),      # expands: holes
+                                ((256, 256), 128.0, 128.0, [0.9, -5.0e-4]),       # shrinks: collisions
+                                ((97, 130), 70.2, 33.3, [1.0, -2e-3, 1e-5])):
+        mat = rng.random(shape, dtype=np.float32) + 1.0
+        want = post.unwarp_image_forward(mat, xc, yc, fact)                # host NumPy path
+        got = post.unwarp_image_forward(dcb.DeviceArray.from_host(mat), xc, yc, fact)
+        assert isinstance(got, dcb.DeviceArray)
+        assert np.array_equal(got.to_host(), want)
+        assert np.count_nonzero(want == 0) > 0 or fact[0] < 1.0
+
+
 def test_custom_sqrt_is_correctly_rounded():
     import ctypes
     from discorpy_b200 import _cabi
