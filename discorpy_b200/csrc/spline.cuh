@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+constexpr int kSplU = 16;   // rows loaded ahead of the dependent chain
+
 struct SplinePoles {
     int npoles;
     double z[2];
@@ -98,12 +100,12 @@ __global__ void __launch_bounds__(32)
             double acc = __dadd_rn(__dmul_rn(zp, C_(n - 1)), C_(0));
             double z_i = z;
             int i = 1;
-            for (; i + 7 < n - 1; i += 8) {   // loads first: they do not depend on the chain
-                double a[8], b[8];
+            for (; i + (kSplU - 1) < n - 1; i += kSplU) {   // loads first: they do not depend on the chain
+                double a[kSplU], b[kSplU];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] = C_(n - 1 - i - k), b[k] = C_(i + k);
+                for (int k = 0; k < kSplU; ++k) a[k] = C_(n - 1 - i - k), b[k] = C_(i + k);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < kSplU; ++k) {
                     const double t = __dadd_rn(__dmul_rn(a[k], zp), b[k]);
                     acc = __dadd_rn(acc, __dmul_rn(t, z_i));
                     z_i = __dmul_rn(z_i, z);
@@ -120,12 +122,12 @@ __global__ void __launch_bounds__(32)
             double acc = __dadd_rn(__dmul_rn(C_(n - 1), zp), c0);
             double z_i = z;
             int i = 1;
-            for (; i + 7 < n; i += 8) {   // C_(0) is still the original value throughout
-                double a[8], b[8];
+            for (; i + (kSplU - 1) < n; i += kSplU) {   // C_(0) is still the original value throughout
+                double a[kSplU], b[kSplU];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] = C_(n - 1 - i - k), b[k] = C_(i + k);
+                for (int k = 0; k < kSplU; ++k) a[k] = C_(n - 1 - i - k), b[k] = C_(i + k);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < kSplU; ++k) {
                     const double t = __dadd_rn(__dmul_rn(a[k], zp), b[k]);
                     acc = __dadd_rn(acc, __dmul_rn(t, z_i));
                     z_i = __dmul_rn(z_i, z);
@@ -151,12 +153,12 @@ __global__ void __launch_bounds__(32)
         {
             double prev = C_(0);
             int i = 1;
-            for (; i + 7 < n; i += 8) {
-                double v[8];
+            for (; i + (kSplU - 1) < n; i += kSplU) {
+                double v[kSplU];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = C_(i + k);
+                for (int k = 0; k < kSplU; ++k) v[k] = C_(i + k);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < kSplU; ++k) {
                     prev = __dadd_rn(__dmul_rn(prev, z), v[k]);
                     C_(i + k) = prev;
                 }
@@ -185,12 +187,12 @@ __global__ void __launch_bounds__(32)
         {
             double next = C_(n - 1);
             int i = n - 2;
-            for (; i - 7 >= 0; i -= 8) {
-                double v[8];
+            for (; i - (kSplU - 1) >= 0; i -= kSplU) {
+                double v[kSplU];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = C_(i - k);
+                for (int k = 0; k < kSplU; ++k) v[k] = C_(i - k);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < kSplU; ++k) {
                     next = __dmul_rn(__dsub_rn(next, v[k]), z);
                     C_(i - k) = next;
                 }
