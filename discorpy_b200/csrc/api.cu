@@ -373,7 +373,10 @@ static ImageKernelSel pick_image_kernel_nt(int order, int blend) {
 }
 
 constexpr int kImgTileH = 32;     // 128 x 32 output tiles
-constexpr int kImgMinBlocks = 2;  // 128 registers: the per-row loop keeps 4 fp64 chains in flight
+#ifndef DCB_IMG_MINB
+#define DCB_IMG_MINB 2
+#endif
+constexpr int kImgMinBlocks = DCB_IMG_MINB;  // 128 registers: the per-row loop keeps 4 fp64 chains in flight
 
 // nterms: number of polynomial coefficients (radial map); 1..10 have kernels
 // with the Horner chain unrolled at compile time, the rest use the generic one.
@@ -1349,7 +1352,7 @@ int dcb_selftest_tma(const float *src, int D, int H, int W, size_t pitch, size_t
 
 int dcb_microbench(int which, double *gops) {
     REQUIRE(gops != nullptr, "gops is NULL");
-    REQUIRE(which >= 0 && which <= 29, "which must be 0..29");
+    REQUIRE(which >= 0 && which <= 36, "which must be 0..36");
     double *sink = nullptr;
     CUDA_TRY(cudaMalloc(&sink, 2 * sizeof(double)));
     if (which >= 6 && which <= 9) {  // latency probes: cycles per dependent operation
@@ -1398,6 +1401,13 @@ int dcb_microbench(int which, double *gops) {
                 microbench_coords_kernel<<<grid, block, sm>>>(sink, 2050.37, 2040.81);
                 break;
             }
+            case 30: microbench_kernel<30><<<grid, block>>>(sink, 1.0); break;
+            case 31: microbench_kernel<31><<<grid, block>>>(sink, 1.0); break;
+            case 32: microbench_kernel<32><<<grid, block>>>(sink, 1.0); break;
+            case 33: microbench_kernel<33><<<grid, block>>>(sink, 1.0); break;
+            case 34: microbench_kernel<34><<<grid, block>>>(sink, 1.0); break;
+            case 35: microbench_kernel<35><<<grid, block>>>(sink, 1.0); break;
+            case 36: microbench_kernel<36><<<grid, block>>>(sink, 1.0); break;
             case 4: microbench_kernel<4><<<grid, block>>>(sink, 1.0); break;
             case 5: microbench_kernel<5><<<grid, block>>>(sink, 1.0); break;
         }
@@ -1414,6 +1424,9 @@ int dcb_microbench(int which, double *gops) {
     if (which == 1) ops_per_thread *= 2;       // two conversions per step
     if (which == 3 || (which >= 11 && which <= 18)) ops_per_thread = (double)kMbIters * 4;  // pixels
     if (which == 5) ops_per_thread *= 3;       // DFMA + two conversions
+    if (which == 30 || which == 31) ops_per_thread *= 2;   // conversions counted (2 per step)
+    if (which == 32) ops_per_thread *= 1;                  // conversions counted (1 per step)
+    if (which == 33) ops_per_thread *= 1;
     if (which >= 24 && which <= 29) {  // mixes: cycles per warp-level group on one SM sub-partition
         const double groups = (double)kMbIters * grid * block / 32.0;          // warp-groups issued
         const double smsp_cycles = best * 1e-3 * 1.965e9 * 148 * 4;             // at 1965 MHz

@@ -42,6 +42,50 @@ __global__ void __launch_bounds__(256) microbench_kernel(double *sink, double se
                 d[c] = __dadd_rn(d[c], d[(c + 3) % kMbChains]);
             } else if (WHICH == 23) {   // DFMA, two distinct registers, one used twice
                 d[c] = fma(d[c], d[(c + 3) % kMbChains], d[c]);
+            } else if (WHICH == 30) {   // 2 widenings (of values that change) + 1 DFMA + 2 FFMA
+                f[c] = fmaf(f[c], 0.999999f, 1e-7f);
+                const float g = fmaf(f[c], 0.5f, 0.25f);
+                double w1, w2;
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(w1) : "f"(f[c]));
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(w2) : "f"(g));
+                d[c] = fma(w1, w2, d[c]);
+            } else if (WHICH == 31) {   // 2 narrowings (of values that change) + 2 DFMA + 1 FADD
+                d[c] = fma(d[c], 0.999999, 1e-7);
+                const double e = fma(d[c], 0.5, 0.25);
+                float n1, n2;
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(n1) : "d"(d[c]));
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(n2) : "d"(e));
+                f[c] += n1 * n2;
+            } else if (WHICH == 32) {   // 1 widening + 1 DFMA + 1 FFMA
+                f[c] = fmaf(f[c], 0.999999f, 1e-7f);
+                double w;
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(w) : "f"(f[c]));
+                d[c] = fma(d[c], 0.999999, w);
+            } else if (WHICH == 33) {   // 1 narrowing + 2 DFMA
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f[c]) : "d"(d[c]));
+                d[c] = fma(d[c], 0.999999, 1e-7);
+                d[(c + 1) % kMbChains] = fma(d[(c + 1) % kMbChains], 0.999999, 1e-7);
+            } else if (WHICH == 34) {   // balanced: 1 widening (8 XU cycles) + 4 DFMA (8 fp64 cycles)
+                f[c] = fmaf(f[c], 0.999999f, 1e-7f);
+                double w;
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(w) : "f"(f[c]));
+                d[c] = fma(d[c], 0.999999, w);
+                d[(c + 1) % kMbChains] = fma(d[(c + 1) % kMbChains], 0.999999, 1e-7);
+                d[(c + 2) % kMbChains] = fma(d[(c + 2) % kMbChains], 0.999999, 1e-7);
+                d[(c + 3) % kMbChains] = fma(d[(c + 3) % kMbChains], 0.999999, 1e-7);
+            } else if (WHICH == 35) {   // balanced: 1 narrowing + 4 DFMA
+                float n1;
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(n1) : "d"(d[c]));
+                f[c] += n1;
+                d[c] = fma(d[c], 0.999999, 1e-7);
+                d[(c + 1) % kMbChains] = fma(d[(c + 1) % kMbChains], 0.999999, 1e-7);
+                d[(c + 2) % kMbChains] = fma(d[(c + 2) % kMbChains], 0.999999, 1e-7);
+                d[(c + 3) % kMbChains] = fma(d[(c + 3) % kMbChains], 0.999999, 1e-7);
+            } else if (WHICH == 36) {   // 4 DFMA only, same shape (the fp64 side of 34/35 alone)
+                d[c] = fma(d[c], 0.999999, 1e-7);
+                d[(c + 1) % kMbChains] = fma(d[(c + 1) % kMbChains], 0.999999, 1e-7);
+                d[(c + 2) % kMbChains] = fma(d[(c + 2) % kMbChains], 0.999999, 1e-7);
+                d[(c + 3) % kMbChains] = fma(d[(c + 3) % kMbChains], 0.999999, 1e-7);
             } else if (WHICH == 5) {
                 d[c] = fma(d[c], 0.999999, 1e-7);
                 double w;

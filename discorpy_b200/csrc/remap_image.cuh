@@ -421,7 +421,11 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             const bool full_w = (txi * kTileW + kTileW - 1 <= wmax);  // CTA-uniform
             float *orow = p.dst + (long long)(y_base - p.row0) * p.dst_pitch + x_base;
             double yd = (double)y_base;
-#pragma unroll 1
+#ifndef DCB_IMG_UNROLL
+#define DCB_IMG_UNROLL 1
+#endif
+            constexpr int kRowUnroll = DCB_IMG_UNROLL;   // A/B builds; 1 measured best
+#pragma unroll kRowUnroll
             for (int j = 0; j < nrow; ++j, yd += 1.0, orow += p.dst_pitch) {
                 float xf[kCols], yf[kCols];
                 ev.row(p, yd, xf, yf);
