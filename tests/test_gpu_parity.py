@@ -344,8 +344,13 @@ def test_edge_shapes_and_values():
     got = post.unwarp_image_backward(rgb[:, :, 1], 30.2, 24.9, [1.0, 2e-3])
     want = orc.unwarp_image_backward(rgb[:, :, 1], 30.2, 24.9, [1.0, 2e-3])
     assert np.array_equal(got, want)
+    # float64 images: float64 in, float64 out (the spline path); float16 is still refused
+    f64 = post.unwarp_image_backward(rgb[:, :, 1].astype(np.float64), 30.2, 24.9, [1.0, 2e-3])
+    assert f64.dtype == np.float64
+    assert np.array_equal(f64, orc.unwarp_image_backward(rgb[:, :, 1].astype(np.float64), 30.2,
+                                                         24.9, [1.0, 2e-3]))
     with pytest.raises(NotImplementedError, match="dtype"):
-        post.unwarp_image_backward(np.zeros((8, 8), np.float64), 4, 4, [1.0])
+        post.unwarp_image_backward(np.zeros((8, 8), np.float16), 4, 4, [1.0])
 
 
 def test_integer_frames_full_compare():
