@@ -277,9 +277,37 @@ struct ImageKernelSel {
     int th;     // tile height the kernel was instantiated for
 };
 
+// Does the map send any pixel of the output rows' border outside the image (so that part of the
+// output is clipped and takes the slow row path)?  Sampled on the four edges; the maps of this
+// path are monotone enough that clipping starts at the border.
+static bool map_clips_at_border(const ImageParams &p, int map_kind) {
+    const int y0 = p.row0, y1 = p.row0 + p.nrows - 1;
+    const int sx = std::max(1, p.W / 64), sy = std::max(1, p.nrows / 64);
+    auto outside = [&](int x, int y) -> bool {
+        double xd, yd;
+        if (map_kind == MAP_RADIAL) {
+            const double xu = x - p.rad.xc, yu = y - p.rad.yc, r = std::sqrt(xu * xu + yu * yu);
+            double f = 0.0;
+            for (int i = p.rad.n - 1; i >= 0; --i) f = f * r + p.rad.a[i];
+            xd = p.rad.xc + f * xu;
+            yd = p.rad.yc + f * yu;
+        } else {
+            const double den = p.per.c[6] * x + p.per.c[7] * y + 1.0;
+            xd = (p.per.c[0] * x + p.per.c[1] * y + p.per.c[2]) / den;
+            yd = (p.per.c[3] * x + p.per.c[4] * y + p.per.c[5]) / den;
+        }
+        return !(xd >= 0.0 && xd <= (double)(p.W - 1) && yd >= 0.0 && yd <= (double)(p.H - 1));
+    };
+    for (int x = 0; x < p.W; x += sx)
+        if (outside(x, y0) || outside(x, y1)) return true;
+    for (int y = y0; y <= y1; y += sy)
+        if (outside(0, y) || outside(p.W - 1, y)) return true;
+    return outside(p.W - 1, y0) || outside(p.W - 1, y1);
+}
+
 static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, double gmain,
                                  double gcross, int path_req, size_t src_pitch_bytes,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, int map_kind) {
     DevProps props;
     int rc = device_props(&props);
     if (rc != DCB_OK) return rc;
@@ -300,6 +328,7 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
                     "of 16 bytes (and a driver exporting cuTensorMapEncodeTiled)");
     bool staged = layout_ok && path_req != DCB_PATH_DIRECT;
     int bw = 0, bh = 0;
+    bool fallback_box = false;
     if (staged) {
         if (!(gmain < 64.0) || !(gcross < 64.0)) gmain = gcross = 64.0;
         const double tw = std::min(kTileW, p.W) - 1, th = std::min(TH, p.nrows) - 1;
@@ -316,10 +345,13 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
             // probes do not fit are gathered straight from global memory
             bw = std::min(256, std::min(kTileW + 16, (p.W + 3) / 4 * 4 + 4));
             bh = std::min(std::min(TH + 8, src_rows), max_stage / (bw * 4));
+            fallback_box = true;
         }
         bw = std::max(bw, 4);
         bh = std::max(bh, 1);
     }
+    // uneven tiles (clipped regions, tiles that will not fit the box): deal them round-robin
+    p.deal = (fallback_box || map_clips_at_border(p, map_kind)) ? 1 : 0;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (staged) {
@@ -703,7 +735,7 @@ int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, in
         q.dbg = (o.flags >> 4) & 0xf;
         q.rint = p.rint;
         const ImageKernelSel k = pick_image_kernel<MAP_RADIAL>(o.order, o.blend, model->n, o.flags);
-        return plan_and_launch_image(k, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
+        return plan_and_launch_image(k, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream, MAP_RADIAL);
     }
     const bool widen = false;  // no float64 copy of the staged box (see StackWeights)
     if (coord_round)
@@ -916,7 +948,7 @@ int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W
     q.ylast = H - 1;
     q.rint = (o.flags & DCB_FLAG_ROUND_INT) ? 1 : 0;
     const ImageKernelSel k = pick_image_kernel<MAP_PERSP>(o.order, o.blend, 0, o.flags);
-    return plan_and_launch_image(k, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream);
+    return plan_and_launch_image(k, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream, MAP_PERSP);
 }
 
 int dcb_unwarp_image_backward_perspective_f32(const float *src, float *dst, float *scratch, int H,

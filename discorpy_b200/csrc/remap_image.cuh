@@ -45,6 +45,8 @@ struct ImageParams {
     int bw, bh;        // staged box, bw % 4 == 0; bw == 0 => never stage
     unsigned box_bytes, stage_bytes;
     int dbg;           // A/B builds (-DDCB_AB): ablation switches, 0 otherwise
+    int deal;          // 0: each CTA a contiguous range of the tile order; 1: tiles dealt round-robin
+    int pad_;
     int rint;          // 1: integer image, round half away from zero (finish_f64 in remap.cuh)
     RadialDev rad;
     PerspDev per;
@@ -93,7 +95,7 @@ __device__ __forceinline__ double dsqrt_nz(double s) {
 // rounded except in rare last-bit cases (like dsqrt: far below what can flip an
 // fp32-rounded coordinate).  A zero / non-finite / subnormal denominator takes
 // the IEEE division, so the projective singularity behaves like the reference.
-__device__ __forceinline__ void ddiv_pair(double nx, double ny, double den, double &qx, double &qy) {
+__device__ __forceinline__ bool ddiv_pair(double nx, double ny, double den, double &qx, double &qy) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
     double e = fma(-den, r, 1.0);
@@ -103,10 +105,11 @@ __device__ __forceinline__ void ddiv_pair(double nx, double ny, double den, doub
     const double x0 = __dmul_rn(nx, r), y0 = __dmul_rn(ny, r);
     qx = fma(fma(-den, x0, nx), r, x0);
     qy = fma(fma(-den, y0, ny), r, y0);
-    if (!(fabs(r) < 1e300) || !(fabs(r) > 1e-300)) {  // den = 0, huge, tiny or NaN
-        qx = __ddiv_rn(nx, den);
-        qy = __ddiv_rn(ny, den);
-    }
+    // den = 0, huge, tiny or NaN <=> the exponent of 1/den leaves [2^-995, 2^995]: the caller
+    // redoes such pixels with the IEEE division (one integer test instead of two DSETP and a
+    // divergent branch per pixel -- profiles/r1/ncu_persp_v10.txt)
+    const unsigned ex = ((unsigned)__double2hiint(r) >> 20) & 0x7ffu;
+    return (ex - 28u) > (2018u - 28u);
 }
 
 // SciPy's order-1 value  sum_ij  rn(rn(m_ij * wy_i) * wx_j)  accumulated first
@@ -192,15 +195,26 @@ struct MapEval<MAP_PERSP, NT> {
         const double c2y = __dmul_rn(p.per.c[1], yd);
         const double c5y = __dmul_rn(p.per.c[4], yd);
         const double c8y = __dmul_rn(p.per.c[7], yd);
+        bool odd = false;
 #pragma unroll
         for (int k = 0; k < kCols; ++k) {
             const double den = __dadd_rn(__dadd_rn(c7x[k], c8y), 1.0);
             const double nx = __dadd_rn(__dadd_rn(c1x[k], c2y), p.per.c[2]);
             const double ny = __dadd_rn(__dadd_rn(c4x[k], c5y), p.per.c[5]);
             double qx, qy;
-            ddiv_pair(nx, ny, den, qx, qy);
+            odd |= ddiv_pair(nx, ny, den, qx, qy);
             xf[k] = __double2float_rn(qx);
             yf[k] = __double2float_rn(qy);
+        }
+        if (__any_sync(0xffffffffu, odd)) {   // projective singularity in this row: IEEE divisions
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) {
+                const double den = __dadd_rn(__dadd_rn(c7x[k], c8y), 1.0);
+                const double nx = __dadd_rn(__dadd_rn(c1x[k], c2y), p.per.c[2]);
+                const double ny = __dadd_rn(__dadd_rn(c4x[k], c5y), p.per.c[5]);
+                xf[k] = __double2float_rn(__ddiv_rn(nx, den));
+                yf[k] = __double2float_rn(__ddiv_rn(ny, den));
+            }
         }
     }
 };
@@ -282,8 +296,18 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
 
     // this CTA's tiles: a contiguous range of the column-major tile order, so
     // consecutive tiles sit below each other and share their column terms
-    const int t0 = (int)((long long)blockIdx.x * p.ntiles / gridDim.x);
-    const int n = (int)((long long)(blockIdx.x + 1) * p.ntiles / gridDim.x) - t0;
+    // This CTA's tiles.  deal == 0: a contiguous range of the column-major tile order, so that
+    // consecutive tiles sit below each other and share their column terms -- 3 % faster when every
+    // tile costs the same.  deal == 1 (the host sets it when part of the map is clipped at the
+    // image border or the staged box is only the fallback size, i.e. when some tiles take the slow
+    // row path): tiles dealt round-robin, otherwise whole CTAs own nothing but slow tiles -- the
+    // config-1 geometry (19.9 % clipped) took 166 us instead of 100, the config-3 perspective 93
+    // instead of 70 (profiles/r1/bench_tile_dealing.txt).
+    const int tstep = p.deal ? (int)gridDim.x : 1;
+    const int t0 = p.deal ? (int)blockIdx.x : (int)((long long)blockIdx.x * p.ntiles / gridDim.x);
+    const int n = p.deal ? (p.ntiles - t0 + tstep - 1) / tstep
+                         : (int)((long long)(blockIdx.x + 1) * p.ntiles / gridDim.x) - t0;
+    auto tile_of = [&](int k) -> int { return t0 + k * tstep; };   // local tile k -> tile index
 
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b) {
@@ -320,7 +344,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         // =========================== producer warp ===================================
         // place the source box of local tile k from 9 probe points (all 32 lanes)
         auto place_box = [&](int k) -> bool {
-            const int t = t0 + k;
+            const int t = tile_of(k);
             const int txi = t / p.tiles_y, tyi = t - txi * p.tiles_y;
             const int x_lo = txi * kTileW, y_lo = p.row0 + tyi * TH;
             const int x_hi = min(x_lo + kTileW - 1, wmax), y_hi = min(y_lo + TH - 1, y_end - 1);
@@ -509,14 +533,18 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         // this warp is done with buffer i&1 (and with boxes[i % kBoxRing])
         __syncwarp();
         if (lane == 0) mbar_arrive(&data_empty[i & 1]);
-        // next tile of the column-major order
-        if (++tyi == p.tiles_y) {
-            tyi = 0;
-            ++txi;
-            int xs[kCols];
+        // next tile of this CTA
+        if (i + 1 < n) {
+            const int tn = tile_of(i + 1);
+            const int txn = tn / p.tiles_y;
+            tyi = tn - txn * p.tiles_y;
+            if (txn != txi) {
+                txi = txn;
+                int xs[kCols];
 #pragma unroll
-            for (int k = 0; k < kCols; ++k) xs[k] = min(txi * kTileW + lane + 32 * k, wmax);
-            ev.set_columns(p, xs);
+                for (int k = 0; k < kCols; ++k) xs[k] = min(txi * kTileW + lane + 32 * k, wmax);
+                ev.set_columns(p, xs);
+            }
         }
     }
 }
