@@ -1225,17 +1225,35 @@ int dcb_spline_prefilter(const void *src, int src_is_f64, int H, int W, size_t s
                                                        pl.npad, pl.pad_const, gain0);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (order > 1) {
-        if (Hc >= 2) {
-            spline_filter_cols_kernel<<<(Wc + 31) / 32, 32, 0, st>>>(coef, Wc, Hc, Wc, p0, pl.filt_kind);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
+        // lines of >= 256 samples go through the shared-memory staged kernel, short ones through
+        // the one-thread-per-line kernel (DCB_SPLINE_STAGED=0/1 forces one of them: diagnostics)
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute((const void *)spline_filter_cols_staged_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kSplSmemBytes));
+            attr_set = true;
         }
+        int force = -1;
+        if (const char *env = getenv("DCB_SPLINE_STAGED")) force = atoi(env);
+        auto filter_cols = [&](double *a, int pitch, int n, int ncols, const SplinePoles &pp) {
+            const bool staged = force >= 0 ? force != 0 : n >= 256;
+            if (staged)
+                spline_filter_cols_staged_kernel<<<(ncols + 31) / 32, 256, kSplSmemBytes, st>>>(
+                    a, pitch, n, ncols, pp, pl.filt_kind);
+            else
+                spline_filter_cols_kernel<<<(ncols + 31) / 32, 32, 0, st>>>(a, pitch, n, ncols, pp,
+                                                                            pl.filt_kind);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        };
+        if (Hc >= 2) filter_cols(coef, Wc, Hc, Wc, p0);
         if (Wc >= 2) {
             // axis 1: transpose (with the gain), filter the columns of the transposed image, transpose back
             const dim3 tg((Wc + 31) / 32, (Hc + 31) / 32), tb((Hc + 31) / 32, (Wc + 31) / 32);
             spline_transpose_kernel<<<tg, 256, 0, st>>>(coef, Wc, Hc, Wc, scratch, Hc, gain1);
-            spline_filter_cols_kernel<<<(Hc + 31) / 32, 32, 0, st>>>(scratch, Hc, Wc, Hc, p1, pl.filt_kind);
+            filter_cols(scratch, Hc, Wc, Hc, p1);
             spline_transpose_kernel<<<tb, 256, 0, st>>>(scratch, Hc, Wc, Hc, coef, Wc, 1.0);
-            g_launches.fetch_add(3, std::memory_order_relaxed);
+            g_launches.fetch_add(2, std::memory_order_relaxed);
         }
     }
     CUDA_TRY(cudaGetLastError());

@@ -206,6 +206,177 @@ __global__ void __launch_bounds__(32)
 #undef C_
 }
 
+// The same filter with the rows staged through shared memory: the one-thread-per-line kernel
+// above keeps only 16 rows per line in flight (128 warps on the whole GPU for a 4096-wide
+// image, ~0.5 TB/s); here a CTA owns 32 columns, seven warps move windows of kSplR rows
+// between global and shared memory (double-buffered) while warp 0 runs the sequential
+// recursions on the window that has landed.  Same operations in the same order per line.
+constexpr int kSplR = 64;   // rows per window; shared memory = 2 stages x 2 streams x kSplR x 32 doubles
+constexpr size_t kSplSmemBytes = (size_t)2 * 2 * kSplR * 32 * sizeof(double);
+
+// One sweep over `count` steps: step j reads row firstA + dirA * j (stream A) and, if TWO, row
+// firstB + dirB * j (stream B).  body(a, b, m) is run by warp 0 on every window (a[j * 32],
+// b[j * 32] for j < m, this lane's column); if WRITE the window of stream A is written back.
+template <bool TWO, bool WRITE, class Body>
+__device__ __forceinline__ void spline_sweep(double *__restrict__ gcol, bool colok, long long pitch,
+                                             double *sbuf, int firstA, int dirA, int firstB, int dirB,
+                                             int count, Body &&body) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = (count + kSplR - 1) / kSplR;
+    auto win = [&](int st, int strm) { return sbuf + (size_t)((st * 2 + strm) * kSplR) * 32 + lane; };
+    auto move = [&](int w, bool to_smem) {   // loader warps 1..7: window w <-> global
+        const int j0 = w * kSplR, m = min(kSplR, count - j0);
+        double *a = win(w & 1, 0), *b = win(w & 1, 1);
+        if (!colok) return;
+        // (issuing all loads of a window before the first shared-memory store was measured:
+        //  no faster, 254 registers)
+        for (int r = warp - 1; r < m; r += 7) {
+            const long long ra = (long long)(firstA + dirA * (j0 + r)) * pitch;
+            if (to_smem) {
+                a[r * 32] = gcol[ra];
+                if (TWO) b[r * 32] = gcol[(long long)(firstB + dirB * (j0 + r)) * pitch];
+            } else {
+                gcol[ra] = a[r * 32];
+            }
+        }
+    };
+    if (nw <= 0) return;
+    if (warp != 0) move(0, true);
+    __syncthreads();
+    for (int w = 0; w < nw; ++w) {
+        if (warp == 0) {
+            body(win(w & 1, 0), win(w & 1, 1), min(kSplR, count - w * kSplR));
+        } else {
+            if (WRITE && w >= 1) move(w - 1, false);   // results of the previous window
+            if (w + 1 < nw) move(w + 1, true);         // then refill that buffer
+        }
+        __syncthreads();
+    }
+    if (WRITE) {
+        if (warp != 0) move(nw - 1, false);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    spline_filter_cols_staged_kernel(double *__restrict__ c, long long pitch, int n, int ncols,
+                                     SplinePoles pl, int kind) {
+    extern __shared__ __align__(16) double spl_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    const bool colok = col < ncols;
+    double *gcol = c + (colok ? col : 0);
+    if (n < 2) return;
+#define C_(i) gcol[(long long)(i) * pitch]
+    for (int p = 0; p < pl.npoles; ++p) {
+        const double z = pl.z[p], zp = pl.zp[p];
+        double acc = 0.0, z_i = z, prev = 0.0, prev2 = 0.0;   // live in warp 0 only
+        // ---- causal initialisation -------------------------------------------------
+        if (kind == SPL_MIRROR) {
+            if (warp == 0) acc = __dadd_rn(__dmul_rn(zp, C_(n - 1)), C_(0));
+            spline_sweep<true, false>(gcol, colok, pitch, spl_smem, 1, 1, n - 2, -1, n - 2,
+                                      [&](double *a, double *b, int m) {
+                                          for (int j = 0; j < m; ++j) {
+                                              const double t = __dadd_rn(__dmul_rn(b[j * 32], zp), a[j * 32]);
+                                              acc = __dadd_rn(acc, __dmul_rn(t, z_i));
+                                              z_i = __dmul_rn(z_i, z);
+                                          }
+                                      });
+            prev = __ddiv_rn(acc, __dsub_rn(1.0, __dmul_rn(zp, zp)));
+        } else if (kind == SPL_REFLECT) {
+            double c0 = 0.0;
+            if (warp == 0) {
+                c0 = C_(0);
+                acc = __dadd_rn(__dmul_rn(C_(n - 1), zp), c0);
+            }
+            spline_sweep<true, false>(gcol, colok, pitch, spl_smem, 1, 1, n - 2, -1, n - 1,
+                                      [&](double *a, double *b, int m) {
+                                          for (int j = 0; j < m; ++j) {
+                                              const double t = __dadd_rn(__dmul_rn(b[j * 32], zp), a[j * 32]);
+                                              acc = __dadd_rn(acc, __dmul_rn(t, z_i));
+                                              z_i = __dmul_rn(z_i, z);
+                                          }
+                                      });
+            prev = __dadd_rn(__ddiv_rn(__dmul_rn(z, acc), __dsub_rn(1.0, __dmul_rn(zp, zp))), c0);
+        } else {
+            if (warp == 0) acc = C_(0);
+            spline_sweep<false, false>(gcol, colok, pitch, spl_smem, n - 1, -1, 0, 0, n - 1,
+                                       [&](double *a, double *, int m) {
+                                           for (int j = 0; j < m; ++j) {
+                                               acc = __dadd_rn(acc, __dmul_rn(a[j * 32], z_i));
+                                               z_i = __dmul_rn(z_i, z);
+                                           }
+                                       });
+            prev = __ddiv_rn(acc, __dsub_rn(1.0, z_i));
+        }
+        if (warp == 0 && colok) C_(0) = prev;
+        __syncthreads();
+        // ---- forward recursion over rows 1 .. n-1 -----------------------------------------
+        prev2 = prev;
+        spline_sweep<false, true>(gcol, colok, pitch, spl_smem, 1, 1, 0, 0, n - 1,
+                                  [&](double *a, double *, int m) {
+                                      int j = 0;
+                                      for (; j + 7 < m; j += 8) {   // loads first: the stores alias them
+                                          double v[8];
+#pragma unroll
+                                          for (int k = 0; k < 8; ++k) v[k] = a[(j + k) * 32];
+#pragma unroll
+                                          for (int k = 0; k < 8; ++k) {
+                                              prev2 = prev;
+                                              prev = __dadd_rn(__dmul_rn(prev, z), v[k]);
+                                              a[(j + k) * 32] = prev;
+                                          }
+                                      }
+                                      for (; j < m; ++j) {
+                                          prev2 = prev;
+                                          prev = __dadd_rn(__dmul_rn(prev, z), a[j * 32]);
+                                          a[j * 32] = prev;
+                                      }
+                                  });
+        // ---- anticausal initialisation (prev = c[n-1], prev2 = c[n-2]) ---------------------
+        double next;
+        if (kind == SPL_MIRROR) {
+            const double t = __dadd_rn(__dmul_rn(prev2, z), prev);
+            next = __ddiv_rn(__dmul_rn(t, z), __dsub_rn(__dmul_rn(z, z), 1.0));
+        } else if (kind == SPL_REFLECT) {
+            next = __dmul_rn(__ddiv_rn(z, __dsub_rn(z, 1.0)), prev);
+        } else {
+            acc = prev;
+            z_i = z;
+            spline_sweep<false, false>(gcol, colok, pitch, spl_smem, 0, 1, 0, 0, n - 1,
+                                       [&](double *a, double *, int m) {
+                                           for (int j = 0; j < m; ++j) {
+                                               acc = __dadd_rn(acc, __dmul_rn(a[j * 32], z_i));
+                                               z_i = __dmul_rn(z_i, z);
+                                           }
+                                       });
+            next = __dmul_rn(__ddiv_rn(z, __dsub_rn(z_i, 1.0)), acc);
+        }
+        if (warp == 0 && colok) C_(n - 1) = next;
+        __syncthreads();
+        // ---- backward recursion over rows n-2 .. 0 -----------------------------------------
+        spline_sweep<false, true>(gcol, colok, pitch, spl_smem, n - 2, -1, 0, 0, n - 1,
+                                  [&](double *a, double *, int m) {
+                                      int j = 0;
+                                      for (; j + 7 < m; j += 8) {
+                                          double v[8];
+#pragma unroll
+                                          for (int k = 0; k < 8; ++k) v[k] = a[(j + k) * 32];
+#pragma unroll
+                                          for (int k = 0; k < 8; ++k) {
+                                              next = __dmul_rn(__dsub_rn(next, v[k]), z);
+                                              a[(j + k) * 32] = next;
+                                          }
+                                      }
+                                      for (; j < m; ++j) {
+                                          next = __dmul_rn(__dsub_rn(next, a[j * 32]), z);
+                                          a[j * 32] = next;
+                                      }
+                                  });
+    }
+#undef C_
+}
+
 // ---------------------------------------------------------------------------
 // sampler
 // ---------------------------------------------------------------------------

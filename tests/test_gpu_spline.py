@@ -59,13 +59,19 @@ def test_spline_seeded_image_against_oracle(order, mode):
     assert n_ne <= 1, "%d samples not identical (max %g)" % (n_ne, float(diff.max()))
 
 
-def test_prefilter_coefficients_bit_exact():
-    """dcb_spline_prefilter alone against the oracle's spline_filter (== SciPy's)."""
+@pytest.mark.parametrize("staged", ["auto", "0", "1"])
+def test_prefilter_coefficients_bit_exact(staged, monkeypatch):
+    """dcb_spline_prefilter alone against the oracle's spline_filter (== SciPy's), through
+    the one-thread-per-line kernel, the shared-memory staged kernel, and the library's own
+    choice between them."""
     import ctypes
     from discorpy_b200 import _cabi, device as dev
+    if staged != "auto":
+        monkeypatch.setenv("DCB_SPLINE_STAGED", staged)
     rng = np.random.default_rng(5)
     for shape, dt in (((130, 77), np.float32), ((64, 200), np.float64), ((1, 33), np.float32),
-                      ((45, 1), np.float32)):
+                      ((45, 1), np.float32), ((300, 521), np.float32), ((2, 3), np.float32),
+                      ((65, 129), np.float64)):
         mat = (rng.random(shape) * 200 - 30).astype(dt)
         h, w = shape
         for order in (2, 3, 4, 5):
