@@ -232,6 +232,7 @@ def run_gpu_arm(args, rank, local_rank, world):
         tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = tdist
     dcb.set_device(local_rank)
+    numa_cores = dcb.bind_host_to_device(local_rank) if world > 1 else None   # before any pinned allocation
     post.config["blend"] = {"exact": dcb.BLEND_EXACT, "lerp64": dcb.BLEND_LERP64,
                             "lerp32": dcb.BLEND_LERP32}[args.blend]
     post.config["path"] = {"auto": dcb.PATH_AUTO, "direct": dcb.PATH_DIRECT,
@@ -400,6 +401,7 @@ def run_gpu_arm(args, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": e2e_n * H * W * 4, "d2h_bytes_per_step": e2e_n * H * W * 4,
                 "steps": e2e_steps, "images_per_step_per_gpu": e2e_n,
+                "host_cores_bound_per_rank": len(numa_cores) if numa_cores else None,
                 "api": "discorpy_b200.post.postprocessing.unwarp_image_backward(pinned ndarray)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -46,6 +46,31 @@ def ensure_init():
     return dev
 
 
+def bind_host_to_device(index=None):
+    """Pin the calling process to the CPU cores next to GPU ``index`` (NVML's CPU affinity
+    of the device) so that the pinned staging buffers allocated afterwards are placed on
+    that GPU's NUMA node.  With one process per GPU on a multi-socket host this keeps the
+    host<->device copies off the inter-socket link.  Returns the core set, or None when
+    NVML (``pynvml``) or the information is unavailable -- never an error."""
+    index = ensure_init() if index is None else int(index)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cores = {64 * w + b for w, word in enumerate(words) for b in range(64)
+                 if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cores &= allowed
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
+
+
 def device_count():
     n = ctypes.c_int(0)
     try:
