@@ -81,6 +81,20 @@ __device__ __forceinline__ float finish_f32(float v, int rint) {
     return rint ? truncf(v + (v >= 0.0f ? 0.5f : -0.5f)) : v;
 }
 
+// floor and fraction of a coordinate in [0, 2^23) without the XU pipe (no F2I / I2F): a
+// round-down add of 2^23 (2^52 for float64 coordinates) leaves floor(c) in the low mantissa
+// bits; both subtractions are exact
+__device__ __forceinline__ void split_floor(float c, int &i, float &t) {
+    const float m = __fadd_rd(c, 8388608.0f);
+    i = __float_as_int(m) - 0x4B000000;
+    t = c - (m - 8388608.0f);
+}
+__device__ __forceinline__ void split_floor(double c, int &i, double &t) {
+    const double m = __dadd_rd(c, 4503599627370496.0);
+    i = __double2loint(m);
+    t = __dsub_rn(c, __dsub_rn(m, 4503599627370496.0));
+}
+
 // ---------------------------------------------------------------------------
 // one output pixel: the arithmetic of scipy.ndimage.map_coordinates(order 0|1)
 // for a coordinate that already lies in [0, W-1] x [0, H-1]
@@ -88,10 +102,10 @@ __device__ __forceinline__ float finish_f32(float v, int rint) {
 template <int ORDER, int BLEND, class CT, class Fetch>
 __device__ __forceinline__ float sample_px(const Fetch &fetch, CT x, CT y, int wmax, int ylo,
                                            int yhi, int rint = 0) {
-    int x0 = (int)x;  // truncation == floor, coordinates are >= 0
-    int y0 = (int)y;
-    const CT tx = x - (CT)x0;  // exact
-    const CT ty = y - (CT)y0;
+    int x0, y0;
+    CT tx, ty;
+    split_floor(x, x0, tx);
+    split_floor(y, y0, ty);
     if (ORDER == 0) {
         // SciPy: floor(c + 0.5) evaluated in double; the fractional part of a
         // float is exact, so comparing it with 0.5 is the same decision.

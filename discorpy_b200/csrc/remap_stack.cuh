@@ -39,6 +39,18 @@ constexpr int kStkRows = kStkTileH / kWarps;  // 2 rows per warp
 constexpr int kStkPx = kStkRows * kCols;      // 8 pixels per thread
 constexpr int kStkMaxStages = 8;
 
+// sqrt for the tile geometry: the 5-operation one-ulp form of remap_image.cuh (dsqrt_nz) with
+// the guard for s == 0 (a pixel exactly on the centre) and subnormal s that dsqrt_pos has.
+__device__ __forceinline__ double dsqrt_fast0(double s) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    const double g = s * y;
+    const double e = fma(-g, y, 1.0);
+    const double q = fma(e, 0.375, 0.5) * e;
+    const double r = fma(g, q, g);
+    return (__double2hiint(s) < 0x00100000) ? 0.0 : r;
+}
+
 // How the per-pixel sampling state is kept across the slices of a chunk.
 template <int ORDER, int BLEND, bool ROUND32>
 struct StackWeights {
@@ -121,16 +133,19 @@ __global__ void __launch_bounds__(kThreads, 2)
                 const double yu2 = __dmul_rn(yu, yu);
                 double r[kCols], f[kCols];
 #pragma unroll
-                for (int k = 0; k < kCols; ++k) r[k] = dsqrt_pos(__dadd_rn(xu2[k], yu2));  // :141
+                for (int k = 0; k < kCols; ++k) r[k] = dsqrt_fast0(__dadd_rn(xu2[k], yu2));  // :141
                 radial_factor<kCols>(p.rad.a, p.rad.n, r, f);                              // :142-143
 #pragma unroll
                 for (int k = 0; k < kCols; ++k) {  // :144-145 (image, chunk) / :219-220 (slice)
                     const int i = j * kCols + k;
                     const CT cx = clamp_coord<CT>(fma(f[k], xu[k], p.rad.xc), wmax);
                     const CT cy = clamp_coord<CT>(fma(f[k], yu, p.rad.yc), hmax);
-                    int xi = (int)cx, yi = (int)cy;  // truncation == floor, coordinates are >= 0
-                    tx[i] = cx - (CT)xi;             // exact
-                    ty[i] = cy - (CT)yi;
+                    // floor and fraction of a coordinate in [0, 2^23) without the XU pipe (F2I / I2F):
+                    // a round-down add of 2^23 (2^52 for float64 coordinates) leaves floor(c) in the
+                    // low mantissa bits; both subtractions are exact
+                    int xi, yi;
+                    split_floor(cx, xi, tx[i]);
+                    split_floor(cy, yi, ty[i]);
                     if (ORDER == 0) {
                         // SciPy: floor(c + 0.5) in double == compare the exact fraction with 0.5
                         if (tx[i] >= (CT)0.5) ++xi;
@@ -195,6 +210,19 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
 
         if (fits) {
+            // the first slices start moving before the weights are formed (hides one TMA latency
+            // per item, which matters when a chunk is only a few slices deep)
+            const uint32_t base = fills;
+            if (threadIdx.x == 0) {
+                const int npre = min(nz, p.nstage - 1);
+                for (int s = 0; s < npre; ++s) {
+                    const uint32_t g = base + s, st = g % S;
+                    if (g >= S) mbar_wait(&empty[st], ((g / S) - 1u) & 1u);
+                    mbar_expect_tx(&full[st], p.box_bytes);
+                    tma_load_3d(smem + (size_t)st * p.stage_bytes, &tmap, bx0, by0 - p.yorg, z0 + s,
+                                &full[st]);
+                }
+            }
             // ---- per-pixel state kept across the chunk --------------------------------
             int off[kStkPx];
             double wd[kStkPx][SW::kDoubles > 0 ? SW::kDoubles : 1];
@@ -215,17 +243,6 @@ __global__ void __launch_bounds__(kThreads, 2)
                 } else if (SW::kF32) {
                     wf[i][0] = (float)tx[i];
                     wf[i][1] = (float)ty[i];
-                }
-            }
-            const uint32_t base = fills;
-            if (threadIdx.x == 0) {
-                const int npre = min(nz, p.nstage - 1);
-                for (int s = 0; s < npre; ++s) {
-                    const uint32_t g = base + s, st = g % S;
-                    if (g >= S) mbar_wait(&empty[st], ((g / S) - 1u) & 1u);
-                    mbar_expect_tx(&full[st], p.box_bytes);
-                    tma_load_3d(smem + (size_t)st * p.stage_bytes, &tmap, bx0, by0 - p.yorg, z0 + s,
-                                &full[st]);
                 }
             }
             float *orow = p.dst + (long long)z0 * p.dst_slice +
