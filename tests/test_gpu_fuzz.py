@@ -1,0 +1,17 @@
+"""GPU: randomised differential test against the oracle (tools/fuzz_parity.py): random shapes,
+centres inside and far outside the image, polynomial lengths, orders 0..5, all boundary modes,
+six dtypes, perspective maps and row chunks of stacks -- every output bit-identical."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_random_cases_bit_identical(seed):
+    import fuzz_parity
+    assert fuzz_parity.run(250, seed) == 0
