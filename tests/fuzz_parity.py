@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""Randomised differential test of the CUDA path against the oracle (run on a GPU box):
+"""Randomised differential test of the CUDA path against the oracle (run on a GPU box; lives under
+tests/ because only tests may use the oracle):
 random shapes, centres (also far outside the image), polynomial lengths and strengths,
 orders 0 / 1 / 2..5, modes, dtypes, perspective coefficients, row chunks of stacks.
-Prints every case whose outputs are not bit-identical.  Usage: fuzz_parity.py [N] [seed]"""
+Prints every case whose outputs are not bit-identical.  Usage: python tests/fuzz_parity.py [N] [seed]"""
 import os
 import sys
 

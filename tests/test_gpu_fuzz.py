@@ -1,4 +1,4 @@
-"""GPU: randomised differential test against the oracle (tools/fuzz_parity.py): random shapes,
+"""GPU: randomised differential test against the oracle (tests/fuzz_parity.py): random shapes,
 centres inside and far outside the image, polynomial lengths, orders 0..5, all boundary modes,
 six dtypes, perspective maps and row chunks of stacks -- every output bit-identical."""
 import os
@@ -6,7 +6,7 @@ import sys
 
 import pytest
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 

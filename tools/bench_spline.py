@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Device-timed cost of the spline path (dcb_spline_prefilter + dcb_spline_remap) on a
-4096 x 4096 float32 image, 5-term radial model, per order / mode; the reference's CPU
-time for the same call (scipy through oracle_np.unwarp_rows_scipy) beside it on request.
+4096 x 4096 float32 image, 5-term radial model, per order / mode; with --cpu the reference's
+own code path for the same call (NumPy float64 coordinates + scipy.ndimage.map_coordinates,
+postprocessing.py:138-147) is timed beside it on one host core.
 Usage: bench_spline.py [--size N] [--cpu]"""
 import argparse
 import ctypes
@@ -63,10 +64,15 @@ def main():
         row["total_ms"] = row["prefilter_ms"] + row["remap_ms"]
         row["Mpix_s"] = n * n / 1e6 / (row["total_ms"] * 1e-3)
         if args.cpu and order == 3 and mode == "reflect":
-            from oracle import oracle_np
+            from scipy.ndimage import map_coordinates
             mat = src.to_host()
             t0 = time.perf_counter()
-            oracle_np.unwarp_rows_scipy(mat, model.xc, model.yc, fact, 0, n, order=3, mode=mode)
+            xu, yu = np.meshgrid(np.arange(n) - model.xc, np.arange(n) - model.yc)
+            ru = np.sqrt(xu ** 2 + yu ** 2)
+            fmat = np.sum(np.asarray([a * ru ** i for i, a in enumerate(fact)]), axis=0)
+            xd = np.float32(np.clip(model.xc + fmat * xu, 0, n - 1))
+            yd = np.float32(np.clip(model.yc + fmat * yu, 0, n - 1))
+            map_coordinates(mat, (np.reshape(yd, (-1, 1)), np.reshape(xd, (-1, 1))), order=3, mode=mode)
             row["cpu_reference_path_s_1core"] = time.perf_counter() - t0
         print(json.dumps(row), flush=True)
         dcb.device.device_pool.give(work)
