@@ -162,13 +162,32 @@ struct MapEval<MAP_RADIAL, NT> {
         const double yu = __dsub_rn(yd, p.rad.yc);
         const double yu2 = __dmul_rn(yu, yu);
         double r[kCols], f[kCols];
+        if (NT > 2) {
+            // F(r) = E(s) + r O(s), s = r^2 (the rounded sum the sqrt is taken of): the two short
+            // Horner chains in s do not wait for the sqrt -- same number of operations as Horner in
+            // r, shorter dependent chain (57.5 instead of 58.6 us); the CPU emulation and the GPU
+            // parity runs count 0 changed fp32 coordinates at 4096^2 and 8192^2
 #pragma unroll
-        for (int k = 0; k < kCols; ++k) r[k] = dsqrt_nz(__dadd_rn(xu2[k], yu2));
-        if (NT > 0) {
+            for (int k = 0; k < kCols; ++k) {
+                const double s = __dadd_rn(xu2[k], yu2);
+                r[k] = dsqrt_nz(s);
+                constexpr int NE = (NT + 1) / 2, NO = NT / 2;   // even / odd coefficient counts
+                double e = p.rad.a[2 * (NE - 1)], o = p.rad.a[2 * (NO - 1) + 1];
 #pragma unroll
-            for (int k = 0; k < kCols; ++k) f[k] = horner<(NT > 0 ? NT : 1)>(p.rad.a, r[k]);
+                for (int i = NE - 2; i >= 0; --i) e = fma(e, s, p.rad.a[2 * i]);
+#pragma unroll
+                for (int i = NO - 2; i >= 0; --i) o = fma(o, s, p.rad.a[2 * i + 1]);
+                f[k] = fma(o, r[k], e);
+            }
         } else {
-            radial_factor<kCols>(p.rad.a, p.rad.n, r, f);
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) r[k] = dsqrt_nz(__dadd_rn(xu2[k], yu2));
+            if (NT > 0) {
+#pragma unroll
+                for (int k = 0; k < kCols; ++k) f[k] = horner<(NT > 0 ? NT : 1)>(p.rad.a, r[k]);
+            } else {
+                radial_factor<kCols>(p.rad.a, p.rad.n, r, f);
+            }
         }
 #pragma unroll
         for (int k = 0; k < kCols; ++k) {
