@@ -1227,13 +1227,10 @@ int dcb_spline_prefilter(const void *src, int src_is_f64, int H, int W, size_t s
     if (order > 1) {
         // lines of >= 256 samples go through the shared-memory staged kernel, short ones through
         // the one-thread-per-line kernel (DCB_SPLINE_STAGED=0/1 forces one of them: diagnostics)
-        static bool attr_set = false;
-        if (!attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute((const void *)spline_filter_cols_staged_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kSplSmemBytes));
-            attr_set = true;
-        }
+        // (per device and cheap: set on every call, like the remap planners do)
+        CUDA_TRY(cudaFuncSetAttribute((const void *)spline_filter_cols_staged_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSplSmemBytes));
         int force = -1;
         if (const char *env = getenv("DCB_SPLINE_STAGED")) force = atoi(env);
         auto filter_cols = [&](double *a, int pitch, int n, int ncols, const SplinePoles &pp) {
