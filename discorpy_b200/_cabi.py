@@ -90,6 +90,9 @@ SIGNATURES = {
     "dcb_event_sync": [_vp],
     "dcb_stream_wait_event": [_vp, _vp],
     "dcb_event_elapsed_ms": [_vp, _vp, ctypes.POINTER(ctypes.c_float)],
+    "dcb_ipc_export": [_vp, _vp],
+    "dcb_ipc_open": [_vp, ctypes.POINTER(_vp)],
+    "dcb_ipc_close": [_vp],
     "dcb_unwarp_image_backward_f32": [_vp, _vp, _i, _i, _sz, _sz,
                                       ctypes.POINTER(Radial),
                                       ctypes.POINTER(Options), _vp],

@@ -658,6 +658,27 @@ int dcb_event_elapsed_ms(void *start, void *stop, float *ms) {
     return DCB_OK;
 }
 
+// ---- peer windows: a dcb_malloc buffer of one process mapped into another (8e) ----
+static_assert(sizeof(cudaIpcMemHandle_t) == DCB_IPC_HANDLE_BYTES, "IPC handle size");
+int dcb_ipc_export(const void *dptr, void *handle_host) {
+    REQUIRE(dptr != nullptr && handle_host != nullptr, "dptr / handle is NULL");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<void *>(dptr)));
+    memcpy(handle_host, &h, sizeof(h));
+    return DCB_OK;
+}
+int dcb_ipc_open(const void *handle_host, void **peer_dptr) {
+    REQUIRE(handle_host != nullptr && peer_dptr != nullptr, "handle / peer_dptr is NULL");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_host, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(peer_dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DCB_OK;
+}
+int dcb_ipc_close(void *peer_dptr) {
+    CUDA_TRY(cudaIpcCloseMemHandle(peer_dptr));
+    return DCB_OK;
+}
+
 // ---- hot path -----------------------------------------------------------------
 static int radial_to_dev(const dcb_radial *m, RadialDev *out) {
     REQUIRE(m != nullptr, "radial model is NULL");

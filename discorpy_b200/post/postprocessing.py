@@ -239,6 +239,19 @@ def unwarp_slice_backward(mat3D, xcenter, ycenter, list_fact, index):
     array_like
         2D float32 array (depth, width).
     """
+    dst = _unwarp_slice_into(mat3D, xcenter, ycenter, list_fact, index, None)
+    if isinstance(mat3D, DeviceArray):
+        return dst
+    stream = _dev.current_stream()
+    return dst.to_host(stream=stream).reshape(dst.shape)
+
+
+def _unwarp_slice_into(mat3D, xcenter, ycenter, list_fact, index, dst):
+    """Body of :func:`unwarp_slice_backward`: the (depth, width) sinogram is
+    written to ``dst`` -- anything with ``ptr`` / ``pitch`` (bytes between the
+    rows of the sinogram) in device-addressable memory, e.g. this rank's rows
+    of a peer window (``multigpu.SinogramWindow``) -- or to a new DeviceArray
+    when ``dst`` is None.  Asynchronous on the current stream."""
     on_device = isinstance(mat3D, DeviceArray)
     if len(mat3D.shape) < 3:
         raise ValueError("Input must be a 3D data")
@@ -255,22 +268,32 @@ def unwarp_slice_backward(mat3D, xcenter, ycenter, list_fact, index):
             % index)
     model = _cabi.make_radial(xcenter, ycenter, list_fact)
     stream = _dev.current_stream()
-    dst = DeviceArray((depth, 1, width))
+    if dst is None:
+        dst = DeviceArray((depth, width))
+    # the kernel sees the sinogram as a stack of depth x (1, width) slices
+    out = _SliceRows(dst.ptr, dst.pitch)
     if on_device:
         src_ptr = mat3D.ptr + yd_min * mat3D.pitch
-        _stack_call(src_ptr, dst, depth, height, width, yd_min,
+        _stack_call(src_ptr, out, depth, height, width, yd_min,
                     yd_max - yd_min, mat3D.pitch, mat3D.slice_stride, index, 1,
                     0, model, stream)
-        dst.shape = (depth, width)
         return dst
     # integer stacks: SciPy rounds each slice to the stack's dtype before the
     # reference stores it into the float32 sinogram (:227-228)
     win_np, flags, _ = _as_f32_image(np.asarray(mat3D[:, yd_min:yd_max, :]))
     win = DeviceArray.from_host(win_np, stream)
-    _stack_call(win.ptr, dst, depth, height, width, yd_min, yd_max - yd_min,
+    _stack_call(win.ptr, out, depth, height, width, yd_min, yd_max - yd_min,
                 win.pitch, win.slice_stride, index, 1, 0, model, stream,
                 flags=flags)
-    return dst.to_host(stream=stream).reshape(depth, width)
+    dst._keep = win     # the upload stays alive until the caller is done with dst
+    return dst
+
+
+class _SliceRows:
+    """Destination of the one-row-per-slice launch: rows ``pitch`` bytes apart."""
+
+    def __init__(self, ptr, pitch):
+        self.ptr, self.pitch, self.slice_stride = ptr, pitch, pitch
 
 
 def _mapping(mat, xmat, ymat):

@@ -124,6 +124,18 @@ int dcb_event_sync(void *event);
 int dcb_stream_wait_event(void *stream, void *event); /* later work on `stream` waits for `event` */
 int dcb_event_elapsed_ms(void *start, void *stop, float *ms);
 
+/* ---- peer windows (one process per GPU): a device buffer of one rank mapped into the others.
+ * when the caller wants ONE sinogram (D x W) assembled on one GPU, every rank's
+ * unwarp_slice_backward kernel (postprocessing.py:188-229, one output row per slice) writes its D/N
+ * rows straight into the owner's buffer -- the stores of the remap epilogue travel over
+ * NVLink / NVSwitch, there is no separate gather collective.  `dptr` must be the base address of a
+ * dcb_malloc allocation; the handle is DCB_IPC_HANDLE_BYTES opaque bytes that the caller moves to
+ * the other processes (torch.distributed broadcast in discorpy_b200.multigpu). */
+#define DCB_IPC_HANDLE_BYTES 64
+int dcb_ipc_export(const void *dptr, void *handle_host);
+int dcb_ipc_open(const void *handle_host, void **peer_dptr); /* maps it, enabling peer access */
+int dcb_ipc_close(void *peer_dptr);
+
 /* ---- the hot path -------------------------------------------------------- */
 
 /* Replaces discorpy/post/postprocessing.py:111-148 `unwarp_image_backward`

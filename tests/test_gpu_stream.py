@@ -1,6 +1,8 @@
 """GPU: the streaming Z-stack entry (discorpy_b200/post/streaming.py) returns exactly
 what unwarp_chunk_slices_backward returns (same kernel, same window) and what the
 oracle computes, for in-memory, memory-mapped and pinned sources."""
+import os
+
 import numpy as np
 import pytest
 
@@ -69,3 +71,22 @@ def test_stream_argument_errors():
         streaming.unwarp_chunk_slices_backward_stream(st, 4, 4, [1.0], 0, 8)
     with pytest.raises(NotImplementedError):
         streaming.unwarp_chunk_slices_backward_stream(st.astype(np.float64), 4, 4, [1.0])
+
+
+@pytest.mark.gpu
+def test_sinogram_exchange_two_ranks():
+    """SURVEY.md 8e, the optional exchange step: two ranks (one per GPU) assemble one sinogram on
+    rank 0 by peer stores of the remap kernel and by an NCCL all-gather; both bit-identical to the
+    oracle (tests/two_rank_sinogram_check.py).  Needs two GPUs on the box."""
+    import subprocess
+    import sys
+    import discorpy_b200
+    if discorpy_b200.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29617",
+           os.path.join(root, "tests", "two_rank_sinogram_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, (res.stdout[-1500:], res.stderr[-1500:])
+    assert '"ok": true' in res.stdout

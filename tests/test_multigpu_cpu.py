@@ -1,5 +1,7 @@
-"""N > 1 host logic on CPU: two gloo ranks broadcast the coefficient block and
-shard a stack; no data-path collective exists to test."""
+"""N > 1 host logic on CPU: two gloo ranks broadcast the coefficient block, shard a
+stack and run the collective form of the optional sinogram exchange:
+gather_rows with uneven shards, broadcast_bytes (the IPC-handle exchange of the fused
+form; the peer mapping itself needs two GPUs: tests/two_rank_sinogram_check.py)."""
 import os
 import socket
 import subprocess
@@ -50,6 +52,17 @@ params = dict(xcenter=1283.4, ycenter=1275.9,
               list_fact=[1.0, -2e-5, 6e-8, -1e-10, 5e-14]) if rank == 0 else None
 got = multigpu.broadcast_params(params, src=0)
 lo, hi = multigpu.shard_range(11, rank, world)
+# sinogram exchange, collective form: rank r owns rows [lo, hi) of an 11 x 7 array
+full = np.arange(77, dtype=np.float32).reshape(11, 7) * 0.5
+got_full = multigpu.gather_rows(full[lo:hi].copy(), 11)
+assert got_full.dtype == np.float32 and np.array_equal(got_full, full), got_full
+try:
+    multigpu.gather_rows(full[:1], 11)
+    raise SystemExit("gather_rows accepted a block of the wrong size")
+except ValueError:
+    pass
+blob = multigpu.broadcast_bytes(bytes(range(72)) if rank == 1 else b"", 72, src=1)
+assert blob == bytes(range(72))
 # one file per rank: two ranks writing to the shared stdout pipe can interleave
 with open(os.path.join(%(out)r, "rank%%d.json" %% rank), "w") as f:
     json.dump(dict(rank=rank, world=world, params=got, shard=[lo, hi]), f)
