@@ -349,6 +349,11 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
         }
         bw = std::max(bw, 4);
         bh = std::max(bh, 1);
+        if (kImgBoxW > 0) {   // fixed box width: the kernel samples with a compile-time pitch
+            if (bw > kImgBoxW || (long long)kImgBoxW * bh * 4 > max_stage) fallback_box = true;
+            bw = kImgBoxW;
+            bh = std::min(bh, max_stage / (bw * 4));
+        }
     }
     // uneven tiles (clipped regions, tiles that will not fit the box): deal them round-robin
     p.deal = (fallback_box || map_clips_at_border(p, map_kind)) ? 1 : 0;

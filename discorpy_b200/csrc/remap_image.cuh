@@ -34,6 +34,13 @@
 
 namespace dcb {
 
+// > 0: every staged box of the single-image kernel is this many floats wide, so the pitch of the
+// staged tile is a compile-time constant in the sampling loop (tap addresses become immediates).
+#ifndef DCB_IMG_BOXW
+#define DCB_IMG_BOXW 144   // 0 in A/B builds: box as wide as the footprint bound, run-time pitch
+#endif
+constexpr int kImgBoxW = DCB_IMG_BOXW;
+
 struct ImageParams {
     const float *src;
     float *dst;
@@ -51,6 +58,22 @@ struct ImageParams {
     RadialDev rad;
     PerspDev per;
 };
+
+// One float64 tap of the widened tile through a 32-bit shared address with a compile-time byte
+// offset: the tile base is pinned in a register once per tile instead of being re-derived from the
+// generic pointer in every row (ptxas rematerialised S2UR / ULEA / LOP3 / LDC / IMAD per row under
+// the 96-register budget).  Together with the fixed box width: 237 -> 217 instructions per row of
+// 4 x 32 pixels; lerp64 55.3 -> 53.7 us, lerp32 45.1 -> 44.0, exact 57.5 -> 57.4 (not issue-bound).
+// -DDCB_IMG_LDS32=0 restores the generic-pointer loads for A/B builds.
+template <int OFF>
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+#ifndef DCB_IMG_LDS32
+#define DCB_IMG_LDS32 1
+#endif
 
 struct TileBox {
     int bx0, by0;  // image coordinates of box element (0,0)
@@ -455,12 +478,15 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             // fast-path window: footprint inside the box and strictly inside the image
             const int lim_x = box.use ? min(p.bw - 1, wmax - box.bx0) : 0;
             const int lim_y = box.use ? min(p.bh - 1, p.ylast - box.by0) : 0;
-            const int bw = p.bw;
+            const int bw = kImgBoxW > 0 ? kImgBoxW : p.bw;
             const int sb = i & 1;
             const float *rawt =
                 reinterpret_cast<const float *>(smem + (size_t)sb * p.stage_bytes);
             const double *widet = reinterpret_cast<const double *>(
                 smem + (size_t)(1 + 2 * sb) * p.stage_bytes);
+            // (ordered after the mbarrier wait above: every tap address below depends on it)
+            uint32_t wide_s = smem_u32(widet);
+            asm volatile("" : "+r"(wide_s)::"memory");
             const bool full_w = (txi * kTileW + kTileW - 1 <= wmax);  // CTA-uniform
             float *orow = p.dst + (long long)(y_base - p.row0) * p.dst_pitch + x_base;
             double yd = (double)y_base;
@@ -469,6 +495,10 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
 #endif
             constexpr int kRowUnroll = DCB_IMG_UNROLL;   // A/B builds; 1 measured best
 #pragma unroll kRowUnroll
+            // (Rows claimed one at a time from a shared counter by whichever sampling warp is free,
+            // instead of this static split, were measured: 61.5 / 59.4 / 49.4 us against 57.4 / 53.8 /
+            // 44.0 -- the atomic and the lost incremental row state cost more than the 8 % the
+            // warps wait for each other at tile boundaries.)
             for (int j = 0; j < nrow; ++j, yd += 1.0, orow += p.dst_pitch) {
                 float xf[kCols], yf[kCols];
                 ev.row(p, yd, xf, yf);
@@ -503,9 +533,16 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                             const float bot = fmaf(d - c, tx, c);
                             v[k] = fmaf(bot - top, ty, top);
                         } else {
-                            const double *q = widet + idx;
-                            const double a = q[0], b = q[1];
-                            const double c = q[bw], d = q[bw + 1];
+                            double a, b, c, d;
+                            if (DCB_IMG_LDS32 && kImgBoxW > 0) {
+                                const uint32_t qa = wide_s + 8u * (uint32_t)idx;
+                                a = lds_f64<0>(qa), b = lds_f64<8>(qa);
+                                c = lds_f64<8 * kImgBoxW>(qa), d = lds_f64<8 * kImgBoxW + 8>(qa);
+                            } else {
+                                const double *q = widet + idx;
+                                a = q[0], b = q[1];
+                                c = q[bw], d = q[bw + 1];
+                            }
                             // (an integer-pipe widening of tx, ty -- one IMAD.WIDE + a select for
                             // zero -- was measured: 64.7 us instead of 61.7 us; F2F stays)
                             const double wx1 = (double)tx, wy1 = (double)ty;
