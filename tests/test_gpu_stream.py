@@ -90,3 +90,26 @@ def test_sinogram_exchange_two_ranks():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert res.returncode == 0, (res.stdout[-1500:], res.stderr[-1500:])
     assert '"ok": true' in res.stdout
+
+
+@pytest.mark.gpu
+def test_sinogram_window_single_rank():
+    """The fused sinogram path with one rank (no process group): the window is a plain device buffer
+    and unwarp_slice_backward_sharded must equal unwarp_slice_backward and the oracle."""
+    from discorpy_b200 import multigpu
+    rng = np.random.default_rng(11)
+    stack = rng.random((9, 120, 200), dtype=np.float32)
+    params = dict(xcenter=101.3, ycenter=58.6, list_fact=FACT)
+    window = multigpu.SinogramWindow(9, 200, owner=0)
+    assert window.rows == (0, 9) and window.world == 1
+    shard = dcb.DeviceArray.from_host(stack)
+    for index in (0, 57, 119):
+        multigpu.unwarp_slice_backward_sharded(shard, params, index, window)
+        window.fence()
+        got = window.array.to_host()
+        want = orc.unwarp_slice_backward(stack, 101.3, 58.6, FACT, index)
+        assert np.array_equal(got, want)
+        assert np.array_equal(got, post.unwarp_slice_backward(stack, 101.3, 58.6, FACT, index))
+    with pytest.raises(ValueError):
+        multigpu.unwarp_slice_backward_sharded(dcb.DeviceArray((4, 120, 200)), params, 3, window)
+    window.close()
