@@ -7,7 +7,11 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
+#include <vector>
+#include <pthread.h>
 
 #include "remap.cuh"
 #include "remap_image.cuh"
@@ -548,6 +552,93 @@ int dcb_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, siz
     return DCB_OK;
 }
 
+namespace {
+// Pageable (ordinary malloc / NumPy) source images: cudaMemcpyAsync from pageable memory is staged
+// by the driver on ONE thread (measured: 6.3 ms for a 4096^2 float32 image against 1.8 ms from
+// pinned memory).  Instead a few host threads copy each row band into a pinned staging buffer while
+// the DMA engine is still moving the previous band.  One process-wide pool, created on first use;
+// calls are serialised (the copy is memory-bound, two at once would not go faster).
+class CopyPool {
+public:
+    struct Job {
+        const char *src;
+        char *dst;
+        size_t src_pitch, dst_pitch, width_bytes;
+        int rows;
+    };
+    static CopyPool &get() {
+        static CopyPool *pool = nullptr;   // leaked on purpose: worker threads outlive static dtors
+        static std::once_flag once;
+        std::call_once(once, [] {
+            pool = new CopyPool();
+            pthread_atfork(nullptr, nullptr, [] { get().forked_ = true; });
+        });
+        return *pool;
+    }
+    void run(const Job &j) {
+        std::lock_guard<std::mutex> serial(run_mu_);
+        if (forked_ || nth_ <= 1 || (size_t)j.rows * j.width_bytes < (1u << 20)) {
+            copy_rows(j, 0, j.rows);   // small band (or a forked child without the workers): inline
+            return;
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        job_ = j;
+        pending_ = nth_;
+        ++gen_;
+        cv_go_.notify_all();
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+private:
+    CopyPool() {
+        const unsigned hc = std::thread::hardware_concurrency();
+        nth_ = (int)std::max(1u, std::min(8u, hc / 2));
+        if (const char *env = getenv("DCB_COPY_THREADS")) nth_ = std::max(1, std::min(64, atoi(env)));
+        if (nth_ > 1)
+            for (int i = 0; i < nth_; ++i) std::thread(&CopyPool::worker, this, i).detach();
+    }
+    static void copy_rows(const Job &j, int r0, int r1) {
+        if (j.src_pitch == j.width_bytes && j.dst_pitch == j.width_bytes) {
+            memcpy(j.dst + (size_t)r0 * j.dst_pitch, j.src + (size_t)r0 * j.src_pitch,
+                   (size_t)(r1 - r0) * j.width_bytes);
+            return;
+        }
+        for (int r = r0; r < r1; ++r)
+            memcpy(j.dst + (size_t)r * j.dst_pitch, j.src + (size_t)r * j.src_pitch, j.width_bytes);
+    }
+    void worker(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_go_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+            const Job j = job_;
+            lk.unlock();
+            copy_rows(j, (int)((long long)j.rows * id / nth_), (int)((long long)j.rows * (id + 1) / nth_));
+            lk.lock();
+            if (--pending_ == 0) cv_done_.notify_one();
+        }
+    }
+    std::mutex run_mu_, mu_;
+    std::condition_variable cv_go_, cv_done_;
+    Job job_{};
+    uint64_t gen_ = 0;
+    int pending_ = 0, nth_ = 1;
+    bool forked_ = false;
+};
+
+// is `p` ordinary pageable host memory (neither cudaHostAlloc'ed nor registered)?
+bool is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+}  // namespace
+
 // ---- memory / streams / events ---------------------------------------------
 int dcb_malloc(void **dptr, size_t nbytes) {
     REQUIRE(dptr != nullptr, "dptr is NULL");
@@ -789,6 +880,8 @@ struct HostPipe {
     cudaEvent_t ev_up[kMaxBands], ev_run[kMaxBands], ev_free = nullptr;
     void *dsrc = nullptr, *ddst = nullptr;
     size_t src_cap = 0, dst_cap = 0;
+    void *hstage = nullptr;   // pinned staging copy of a pageable source image
+    size_t stage_cap = 0;
     int device = -1;
     bool ok = false;
 };
@@ -801,6 +894,7 @@ int pipe_prepare(size_t src_bytes, size_t dst_bytes) {
     if (hp.ok && hp.device != dev) {  // the thread moved to another GPU: start over
         cudaFree(hp.dsrc);
         cudaFree(hp.ddst);
+        if (hp.hstage) cudaFreeHost(hp.hstage);
         hp = HostPipe();
     }
     if (!hp.ok) {
@@ -894,37 +988,61 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
     const int rows_per = (H + nbands - 1) / nbands;
     nbands = (H + rows_per - 1) / rows_per;
     char *dsrc = (char *)hp.dsrc, *ddst = (char *)hp.ddst;
-    // uploads, in row order
-    for (int b = 0; b < nbands; ++b) {
-        const int r0 = b * rows_per, nr = std::min(rows_per, H - r0);
-        CUDA_TRY(cudaMemcpy2DAsync(dsrc + (size_t)r0 * pitch, pitch,
-                                   (const char *)src_host + (size_t)r0 * src_pitch_host,
-                                   src_pitch_host, (size_t)W * 4, nr, cudaMemcpyHostToDevice, hp.up));
-        CUDA_TRY(cudaEventRecord(hp.ev_up[b], hp.up));
+    // pageable source: bands go through a pinned staging buffer filled by the copy pool
+    const bool stage = is_pageable(src_host);
+    const size_t wbytes = (size_t)W * 4;
+    if (stage && hp.stage_cap < wbytes * (size_t)H) {
+        if (hp.hstage) CUDA_TRY(cudaFreeHost(hp.hstage));
+        hp.hstage = nullptr;
+        hp.stage_cap = 0;
+        CUDA_TRY(cudaHostAlloc(&hp.hstage, wbytes * (size_t)H, cudaHostAllocDefault));
+        hp.stage_cap = wbytes * (size_t)H;
     }
-    // per band: wait for the last source row it can touch, unwarp its rows, download them
-    int waited = -1;
+    // last upload band each output band needs: the last source row it can touch
+    int need[kMaxBands];
     for (int b = 0; b < nbands; ++b) {
         const int r0 = b * rows_per, nr = std::min(rows_per, H - r0);
         int lo, hi;
         radial_row_range(*model, H, W, r0, r0 + nr, &lo, &hi);
-        const int need = std::min(nbands - 1, hi / rows_per);
-        if (need > waited) {
-            CUDA_TRY(cudaStreamWaitEvent(hp.run, hp.ev_up[need], 0));
-            waited = need;
+        need[b] = std::min(nbands - 1, hi / rows_per);
+    }
+    // uploads in row order; an output band is unwarped (second stream) as soon as the upload it
+    // needs has been enqueued, and downloaded (third stream) behind its kernel
+    int next = 0, waited = -1;
+    for (int b = 0; b < nbands; ++b) {
+        const int r0 = b * rows_per, nr = std::min(rows_per, H - r0);
+        const char *from = (const char *)src_host + (size_t)r0 * src_pitch_host;
+        size_t from_pitch = src_pitch_host;
+        if (stage) {
+            char *to = (char *)hp.hstage + (size_t)r0 * wbytes;
+            CopyPool::get().run({from, to, src_pitch_host, wbytes, wbytes, nr});
+            from = to;
+            from_pitch = wbytes;
         }
-        rc = dcb_unwarp_stack_backward_f32((const float *)dsrc, (float *)(ddst + (size_t)r0 * pitch), 1,
-                                           H, W, 0, H, pitch, pitch * (size_t)H, pitch,
-                                           pitch * (size_t)nr, r0, nr, 1, model, opt, hp.run);
-        if (rc) {
-            cudaDeviceSynchronize();
-            return rc;
+        CUDA_TRY(cudaMemcpy2DAsync(dsrc + (size_t)r0 * pitch, pitch, from, from_pitch, wbytes, nr,
+                                   cudaMemcpyHostToDevice, hp.up));
+        CUDA_TRY(cudaEventRecord(hp.ev_up[b], hp.up));
+        // (pinned source: every upload is enqueued before the first launch, as measured best)
+        if (!stage && b < nbands - 1) continue;
+        for (; next < nbands && (need[next] <= b || b == nbands - 1); ++next) {
+            const int q0 = next * rows_per, qn = std::min(rows_per, H - q0);
+            if (need[next] > waited) {
+                CUDA_TRY(cudaStreamWaitEvent(hp.run, hp.ev_up[need[next]], 0));
+                waited = need[next];
+            }
+            rc = dcb_unwarp_stack_backward_f32((const float *)dsrc, (float *)(ddst + (size_t)q0 * pitch),
+                                               1, H, W, 0, H, pitch, pitch * (size_t)H, pitch,
+                                               pitch * (size_t)qn, q0, qn, 1, model, opt, hp.run);
+            if (rc) {
+                cudaDeviceSynchronize();
+                return rc;
+            }
+            CUDA_TRY(cudaEventRecord(hp.ev_run[next], hp.run));
+            CUDA_TRY(cudaStreamWaitEvent(hp.down, hp.ev_run[next], 0));
+            CUDA_TRY(cudaMemcpy2DAsync((char *)dst_host + (size_t)q0 * dst_pitch_host, dst_pitch_host,
+                                       ddst + (size_t)q0 * pitch, pitch, wbytes, qn,
+                                       cudaMemcpyDeviceToHost, hp.down));
         }
-        CUDA_TRY(cudaEventRecord(hp.ev_run[b], hp.run));
-        CUDA_TRY(cudaStreamWaitEvent(hp.down, hp.ev_run[b], 0));
-        CUDA_TRY(cudaMemcpy2DAsync((char *)dst_host + (size_t)r0 * dst_pitch_host, dst_pitch_host,
-                                   ddst + (size_t)r0 * pitch, pitch, (size_t)W * 4, nr,
-                                   cudaMemcpyDeviceToHost, hp.down));
     }
     CUDA_TRY(cudaStreamSynchronize(hp.down));
     CUDA_TRY(cudaStreamSynchronize(hp.run));

@@ -160,6 +160,12 @@ def unwarp_image_backward(mat, xcenter, ycenter, list_fact, order=1,
     model = _cabi.make_radial(xcenter, ycenter, list_fact)
     if _wants_spline(mat, order):
         return _spline.remap(mat, order, mode, _cabi.MAP_RADIAL, radial=model)[0]
+    if not on_device and mat.dtype in _INT_IMAGE_DTYPES:
+        # integer images cross PCIe in their own dtype (2-4 x fewer bytes); widening and SciPy's
+        # round-half-away narrowing happen on the device, not in NumPy on one host core
+        # (4096^2 uint16: 29 ms -> see profiles/r1/e2e_dtypes.txt)
+        return _unwarp_frame_hwc(mat[:, :, None], xcenter, ycenter, list_fact,
+                                 order)[:, :, 0]
     if not on_device:
         # host in, host out: banded upload / compute / download pipeline
         src, flags, out_dtype = _as_f32_image(mat)
