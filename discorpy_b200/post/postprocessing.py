@@ -37,7 +37,10 @@ _MODES = ("reflect", "grid-mirror", "constant", "grid-constant", "nearest",
           "mirror", "grid-wrap", "wrap")
 
 #: blend / path used by the hot functions; see include/discorpy_b200.h
-config = {"blend": _cabi.BLEND_EXACT, "path": _cabi.PATH_AUTO, "bands": 0}
+config = {"blend": _cabi.BLEND_EXACT, "path": _cabi.PATH_AUTO, "bands": 0,
+          # host float32 stacks whose row window is at least this large go through the
+          # three-stream block pipeline of post/streaming.py (upload, kernel and download overlap)
+          "stream_bytes": 256 << 20}
 
 
 # ---------------------------------------------------------------------------
@@ -286,8 +289,7 @@ def _unwarp_slice_into(mat3D, xcenter, ycenter, list_fact, index, dst):
         return dst
     # integer stacks: SciPy rounds each slice to the stack's dtype before the
     # reference stores it into the float32 sinogram (:227-228)
-    win_np, flags, _ = _as_f32_image(np.asarray(mat3D[:, yd_min:yd_max, :]))
-    win = DeviceArray.from_host(win_np, stream)
+    win, flags, _ = _upload_native(mat3D[:, yd_min:yd_max, :], stream)
     _stack_call(win.ptr, out, depth, height, width, yd_min, yd_max - yd_min,
                 win.pitch, win.slice_stride, index, 1, 0, model, stream,
                 flags=flags)
@@ -401,13 +403,19 @@ def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
                     yd_max - yd_min, mat3D.pitch, mat3D.slice_stride,
                     start_index, nrows, 1, model, stream)
         return dst
-    win_np, flags, out_dtype = _as_f32_image(
-        np.asarray(mat3D[:, yd_min:yd_max, :]))
-    win = DeviceArray.from_host(win_np, stream)
+    win_bytes = depth * (yd_max - yd_min) * width * 4
+    if (np.dtype(mat3D.dtype) == np.float32 and depth >= 4
+            and win_bytes >= config["stream_bytes"]):
+        from . import streaming
+        del dst
+        return streaming.unwarp_chunk_slices_backward_stream(
+            mat3D, xcenter, ycenter, list_fact, start_index, stop_index,
+            block_bytes=int(min(256 << 20, max(32 << 20, win_bytes // 8))))
+    win, flags, out_dtype = _upload_native(mat3D[:, yd_min:yd_max, :], stream)
     _stack_call(win.ptr, dst, depth, height, width, yd_min, yd_max - yd_min,
                 win.pitch, win.slice_stride, start_index, nrows, 1, model,
                 stream, flags=flags)
-    return _narrow(dst.to_host(stream=stream), out_dtype)
+    return _download_native(dst, out_dtype, stream)
 
 
 _DTYPE_CODES = {np.dtype(np.float32): _cabi.DTYPE_F32,
@@ -415,6 +423,51 @@ _DTYPE_CODES = {np.dtype(np.float32): _cabi.DTYPE_F32,
                 np.dtype(np.int8): _cabi.DTYPE_I8,
                 np.dtype(np.uint16): _cabi.DTYPE_U16,
                 np.dtype(np.int16): _cabi.DTYPE_I16}
+
+
+def _upload_native(arr, stream):
+    """Host array (H, W) or (D, H, W) of a supported dtype -> (float32
+    DeviceArray of the same shape, kernel flags, dtype to return or None).
+    Integer data crosses PCIe in its own dtype and is widened on the device
+    (exactly: every such value is a float32) instead of by NumPy on one host
+    core."""
+    arr = np.asarray(arr)
+    if arr.dtype == np.float32:
+        return DeviceArray.from_host(arr, stream), 0, None
+    if arr.dtype not in _INT_IMAGE_DTYPES:
+        raise NotImplementedError(
+            "dtype %s is not implemented on the CUDA path yet (float32, uint8, "
+            "int8, uint16 and int16 are); there is no CPU fallback" % arr.dtype)
+    raw = np.ascontiguousarray(arr)
+    dev = DeviceArray(raw.shape)
+    rows = int(np.prod(raw.shape[:-1], dtype=np.int64))
+    sh = _vp(stream.handle)
+    with _dev.borrowed(max(raw.nbytes, 16)) as draw:
+        _cabi.call("dcb_h2d", _vp(draw.ptr), _vp(raw.ctypes.data), raw.nbytes,
+                   sh)
+        _cabi.call("dcb_unpack_hwc_to_planes_f32", _vp(draw.ptr),
+                   _DTYPE_CODES[raw.dtype], _vp(dev.ptr), rows, raw.shape[-1],
+                   1, dev.pitch, dev.pitch * rows, sh)
+        stream.sync()     # `raw` and the borrowed buffer are free again
+    return dev, _cabi.FLAG_ROUND_INT, raw.dtype
+
+
+def _download_native(dev, dtype, stream):
+    """float32 DeviceArray holding integer values (FLAG_ROUND_INT results) ->
+    host array of ``dtype``, narrowed on the device; ``dtype`` None: float32."""
+    if dtype is None:
+        return dev.to_host(stream=stream)
+    rows = int(np.prod(dev.shape[:-1], dtype=np.int64))
+    out = _dev.pinned_empty(dev.shape, dtype)
+    sh = _vp(stream.handle)
+    with _dev.borrowed(max(out.nbytes, 16)) as draw:
+        _cabi.call("dcb_pack_planes_f32_to_hwc", _vp(dev.ptr), _vp(draw.ptr),
+                   _DTYPE_CODES[np.dtype(dtype)], rows, dev.shape[-1], 1,
+                   dev.pitch, dev.pitch * rows, sh)
+        _cabi.call("dcb_d2h", _vp(out.ctypes.data), _vp(draw.ptr), out.nbytes,
+                   sh)
+        stream.sync()
+    return out
 
 
 def _unwarp_frame_hwc(frame, xcenter, ycenter, list_fact, order):

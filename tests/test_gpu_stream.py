@@ -113,3 +113,25 @@ def test_sinogram_window_single_rank():
     with pytest.raises(ValueError):
         multigpu.unwarp_slice_backward_sharded(dcb.DeviceArray((4, 120, 200)), params, 3, window)
     window.close()
+
+
+@pytest.mark.gpu
+def test_chunk_function_delegates_large_host_stacks_to_the_pipeline():
+    """unwarp_chunk_slices_backward hands large float32 host stacks to the streaming pipeline
+    (config["stream_bytes"]); same numbers either way, and integer stacks keep the device-side
+    widening path."""
+    rng = np.random.default_rng(5)
+    stack = rng.random((9, 96, 160), dtype=np.float32)
+    want = orc.unwarp_chunk_slices_backward(stack, 83.7, 44.2, FACT, 10, 80)
+    direct = post.unwarp_chunk_slices_backward(stack, 83.7, 44.2, FACT, 10, 80)
+    old = post.config["stream_bytes"]
+    post.config["stream_bytes"] = 1
+    try:
+        piped = post.unwarp_chunk_slices_backward(stack, 83.7, 44.2, FACT, 10, 80)
+        ints = (stack * 60000).astype(np.uint16)
+        got_int = post.unwarp_chunk_slices_backward(ints, 83.7, 44.2, FACT, 10, 80)
+    finally:
+        post.config["stream_bytes"] = old
+    assert np.array_equal(direct, want) and np.array_equal(piped, want)
+    assert got_int.dtype == np.uint16
+    assert np.array_equal(got_int, orc.unwarp_chunk_slices_backward(ints, 83.7, 44.2, FACT, 10, 80))

@@ -28,3 +28,18 @@ for kind in ("pinned", "pageable", "pageable uint16", "pageable uint8"):
         out = post.unwarp_image_backward(ins[k % 4], xc, yc, fact)
         ts.append(time.perf_counter() - t0)
     print("%-16s best %.2f ms  median %.2f ms  -> %s" % (kind, min(ts) * 1e3, sorted(ts)[10] * 1e3, out.dtype), flush=True)
+
+# a tomography chunk: 32 projections of 2560^2, every row, uint16 and float32
+D, H2 = 32, 2560
+f5 = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]
+for dt in (np.uint16, np.float32):
+    stack = (rng.integers(0, 60000, (D, H2, H2)).astype(dt) if dt == np.uint16
+             else rng.random((D, H2, H2), dtype=np.float32))
+    for _ in range(2):
+        out = post.unwarp_chunk_slices_backward(stack, 1283.4, 1275.9, f5, 0, H2 - 1)
+    ts = []
+    for k in range(5):
+        t0 = time.perf_counter()
+        out = post.unwarp_chunk_slices_backward(stack, 1283.4, 1275.9, f5, 0, H2 - 1)
+        ts.append(time.perf_counter() - t0)
+    print("chunk %-8s 32 x 2560^2 pageable: best %.1f ms median %.1f ms -> %s" % (np.dtype(dt).name, min(ts) * 1e3, sorted(ts)[2] * 1e3, out.dtype), flush=True)
