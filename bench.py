@@ -436,9 +436,9 @@ def run_gpu_arm(args, rank, local_rank, world):
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant
 # kernel, from the committed `ncu --set full` capture (profiles/); None until
 # a capture exists for the current kernel.
-TRAFFIC_BYTES_PER_LAUNCH = 69867776 + 17934848
-TRAFFIC_SOURCE = ("profiles/r1/ncu_image_v13.txt: dram__bytes_read.sum 69.9 MB + "
-                  "dram__bytes_write.sum 17.9 MB of one launch (most of the 64 MiB output is "
+TRAFFIC_BYTES_PER_LAUNCH = 69821696 + 17368832
+TRAFFIC_SOURCE = ("profiles/r1/ncu_image_v14.txt: dram__bytes_read.sum 69.8 MB + "
+                  "dram__bytes_write.sum 17.4 MB of one launch (most of the 64 MiB output is "
                   "still dirty in the 126 MB L2 when the profiled launch ends)")
 
 

@@ -998,14 +998,20 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
         CUDA_TRY(cudaHostAlloc(&hp.hstage, wbytes * (size_t)H, cudaHostAllocDefault));
         hp.stage_cap = wbytes * (size_t)H;
     }
-    // last upload band each output band needs: the last source row it can touch
+    // last upload band an output band needs (the last source row it can touch); evaluated on
+    // first use, i.e. after the first uploads are already under way (8 x 2049 polynomial samples
+    // cost the host ~50 us)
     int need[kMaxBands];
-    for (int b = 0; b < nbands; ++b) {
-        const int r0 = b * rows_per, nr = std::min(rows_per, H - r0);
-        int lo, hi;
-        radial_row_range(*model, H, W, r0, r0 + nr, &lo, &hi);
-        need[b] = std::min(nbands - 1, hi / rows_per);
-    }
+    for (int b = 0; b < nbands; ++b) need[b] = -1;
+    auto need_of = [&](int k) -> int {
+        if (need[k] < 0) {
+            const int q0 = k * rows_per, qn = std::min(rows_per, H - q0);
+            int lo, hi;
+            radial_row_range(*model, H, W, q0, q0 + qn, &lo, &hi);
+            need[k] = std::min(nbands - 1, hi / rows_per);
+        }
+        return need[k];
+    };
     // uploads in row order; an output band is unwarped (second stream) as soon as the upload it
     // needs has been enqueued, and downloaded (third stream) behind its kernel
     int next = 0, waited = -1;
@@ -1024,11 +1030,11 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
         CUDA_TRY(cudaEventRecord(hp.ev_up[b], hp.up));
         // (pinned source: every upload is enqueued before the first launch, as measured best)
         if (!stage && b < nbands - 1) continue;
-        for (; next < nbands && (need[next] <= b || b == nbands - 1); ++next) {
+        for (; next < nbands && (b == nbands - 1 || need_of(next) <= b); ++next) {
             const int q0 = next * rows_per, qn = std::min(rows_per, H - q0);
-            if (need[next] > waited) {
-                CUDA_TRY(cudaStreamWaitEvent(hp.run, hp.ev_up[need[next]], 0));
-                waited = need[next];
+            if (need_of(next) > waited) {
+                CUDA_TRY(cudaStreamWaitEvent(hp.run, hp.ev_up[need_of(next)], 0));
+                waited = need_of(next);
             }
             rc = dcb_unwarp_stack_backward_f32((const float *)dsrc, (float *)(ddst + (size_t)q0 * pitch),
                                                1, H, W, 0, H, pitch, pitch * (size_t)H, pitch,

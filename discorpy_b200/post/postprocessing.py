@@ -569,14 +569,13 @@ def correct_perspective_image(mat, list_coef, order=1, mode="reflect",
     if on_device:
         src = mat
     else:
-        src_np, flags, out_dtype = _as_f32_image(mat)
-        src = DeviceArray.from_host(src_np, stream)
+        src, flags, out_dtype = _upload_native(mat, stream)
     dst = DeviceArray((height, width))
     opt = _opts(order, flags)
     _cabi.call("dcb_correct_perspective_image_f32", _vp(src.ptr),
                _vp(dst.ptr), height, width, src.pitch, dst.pitch,
                ctypes.byref(model), ctypes.byref(opt), _vp(stream.handle))
-    return dst if on_device else _narrow(dst.to_host(stream=stream), out_dtype)
+    return dst if on_device else _download_native(dst, out_dtype, stream)
 
 
 def unwarp_image_backward_perspective(mat, xcenter, ycenter, list_fact,
@@ -606,8 +605,7 @@ def unwarp_image_backward_perspective(mat, xcenter, ycenter, list_fact,
     if on_device:
         src = mat
     else:
-        src_np, flags, out_dtype = _as_f32_image(mat)
-        src = DeviceArray.from_host(src_np, stream)
+        src, flags, out_dtype = _upload_native(mat, stream)
     tmp = DeviceArray((height, width))
     dst = DeviceArray((height, width))
     opt = _opts(order, flags)
@@ -618,7 +616,7 @@ def unwarp_image_backward_perspective(mat, xcenter, ycenter, list_fact,
     if on_device:
         dst._keepalive = tmp      # until the stream has consumed it
         return dst
-    return _narrow(dst.to_host(stream=stream), out_dtype)
+    return _download_native(dst, out_dtype, stream)
 
 
 # ---------------------------------------------------------------------------
