@@ -364,6 +364,82 @@ def _map_coordinates(mat, yd, xd, order, mode):
     return _narrow(out, out_dtype)
 
 
+def _rows_leave_window(height, width, xcenter, ycenter, list_fact, start, stop,
+                       yd_min, yd_max):
+    """Can any output row start..stop sample outside the row window
+    ``[yd_min, yd_max)`` the reference crops to (``:289-301``: taken from the
+    first and the last row only)?  Conservative (True when in doubt), cheap:
+    along a row ``yd = yc + F(r) yu`` is extreme at the row ends, at the column
+    nearest to the centre, or where ``F'(r) = 0``."""
+    fact = np.asarray(list_fact, dtype=np.float64)
+    rows = np.arange(start, stop + 1, dtype=np.float64)
+    yu = rows - ycenter
+    xs = [0.0 - xcenter, (width - 1) - xcenter]
+    x_near = min(max(xcenter, 0.0), width - 1.0) - xcenter     # column nearest the centre
+    cand = [np.sqrt(x * x + yu * yu) for x in xs + [x_near]]
+    rmin, rmax = cand[2], np.maximum(cand[0], cand[1])
+    if len(fact) > 2:
+        deriv = fact[1:] * np.arange(1, len(fact))
+        roots = np.roots(deriv[::-1]) if np.any(deriv[1:] != 0) else np.array([])
+        for root in roots:
+            if abs(root.imag) < 1e-9 * max(1.0, abs(root.real)) and root.real > 0:
+                cand.append(np.clip(root.real, rmin, rmax))
+    lo = np.full(rows.shape, np.inf)
+    hi = np.full(rows.shape, -np.inf)
+    for r in cand:
+        yd = np.clip(ycenter + _radial_factor_1d(r, fact) * yu, 0, height - 1)
+        lo, hi = np.minimum(lo, yd), np.maximum(hi, yd)
+    if not (np.all(np.isfinite(lo)) and np.all(np.isfinite(hi))):
+        return True
+    return bool(lo.min() < yd_min or hi.max() > yd_max - 1)
+
+
+def _reflect_coordinate(cc, n):
+    """SciPy's coordinate mapping for mode 'reflect' (``ni_interpolation.c``
+    ``map_coordinate``), float64 in and out; identity inside ``[0, n-1]``."""
+    cc = np.array(cc, dtype=np.float64, copy=True)
+    if n <= 1:
+        cc[(cc < 0) | (cc > n - 1)] = 0.0
+        return cc
+    sz2 = 2.0 * n
+    neg = cc < 0
+    v = cc[neg]
+    far = v < -sz2
+    v[far] = sz2 * np.trunc(-v[far] / sz2) + v[far]
+    cc[neg] = np.where(v < -n, v + sz2, -v - 1.0)
+    pos = (cc > n - 1) & ~neg
+    v = cc[pos]
+    v = v - sz2 * np.trunc(v / sz2)
+    cc[pos] = np.where(v >= n, sz2 - v - 1.0, v)
+    return cc
+
+
+def _chunk_outside_window(mat3D, xcenter, ycenter, list_fact, start, stop,
+                          yd_min, yd_max):
+    """``unwarp_chunk_slices_backward`` when some rows of the chunk sample
+    outside the reference's row window (a strongly off-centre, non-monotone
+    model).  The reference then samples the CROPPED slices with SciPy's
+    'reflect' boundary (``:310-312`` -> ``_mapping`` ``:251``); restated here:
+    explicit coordinates, reflected into the window like SciPy does, through
+    the explicit-coordinate kernel.  Rare and not tuned."""
+    (depth, height, width) = mat3D.shape
+    xu = np.arange(width) - xcenter
+    yu = np.arange(start, stop + 1) - ycenter
+    xu_mat, yu_mat = np.meshgrid(xu, yu)
+    ru = np.sqrt(xu_mat ** 2 + yu_mat ** 2)
+    fmat = _radial_factor_1d(ru, list_fact)
+    xd = np.float32(np.clip(xcenter + fmat * xu_mat, 0, width - 1))
+    yd = np.float32(np.clip(ycenter + fmat * yu_mat, 0, height - 1))
+    yd = yd - np.int16(yd_min)                     # float32, like :308-309
+    yd = _reflect_coordinate(yd, yd_max - yd_min)  # float64
+    # a mapped coordinate in (-1, 0) or (n-1, n) has both taps on the edge row: clamping
+    # (mode 'nearest' of the explicit-coordinate kernel) gives SciPy's value
+    xd = xd.astype(np.float64)
+    out = [_map_coordinates(np.asarray(mat3D[i, yd_min:yd_max, :]), yd, xd, 1,
+                            "nearest").reshape(yd.shape) for i in range(depth)]
+    return np.asarray(out)
+
+
 def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
                                  start_index, stop_index):
     """
@@ -395,6 +471,12 @@ def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
     yd_max = int(np.int16(np.ceil(np.amax(yd2)))) + 1
     nrows = stop_index - start_index + 1
     model = _cabi.make_radial(xcenter, ycenter, list_fact)
+    if _rows_leave_window(height, width, xcenter, ycenter, list_fact,
+                          start_index, stop_index, yd_min, yd_max):
+        host = mat3D.to_host() if on_device else mat3D
+        res = _chunk_outside_window(host, xcenter, ycenter, list_fact,
+                                    start_index, stop_index, yd_min, yd_max)
+        return DeviceArray.from_host(res) if on_device else res
     stream = _dev.current_stream()
     dst = DeviceArray((depth, nrows, width))
     if on_device:

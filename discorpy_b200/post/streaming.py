@@ -113,6 +113,14 @@ def unwarp_chunk_slices_backward_stream(mat3D, xcenter, ycenter, list_fact,
         raise ValueError("out must have shape %s" % ((depth, nrows, width),))
     if depth == 0:
         return out
+    if _post._rows_leave_window(height, width, xcenter, ycenter, list_fact, start_index,
+                                stop_index, y0, y1):
+        # rows sampling outside the reference's row window: SciPy reflects them into the cropped
+        # slice; the (untuned) explicit-coordinate path of postprocessing.py restates that
+        for z in range(depth):
+            out[z:z + 1] = _post._chunk_outside_window(mat3D[z:z + 1], xcenter, ycenter, list_fact,
+                                                       start_index, stop_index, y0, y1)
+        return out
     if slices_per_block is None:
         slices_per_block = max(1, int(block_bytes // max(1, wrows * width * 4)))
     nb = int(min(max(1, slices_per_block), depth))

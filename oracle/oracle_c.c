@@ -48,7 +48,10 @@ static double radial_factor(double r, const double *a, int n) {
 }
 
 /* order-1 / order-0 sample of one slice at a coordinate inside the image;
- * rows are additionally folded into [ylo, yhi] (the reference's cropped window) */
+ * rows are additionally folded into [ylo, yhi] (the reference's cropped window).  Domain: the
+ * coordinate lies within one row of the window, where folding equals SciPy's 'reflect'; chunk rows
+ * that sample further outside (possible because postprocessing.py:289-301 takes the window from the
+ * first and last row only) are covered by oracle_np.reflect_coordinate, not by this restatement */
 static float sample(const float *img, int64_t pitch, int W, int ylo, int yhi, double y, double x,
                     int order) {
     if (order == 0) {

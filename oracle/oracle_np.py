@@ -119,6 +119,52 @@ def _cast_like_scipy(val, dtype):
     raise TypeError("unsupported dtype %s" % dtype)
 
 
+def reflect_coordinate(cc, n):
+    """SciPy's ``map_coordinate`` for mode 'reflect' (``ni_interpolation.c``),
+    applied to a float64 coordinate array before the spline start index is
+    taken: (d c b a | a b c d | d c b a).  Coordinates inside ``[0, n-1]`` are
+    returned unchanged.  Only ``unwarp_chunk_slices_backward`` can produce
+    coordinates outside the array: its row window comes from the first and the
+    last row of the chunk (``postprocessing.py:289-301``), which a strongly
+    off-centre model need not respect."""
+    cc = np.array(cc, dtype=np.float64, copy=True)
+    if n <= 1:
+        cc[(cc < 0) | (cc > n - 1)] = 0.0
+        return cc
+    sz2 = 2.0 * n
+    neg = cc < 0
+    v = cc[neg]
+    far = v < -sz2
+    v[far] = sz2 * np.trunc(-v[far] / sz2) + v[far]
+    v = np.where(v < -n, v + sz2, -v - 1.0)
+    cc[neg] = v
+    pos = cc > n - 1
+    pos &= ~neg
+    v = cc[pos]
+    v = v - sz2 * np.trunc(v / sz2)
+    v = np.where(v >= n, sz2 - v - 1.0, v)
+    cc[pos] = v
+    return cc
+
+
+def reflect_index(idx, n):
+    """Integer tap index -> index inside ``[0, n)`` by SciPy's 'reflect' rule."""
+    idx = np.array(idx, dtype=np.intp, copy=True)
+    if n <= 1:
+        return np.zeros_like(idx)
+    s2 = 2 * n
+    neg = idx < 0
+    v = idx[neg]
+    far = v < -s2
+    v[far] = s2 * ((-v[far]) // s2) + v[far]
+    idx[neg] = np.where(v < -n, v + s2, -v - 1)
+    pos = (idx >= n) & ~neg
+    v = idx[pos]
+    v = v - s2 * (v // s2)
+    idx[pos] = np.where(v >= n, s2 - v - 1, v)
+    return idx
+
+
 def sample(mat, yd, xd, order=1, out_dtype=None):
     """Sample 2-D ``mat`` at coordinates (yd, xd) that already lie inside
     ``[0, H-1] x [0, W-1]``.
@@ -153,8 +199,12 @@ def sample(mat, yd, xd, order=1, out_dtype=None):
         tx = x - x0f
         y0 = y0f.astype(np.intp)
         x0 = x0f.astype(np.intp)
-        y1 = np.minimum(y0 + 1, h - 1)
-        x1 = np.minimum(x0 + 1, w - 1)
+        # taps that leave the array are reflected (SciPy's default boundary, the
+        # reference never passes another one on this path): for in-range
+        # coordinates only the +1 tap of the last row / column can, and it folds
+        # back onto that row / column with weight 0
+        y0, y1 = reflect_index(y0, h), reflect_index(y0 + 1, h)
+        x0, x1 = reflect_index(x0, w), reflect_index(x0 + 1, w)
         wy0 = 1.0 - ty
         wx0 = 1.0 - tx
         val = 0.0 + (src[y0, x0] * wy0) * wx0
@@ -232,6 +282,8 @@ def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
     yd, xd = radial_coords(height, width, xcenter, ycenter, list_fact,
                            row0=start_index, nrows=nrows)
     yd = yd - yd_min          # float32 - int16 scalar -> float32 (:308-309)
+    # rows the window does not hold are reflected into it by SciPy (mode 'reflect')
+    yd = reflect_coordinate(yd, yd_max - yd_min)
     return np.asarray([sample(mat3D[i, yd_min:yd_max, :], yd, xd, 1)
                        for i in range(depth)])
 

@@ -135,3 +135,18 @@ def test_chunk_function_delegates_large_host_stacks_to_the_pipeline():
     assert np.array_equal(direct, want) and np.array_equal(piped, want)
     assert got_int.dtype == np.uint16
     assert np.array_equal(got_int, orc.unwarp_chunk_slices_backward(ints, 83.7, 44.2, FACT, 10, 80))
+
+
+@pytest.mark.gpu
+def test_chunk_rows_outside_the_reference_window_gpu():
+    """Chunk rows that sample outside the reference's row window (golden outputs of the real
+    reference, tests/golden/chunk_window.npz): one-shot and streaming entries both reproduce SciPy's
+    reflection into the cropped slices."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "chunk_window.npz"))
+    for i in range(int(z["n"])):
+        stack, par, ref = z["stack%d" % i], z["par%d" % i], z["ref%d" % i]
+        xc, yc, a, b, fact = float(par[0]), float(par[1]), int(par[2]), int(par[3]), [float(v) for v in par[4:]]
+        got = post.unwarp_chunk_slices_backward(stack, xc, yc, fact, a, b)
+        assert got.dtype == ref.dtype and np.array_equal(got, ref), i
+        piped = streaming.unwarp_chunk_slices_backward_stream(stack, xc, yc, fact, a, b)
+        assert piped.dtype == ref.dtype and np.array_equal(piped, ref), i

@@ -135,3 +135,29 @@ def test_numpy_oracle_vs_live_reference_large():
     coef = [1.02, 0.01, -15.0, 0.005, 1.01, -8.0, 8e-6, -5e-6]
     assert np.array_equal(ref.correct_perspective_image(mat, coef),
                           orc.correct_perspective_image(mat, coef))
+
+
+def test_chunk_rows_outside_the_reference_window():
+    """unwarp_chunk_slices_backward crops every slice to a row window taken from the first and last
+    row of the chunk (postprocessing.py:289-301); rows in between can sample outside it and SciPy
+    reflects them into the crop.  Golden outputs of the real reference
+    (oracle/make_golden_chunk_window.py): the oracle restates the reflection bit for bit, and the
+    host-side test of the product flags exactly these cases."""
+    import os
+    import discorpy_b200.post.postprocessing as post
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "chunk_window.npz"))
+    for i in range(int(z["n"])):
+        stack, par, ref = z["stack%d" % i], z["par%d" % i], z["ref%d" % i]
+        xc, yc, a, b, fact = float(par[0]), float(par[1]), int(par[2]), int(par[3]), [float(v) for v in par[4:]]
+        got = orc.unwarp_chunk_slices_backward(stack, xc, yc, fact, a, b)
+        assert got.dtype == ref.dtype and np.array_equal(got, ref)
+        h, w = stack.shape[1:]
+        y0, y1 = orc.chunk_row_window(h, w, xc, yc, fact, a, b)
+        assert post._rows_leave_window(h, w, xc, yc, fact, a, b, y0, y1)
+    cc = np.linspace(-200, 200, 9001).astype(np.float32)
+    for n in (1, 2, 5, 30):
+        assert np.array_equal(post._reflect_coordinate(cc, n), orc.reflect_coordinate(cc, n))
+    # the BASELINE config-4 model keeps every row inside its window
+    f4 = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]
+    assert not post._rows_leave_window(2560, 2560, 1283.4, 1275.9, f4, 100, 300,
+                                       *orc.chunk_row_window(2560, 2560, 1283.4, 1275.9, f4, 100, 300))
