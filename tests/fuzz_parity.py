@@ -2,7 +2,8 @@
 """Randomised differential test of the CUDA path against the oracle (run on a GPU box; lives under
 tests/ because only tests may use the oracle):
 random shapes, centres (also far outside the image), polynomial lengths and strengths,
-orders 0 / 1 / 2..5, modes, dtypes, perspective coefficients, row chunks of stacks.
+orders 0 / 1 / 2..5, modes, dtypes, perspective coefficients, row chunks and single slices of
+stacks, the combined radial + perspective entry.
 Prints every case whose outputs are not bit-identical.  Usage: python tests/fuzz_parity.py [N] [seed]"""
 import os
 import sys
@@ -37,7 +38,7 @@ def run(n, seed):
         fact = [float(rng.uniform(0.6, 1.4))] + [float(rng.normal() * 0.3 / scale ** i) for i in range(1, nt)]
         xc = float(rng.uniform(-0.5, 1.5) * w)
         yc = float(rng.uniform(-0.5, 1.5) * h)
-        kind = rng.choice(["radial", "radial", "persp", "chunk"])
+        kind = rng.choice(["radial", "radial", "persp", "chunk", "slice", "both"])
         order = int(rng.choice([0, 1, 1, 1, 2, 3, 3, 4, 5]))
         mode = str(rng.choice(MODES))
         try:
@@ -51,6 +52,22 @@ def run(n, seed):
                 coef = [float(c) for c in coef]
                 got = post.correct_perspective_image(mat, coef, order=order, mode=mode)
                 want = osp.correct_perspective_image(mat, coef, order, mode)
+            elif kind == "slice":
+                if dt == "float64":
+                    continue
+                d = int(rng.integers(1, 5))
+                stack = np.stack([np.roll(mat, k, axis=1) for k in range(d)])
+                index = int(rng.integers(0, h))
+                got = post.unwarp_slice_backward(stack, xc, yc, fact, index)
+                want = orc.unwarp_slice_backward(stack, xc, yc, fact, index)
+            elif kind == "both":
+                if dt == "float64" or order > 1:
+                    continue
+                coef = [float(c) for c in (1 + rng.normal() * 0.05, rng.normal() * 0.05, rng.normal() * 5,
+                                           rng.normal() * 0.05, 1 + rng.normal() * 0.05, rng.normal() * 5,
+                                           rng.normal() * 1e-4, rng.normal() * 1e-4)]
+                got = post.unwarp_image_backward_perspective(mat, xc, yc, fact, coef, order=order)
+                want = orc.unwarp_image_backward_perspective(mat, xc, yc, fact, coef, order=order)
             else:
                 if dt == "float64" or h < 2:
                     continue
