@@ -3,7 +3,7 @@
 tests/ because only tests may use the oracle):
 random shapes, centres (also far outside the image), polynomial lengths and strengths,
 orders 0 / 1 / 2..5, modes, dtypes, perspective coefficients, row chunks and single slices of
-stacks, the combined radial + perspective entry.
+stacks, the combined radial + perspective entry, colour frames with padding.
 Prints every case whose outputs are not bit-identical.  Usage: python tests/fuzz_parity.py [N] [seed]"""
 import os
 import sys
@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import discorpy_b200 as dcb                                    # noqa: E402
 import discorpy_b200.post.postprocessing as post               # noqa: E402
+import discorpy_b200.util.utility as util                      # noqa: E402
 from oracle import oracle_np as orc                            # noqa: E402
 from oracle import oracle_spline as osp                        # noqa: E402
 
@@ -38,7 +39,7 @@ def run(n, seed):
         fact = [float(rng.uniform(0.6, 1.4))] + [float(rng.normal() * 0.3 / scale ** i) for i in range(1, nt)]
         xc = float(rng.uniform(-0.5, 1.5) * w)
         yc = float(rng.uniform(-0.5, 1.5) * h)
-        kind = rng.choice(["radial", "radial", "persp", "chunk", "slice", "both"])
+        kind = rng.choice(["radial", "radial", "persp", "chunk", "slice", "both", "color"])
         order = int(rng.choice([0, 1, 1, 1, 2, 3, 3, 4, 5]))
         mode = str(rng.choice(MODES))
         try:
@@ -60,6 +61,14 @@ def run(n, seed):
                 index = int(rng.integers(0, h))
                 got = post.unwarp_slice_backward(stack, xc, yc, fact, index)
                 want = orc.unwarp_slice_backward(stack, xc, yc, fact, index)
+            elif kind == "color":
+                if dt == "float64" or order > 1:
+                    continue
+                chan = int(rng.integers(1, 5))
+                frame = np.stack([np.roll(mat, 3 * k, axis=0) for k in range(chan)], axis=2)
+                pad = [0, int(rng.integers(0, 9)), tuple(int(v) for v in rng.integers(0, 7, 4))][int(rng.integers(0, 3))]
+                got = util.unwarp_color_image_backward(frame, xc, yc, fact, order=order, pad=pad)
+                want = orc.unwarp_color_image_backward(frame, xc, yc, fact, order=order, pad=pad)
             elif kind == "both":
                 if dt == "float64" or order > 1:
                     continue
