@@ -470,6 +470,11 @@ def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
     yd_min = int(np.int16(np.floor(np.amin(yd1))))
     yd_max = int(np.int16(np.ceil(np.amax(yd2)))) + 1
     nrows = stop_index - start_index + 1
+    if yd_max <= yd_min:
+        # the reference hands SciPy an empty slice here and SciPy reads past it
+        raise ValueError("empty row window [%d, %d): the model maps the last row of the "
+                         "chunk above the first one (the reference's result is undefined "
+                         "here)" % (yd_min, yd_max))
     model = _cabi.make_radial(xcenter, ycenter, list_fact)
     if _rows_leave_window(height, width, xcenter, ycenter, list_fact,
                           start_index, stop_index, yd_min, yd_max):

@@ -107,6 +107,9 @@ def unwarp_chunk_slices_backward_stream(mat3D, xcenter, ycenter, list_fact,
     y0 = int(np.int16(np.floor(np.amin(yd1))))
     y1 = int(np.int16(np.ceil(np.amax(yd2)))) + 1          # reference :289-301
     wrows = y1 - y0
+    if wrows <= 0:
+        raise ValueError("empty row window [%d, %d): the model maps the last row of the chunk "
+                         "above the first one (the reference's result is undefined here)" % (y0, y1))
     if out is None:
         out = np.empty((depth, nrows, width), dtype=out_dtype)
     if tuple(out.shape) != (depth, nrows, width):

@@ -278,6 +278,11 @@ def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
         raise ValueError("Selected index is out of the range")
     yd_min, yd_max = chunk_row_window(height, width, xcenter, ycenter,
                                       list_fact, start_index, stop_index)
+    if yd_max <= yd_min:
+        # a model that maps the last chunk row above the first one: the reference hands SciPy an
+        # EMPTY slice and SciPy reads past it (the values returned differ from run to run)
+        raise ValueError("empty row window [%d, %d): the reference's result is undefined here"
+                         % (yd_min, yd_max))
     nrows = stop_index - start_index + 1
     yd, xd = radial_coords(height, width, xcenter, ycenter, list_fact,
                            row0=start_index, nrows=nrows)

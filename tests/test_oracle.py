@@ -161,3 +161,18 @@ def test_chunk_rows_outside_the_reference_window():
     f4 = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]
     assert not post._rows_leave_window(2560, 2560, 1283.4, 1275.9, f4, 100, 300,
                                        *orc.chunk_row_window(2560, 2560, 1283.4, 1275.9, f4, 100, 300))
+
+
+def test_chunk_with_an_empty_row_window_is_refused():
+    """A model that maps the last chunk row above the first gives the reference an empty slice (SciPy
+    then reads past it: undefined values); the oracle and the product's host check both refuse."""
+    import discorpy_b200.post.postprocessing as post
+    fact = [0.7121505980847279, -0.0034137040107838647, -2.6659489737081743e-05,
+            -2.2097870183732417e-08, -1.5716877223813336e-10, -7.430580089833948e-14]
+    stack = np.zeros((2, 168, 6), dtype=np.float32)
+    y0, y1 = orc.chunk_row_window(168, 6, 5.782255233984425, -9.275425402650226, fact, 10, 95)
+    assert y1 <= y0
+    with pytest.raises(ValueError):
+        orc.unwarp_chunk_slices_backward(stack, 5.782255233984425, -9.275425402650226, fact, 10, 95)
+    with pytest.raises(ValueError):     # raised before any GPU work
+        post.unwarp_chunk_slices_backward(stack, 5.782255233984425, -9.275425402650226, fact, 10, 95)
