@@ -176,3 +176,18 @@ def test_chunk_with_an_empty_row_window_is_refused():
         orc.unwarp_chunk_slices_backward(stack, 5.782255233984425, -9.275425402650226, fact, 10, 95)
     with pytest.raises(ValueError):     # raised before any GPU work
         post.unwarp_chunk_slices_backward(stack, 5.782255233984425, -9.275425402650226, fact, 10, 95)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/discorpy"),
+                    reason="the reference tree only exists in the build container")
+def test_oracle_against_the_real_reference_randomised():
+    """Where /root/reference is present (the build container, not the GPU box): 200 random cases of
+    tests/fuzz_oracle_vs_reference.py -- the reference's own functions against the oracle, every
+    function, order, mode and dtype -- must be bit-identical."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = subprocess.run([sys.executable, os.path.join(here, "fuzz_oracle_vs_reference.py"), "200", "3"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+    assert "0 not bit-identical" in res.stdout
