@@ -451,7 +451,7 @@ def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
     Returns
     -------
     array_like
-        3D array (depth, stop-start+1, width), float32.
+        3D array (depth, stop-start+1, width) of ``mat3D``'s dtype.
     """
     on_device = isinstance(mat3D, DeviceArray)
     if len(mat3D.shape) < 3:
