@@ -191,7 +191,7 @@ def sample(mat, yd, xd, order=1, out_dtype=None):
     if order == 0:
         yi = np.floor(y + 0.5).astype(np.intp)
         xi = np.floor(x + 0.5).astype(np.intp)
-        val = src[yi, xi]
+        val = 0.0 + src[yi, xi]       # SciPy accumulates from 0.0: a -0.0 pixel comes out +0.0
     elif order == 1:
         y0f = np.floor(y)
         x0f = np.floor(x)
