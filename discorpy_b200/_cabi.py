@@ -117,6 +117,8 @@ SIGNATURES = {
     "dcb_launch_count": [ctypes.POINTER(_u64)],
     "dcb_launch_count_reset": [],
     "dcb_last_plan": [ctypes.POINTER(_i)] * 5,
+    "dcb_image_stats": [_i, ctypes.POINTER(_u64), _i],
+    "dcb_plan_cache_clear": [ctypes.POINTER(_u64)],
     "dcb_selftest_sqrt": [_sz, _u64, ctypes.POINTER(_u64)],
     "dcb_selftest_sqrt_fast": [_sz, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_u64)],
     "dcb_selftest_tma": [_vp, _i, _i, _i, _sz, _sz, _i, _i, _i, _i, _i, _vp,

@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>
+#include <map>
+#include <string>
 #include <thread>
 #include <vector>
 #include <pthread.h>
@@ -273,6 +275,8 @@ static int plan_and_launch_stack(StackKernel kern, bool widen, RemapParams &p, d
 }
 
 typedef void (*ImageKernel)(const ImageParams, const CUtensorMap);
+static unsigned long long *g_image_stats = nullptr;   // dcb_image_stats: device counters or NULL
+static unsigned long long *g_image_stats_fwd() { return g_image_stats; }
 
 // Launch planning for the single-image kernel (remap_image.cuh).
 struct ImageKernelSel {
@@ -309,6 +313,139 @@ static bool map_clips_at_border(const ImageParams &p, int map_kind) {
     return outside(p.W - 1, y0) || outside(p.W - 1, y1);
 }
 
+// ---------------------------------------------------------------------------
+// Plan cache of the single-image kernel (remap_image.cuh, TilePlan): the per-tile staged boxes and
+// verified row patches depend on the model and the launch geometry alone, so they are built once
+// (image_plan_kernel, ~35 us for 4096^2) and kept on the device for every later frame unwarped
+// with the same calibration -- the reference's usage (one calibration, many projections).
+// Least recently used plans are dropped beyond DCB_PLAN_CACHE_MB (default 512); DCB_PLAN_CACHE=0
+// builds a fresh plan for every launch (stream-ordered allocation).
+// ---------------------------------------------------------------------------
+namespace {
+struct PlanKey {
+    int device, map_kind, th, H, W, row0, nrows, yorg, ylast, bw, bh, fast, n;
+    double xc, yc, a[DCB_MAX_TERMS], c[8];
+};
+struct PlanEntry {
+    void *dptr = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t ready = nullptr;
+    bool ready_done = false;
+    uint64_t last_use = 0;
+};
+std::map<std::string, PlanEntry> g_plans;
+std::mutex g_plans_mu;
+uint64_t g_plan_clock = 0;
+size_t g_plan_bytes = 0;
+std::atomic<uint64_t> g_plan_builds{0};
+
+typedef void (*PlanKernel)(const ImageParams, void *, unsigned long long *);
+template <int MAP, int TH>
+void launch_plan_kernel(const ImageParams &p, void *out, unsigned long long *stats, cudaStream_t st) {
+    image_plan_kernel<MAP, TH><<<p.ntiles, kThreads, 0, st>>>(
+        p, reinterpret_cast<TilePlan<TH> *>(out), stats);
+}
+void launch_plan(int map_kind, int th, const ImageParams &p, void *out, unsigned long long *stats,
+                 cudaStream_t st) {
+    if (map_kind == MAP_RADIAL)
+        th == 32 ? launch_plan_kernel<MAP_RADIAL, 32>(p, out, stats, st)
+                 : launch_plan_kernel<MAP_RADIAL, 16>(p, out, stats, st);
+    else
+        th == 32 ? launch_plan_kernel<MAP_PERSP, 32>(p, out, stats, st)
+                 : launch_plan_kernel<MAP_PERSP, 16>(p, out, stats, st);
+}
+size_t plan_cache_limit() {
+    static size_t lim = [] {
+        const char *e = getenv("DCB_PLAN_CACHE_MB");
+        long mb = e ? atol(e) : 512;
+        return (size_t)std::max(16L, mb) << 20;
+    }();
+    return lim;
+}
+bool plan_cache_enabled() {
+    static bool on = [] {
+        const char *e = getenv("DCB_PLAN_CACHE");
+        return !(e != nullptr && e[0] == '0');
+    }();
+    return on;
+}
+}  // namespace
+
+static unsigned long long *g_image_stats_fwd();
+
+// Finds or builds the plan of this launch on `stream`; *transient receives a buffer the caller
+// must release with cudaFreeAsync after the launch (cache disabled), else NULL.
+static int get_image_plan(int map_kind, int th, ImageParams &p, cudaStream_t stream,
+                          void **transient) {
+    *transient = nullptr;
+    const size_t bytes = (size_t)p.ntiles * image_rec_bytes(th);
+    if (!plan_cache_enabled()) {
+        void *d = nullptr;
+        CUDA_TRY(cudaMallocAsync(&d, bytes, stream));
+        launch_plan(map_kind, th, p, d, g_image_stats_fwd(), stream);
+        CUDA_TRY(cudaGetLastError());
+        g_plan_builds.fetch_add(1, std::memory_order_relaxed);
+        p.plan = d;
+        *transient = d;
+        return DCB_OK;
+    }
+    PlanKey key;
+    memset(&key, 0, sizeof(key));
+    CUDA_TRY(cudaGetDevice(&key.device));
+    key.map_kind = map_kind, key.th = th, key.H = p.H, key.W = p.W, key.row0 = p.row0;
+    key.nrows = p.nrows, key.yorg = p.yorg, key.ylast = p.ylast, key.bw = p.bw, key.bh = p.bh;
+    key.fast = p.fast;
+    if (map_kind == MAP_RADIAL) {
+        key.n = p.rad.n, key.xc = p.rad.xc, key.yc = p.rad.yc;
+        memcpy(key.a, p.rad.a, sizeof(key.a));
+    } else {
+        memcpy(key.c, p.per.c, sizeof(key.c));
+    }
+    const std::string k(reinterpret_cast<const char *>(&key), sizeof(key));
+    std::lock_guard<std::mutex> lk(g_plans_mu);
+    auto it = g_plans.find(k);
+    if (it == g_plans.end()) {
+        // make room: drop least recently used plans (cudaFree waits for kernels still reading them)
+        while (!g_plans.empty() && g_plan_bytes + bytes > plan_cache_limit()) {
+            auto old = g_plans.begin();
+            for (auto jt = g_plans.begin(); jt != g_plans.end(); ++jt)
+                if (jt->second.last_use < old->second.last_use) old = jt;
+            cudaFree(old->second.dptr);
+            cudaEventDestroy(old->second.ready);
+            g_plan_bytes -= old->second.bytes;
+            g_plans.erase(old);
+        }
+        PlanEntry e;
+        CUDA_TRY(cudaMalloc(&e.dptr, bytes));
+        e.bytes = bytes;
+        cudaError_t ce = cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming);
+        if (ce != cudaSuccess) {
+            cudaFree(e.dptr);
+            return fail(DCB_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(ce));
+        }
+        launch_plan(map_kind, th, p, e.dptr, g_image_stats_fwd(), stream);
+        ce = cudaGetLastError();
+        if (ce == cudaSuccess) ce = cudaEventRecord(e.ready, stream);
+        if (ce != cudaSuccess) {
+            cudaFree(e.dptr);
+            cudaEventDestroy(e.ready);
+            return fail(DCB_ERR_CUDA, "plan kernel launch failed: %s", cudaGetErrorString(ce));
+        }
+        g_plan_builds.fetch_add(1, std::memory_order_relaxed);
+        g_plan_bytes += bytes;
+        it = g_plans.emplace(k, e).first;
+    } else if (!it->second.ready_done) {
+        // built on some stream, maybe not finished: order this stream behind it
+        if (cudaEventQuery(it->second.ready) == cudaSuccess)
+            it->second.ready_done = true;
+        else
+            CUDA_TRY(cudaStreamWaitEvent(stream, it->second.ready, 0));
+    }
+    it->second.last_use = ++g_plan_clock;
+    p.plan = it->second.dptr;
+    return DCB_OK;
+}
+
 static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, double gmain,
                                  double gcross, int path_req, size_t src_pitch_bytes,
                                  cudaStream_t stream, int map_kind) {
@@ -343,7 +480,9 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
         need_h = std::min<long long>(need_h, src_rows);
         bw = (int)((need_w + 3) / 4 * 4);
         bh = (int)need_h;
-        const int max_stage = (TH >= 32 ? 22 : 14) * 1024;  // 5 stages x 2 CTAs within 227 KB
+        // 5 stages + tail, x 2 CTAs (each + 1 KB reserved) within the SM's 228 KB
+        const int max_stage =
+            TH >= 32 ? (int)((116736 - 1024 - image_tail_bytes(TH, true)) / 5 / 128 * 128) : 14 * 1024;
         if (bw > 256 || bh > 256 || (long long)bw * bh * 4 > max_stage) {
             // strong magnification somewhere: stage a modest box, tiles whose
             // probes do not fit are gathered straight from global memory
@@ -354,11 +493,21 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
         bw = std::max(bw, 4);
         bh = std::max(bh, 1);
         if (kImgBoxW > 0) {   // fixed box width: the kernel samples with a compile-time pitch
-            if (bw > kImgBoxW || (long long)kImgBoxW * bh * 4 > max_stage) fallback_box = true;
+            // (a box one or two rows short of the bound only sends single rows of the tallest
+            // tiles down the exact path; much shorter and whole tiles miss it)
+            if (bw > kImgBoxW || bh > max_stage / (kImgBoxW * 4) + 2) fallback_box = true;
             bw = kImgBoxW;
             bh = std::min(bh, max_stage / (bw * 4));
         }
     }
+    // DCB_IMG_FAST=0 (diagnostics, A/B runs): every row takes the exact coordinate path
+    {
+        const char *env = getenv("DCB_IMG_FAST");
+        // (integer images round half away from zero in fp64, which the patch path's blend
+        // certificate does not cover yet: they keep the exact path)
+        p.fast = ((env != nullptr && env[0] == '0') || p.rint) ? 0 : 1;
+    }
+    p.stats = g_image_stats;
     // uneven tiles (clipped regions, tiles that will not fit the box): deal them round-robin
     p.deal = (fallback_box || map_clips_at_border(p, map_kind)) ? 1 : 0;
     CUtensorMap tmap;
@@ -384,7 +533,7 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
     p.bh = bh;
     p.box_bytes = (unsigned)(bw * bh * 4);
     p.stage_bytes = (p.box_bytes + 127u) / 128u * 128u;
-    const size_t smem = (size_t)(sel.wide ? 5 : 2) * p.stage_bytes + image_tail_bytes();
+    const size_t smem = (size_t)(sel.wide ? 5 : 2) * p.stage_bytes + image_tail_bytes(TH, sel.wide);
     if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute((const void *)sel.kern,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -393,8 +542,12 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
                                                            kImgThreads, smem));
     if (occ < 1) return fail(DCB_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
     const int grid = (int)std::min<long long>(ntiles, (long long)occ * props.sm_count);
+    void *transient = nullptr;
+    rc = get_image_plan(map_kind, TH, p, stream, &transient);
+    if (rc != DCB_OK) return rc;
     sel.kern<<<grid, kImgThreads, smem, stream>>>(p, tmap);
     CUDA_TRY(cudaGetLastError());
+    if (transient != nullptr) CUDA_TRY(cudaFreeAsync(transient, stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     g_last_plan = {staged ? DCB_PATH_TMA : DCB_PATH_DIRECT, bw, bh, grid, (int)smem};
     return DCB_OK;
@@ -1320,6 +1473,36 @@ int dcb_launch_count_reset(void) {
     g_launches.store(0, std::memory_order_relaxed);
     return DCB_OK;
 }
+int dcb_plan_cache_clear(uint64_t *plans_built) {
+    std::lock_guard<std::mutex> lk(g_plans_mu);
+    for (auto &kv : g_plans) {
+        cudaFree(kv.second.dptr);
+        cudaEventDestroy(kv.second.ready);
+    }
+    g_plans.clear();
+    g_plan_bytes = 0;
+    if (plans_built != nullptr) *plans_built = g_plan_builds.load(std::memory_order_relaxed);
+    return DCB_OK;
+}
+
+int dcb_image_stats(int enable, uint64_t *out, int reset) {
+    static unsigned long long *buf = nullptr;
+    if (enable && buf == nullptr) {
+        CUDA_TRY(cudaMalloc((void **)&buf, 8 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(buf, 0, 8 * sizeof(unsigned long long)));
+    }
+    if (buf != nullptr && (out != nullptr || reset)) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (out != nullptr)
+            CUDA_TRY(cudaMemcpy(out, buf, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (reset) CUDA_TRY(cudaMemset(buf, 0, 8 * sizeof(unsigned long long)));
+    } else if (out != nullptr) {
+        memset(out, 0, 8 * sizeof(uint64_t));
+    }
+    g_image_stats = enable ? buf : nullptr;
+    return DCB_OK;
+}
+
 int dcb_last_plan(int *path, int *box_w, int *box_h, int *grid, int *smem_bytes) {
     if (path) *path = g_last_plan.path;
     if (box_w) *box_w = g_last_plan.bw;

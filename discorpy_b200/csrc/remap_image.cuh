@@ -53,8 +53,10 @@ struct ImageParams {
     unsigned box_bytes, stage_bytes;
     int dbg;           // A/B builds (-DDCB_AB): ablation switches, 0 otherwise
     int deal;          // 0: each CTA a contiguous range of the tile order; 1: tiles dealt round-robin
-    int pad_;
+    int fast;          // 1: rows certified by the producer take the patch path (see RowPatch)
     int rint;          // 1: integer image, round half away from zero (finish_f64 in remap.cuh)
+    unsigned long long *stats;   // diagnostics (dcb_image_stats), NULL normally
+    const void *plan;            // TilePlan<TH>[ntiles] (image_plan_kernel), device memory
     RadialDev rad;
     PerspDev per;
 };
@@ -78,7 +80,9 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 struct TileBox {
     int bx0, by0;  // image coordinates of box element (0,0)
     int use;       // 1: TMA issued for this tile, 0: sample straight from global
-    int pad;
+    int shx;       // patch path: 23 - binade of the tile's x coordinates (0: no row of the tile is fast)
+    uint32_t mhi_x;  // high word of 1.5 * 2^(52 - shx)
+    int pad[3];
 };
 
 // floor of a float v in [0, 2^23) without the XU pipe: one round-toward-minus-
@@ -158,6 +162,64 @@ __device__ __forceinline__ double blend_exact(double a, double b, double c, doub
     return s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The patch path (round 2): verified cheap coordinates from a plan.
+//
+// The exact coordinate costs 12 fp64 operations, one MUFU and two conversions per pixel, then two
+// more conversions and six FP32 operations for floor / fraction -- 31.7 us of the 57 us kernel
+// (profiles/r1).  What the reference fixes is only the float32 ROUNDING of the float64 coordinate
+// (postprocessing.py:144-145), and the map depends on the calibration and the image geometry
+// alone, not on the pixels.  So the library keeps a PLAN per (model, geometry) -- built once by
+// image_plan_kernel, cached on the device (api.cu), reused for every frame unwarped with that
+// calibration, which is how the reference is used (one calibration, thousands of projections):
+//   * per tile the staged box (what the producer warp used to derive from 9 probe points);
+//   * per tile row a degree-5 interpolant of F(r(x)) along the 128 pixels (six Chebyshev nodes,
+//     exact evaluations) and, per 32-pixel segment, a bit that says the interpolant was VERIFIED
+//     pixel by pixel against the exact evaluation: same float32 coordinates (with a margin that
+//     covers the last-ulp differences between the exact path's own variants), one float32
+//     binade, 2x2 footprint inside the staged box.
+// The sampling warps then spend 5 DFMA (Horner in tau) + 2 DFMA per pixel of a verified row;
+// rounding to the float32 grid, floor and fraction come from ONE fp64 addition of
+// 1.5 * 2^(52 - sh) (sh = 23 - binade: the sum's low word is the coordinate in units of its
+// float32 ulp), a shift, a mask and one exact subtraction -- no conversion, no MUFU, no box
+// test.  Rows that were not verified (image borders, the distortion centre, binade crossings,
+// strong magnification) take the exact path below, so no result depends on the interpolant.
+// ---------------------------------------------------------------------------------------------
+#include "patch_const.inc"
+
+struct __align__(16) RowPatch {   // one per tile row (64 bytes)
+    double c[6];        // F(tau) = sum c_i tau^i, tau = (x - x_tile - 63.5) / 64
+    uint32_t info;      // bits 0..3: segment k (pixels lane + 32 k) verified; bits 8..12: shy
+    uint32_t mhi_y;     // high word of 1.5 * 2^(52 - shy)
+    uint32_t mky;       // (1 << shy) - 1
+    uint32_t e32y;      // (150 - shy) << 23: float exponent whose ulp is 2^-shy
+};
+
+// high word of 1.5 * 2^(52 - sh); the same constant with mantissa 1.0 is 2^(52 - sh) (0x80000 less)
+__device__ __forceinline__ uint32_t magic_hi(int sh) { return ((uint32_t)(1075 - sh) << 20) | 0x80000u; }
+__device__ __forceinline__ int binade_of(double v) {   // floor(log2 v) of a positive normal double
+    return (int)(((uint32_t)__double2hiint(v) >> 20) & 0x7ffu) - 1023;
+}
+
+// distance test of a double's low mantissa word from the float32 rounding boundary (bit 28 set,
+// bits 27..0 clear): the shifted word is 0x80000000 there
+__device__ __forceinline__ uint32_t cert_key(double v, uint32_t add) {
+    return ((uint32_t)__double2loint(v) << 3) + add;
+}
+// blend certificate: 32 ulp64 around the boundary (the FMA form below is within 10 ulp64 of
+// SciPy's sum for taps of one sign, see lerp_fma)
+constexpr uint32_t kBlendCertAdd = 0x80000000u + 8u * 32u, kBlendCertLim = 16u * 32u;
+
+// (1-ty)((1-tx) a + tx b) + ty ((1-tx) c + tx d) with six FMAs, every intermediate a positive
+// combination of the taps: for taps of one sign nothing cancels, the result is within 2^-51
+// relative of the exact value, SciPy's rn-sum of rn-products (blend_exact) within 2^-51 too.
+__device__ __forceinline__ double lerp_fma(double a, double b, double c, double d, double tx,
+                                           double ty) {
+    const double top = fma(tx, b, fma(-tx, a, a));
+    const double bot = fma(tx, d, fma(-tx, c, c));
+    return fma(ty, bot, fma(-ty, top, top));
+}
+
 // Per-thread column terms of the map (constant down a tile) and the row
 // evaluation producing UNCLIPPED fp32 coordinates for 4 pixels.
 template <int MAP, int NT>
@@ -182,6 +244,17 @@ struct MapEval<MAP_RADIAL, NT> {
     // yd: the row as a double
     __device__ __forceinline__ void row(const ImageParams &p, double yd, float (&xf)[kCols],
                                         float (&yf)[kCols]) const {
+        double xq[kCols], yq[kCols];
+        row64(p, yd, xq, yq);
+#pragma unroll
+        for (int k = 0; k < kCols; ++k) {
+            xf[k] = __double2float_rn(xq[k]);
+            yf[k] = __double2float_rn(yq[k]);
+        }
+    }
+    // the unrounded float64 coordinates of the row (the patch path's exact redo uses them as is)
+    __device__ __forceinline__ void row64(const ImageParams &p, double yd, double (&xq)[kCols],
+                                          double (&yq)[kCols]) const {
         const double yu = __dsub_rn(yd, p.rad.yc);
         const double yu2 = __dmul_rn(yu, yu);
         double r[kCols], f[kCols];
@@ -214,8 +287,8 @@ struct MapEval<MAP_RADIAL, NT> {
         }
 #pragma unroll
         for (int k = 0; k < kCols; ++k) {
-            xf[k] = __double2float_rn(fma(f[k], xu[k], p.rad.xc));
-            yf[k] = __double2float_rn(fma(f[k], yu, p.rad.yc));
+            xq[k] = fma(f[k], xu[k], p.rad.xc);
+            yq[k] = fma(f[k], yu, p.rad.yc);
         }
     }
 };
@@ -280,6 +353,172 @@ __device__ __forceinline__ void map_point(const ImageParams &p, int x, int y, fl
     }
 }
 
+// Exact F at (xu, yu) for the plan (any number of terms; correctly rounded sqrt).
+__device__ __forceinline__ double radial_f(const RadialDev &m, double xu, double yu) {
+    const double r = dsqrt_pos(fma(xu, xu, yu * yu));
+    double f = 0.0;
+    for (int t = m.n - 1; t >= 0; --t) f = fma(f, r, m.a[t]);
+    return f;
+}
+
+// One record of the plan per tile: what the kernel needs to know about the tile before it
+// touches a pixel.  The producer copies it next to the staged box with one bulk copy.
+template <int TH>
+struct __align__(16) TilePlan {
+    TileBox box;
+    RowPatch rows[TH];
+};
+
+// the source box of a tile from 9 probe points (all 32 lanes of one warp)
+template <int MAP, int TH>
+__device__ __forceinline__ TileBox place_tile_box(const ImageParams &p, int x_lo, int y_lo,
+                                                  int lane) {
+    const int wmax = p.W - 1, y_end = p.row0 + p.nrows;
+    const int x_hi = min(x_lo + kTileW - 1, wmax), y_hi = min(y_lo + TH - 1, y_end - 1);
+    const int q = lane % 9;
+    const int px = x_lo + ((x_hi - x_lo) * (q % 3)) / 2;
+    const int py = y_lo + ((y_hi - y_lo) * (q / 3)) / 2;
+    float xf, yf;
+    map_point<MAP>(p, px, py, xf, yf);
+    const int mnx = __reduce_min_sync(0xffffffffu, (int)xf);
+    const int mny = __reduce_min_sync(0xffffffffu, (int)yf);
+    const int mxx = __reduce_max_sync(0xffffffffu, (int)xf);
+    const int mxy = __reduce_max_sync(0xffffffffu, (int)yf);
+    // one pixel of slack around the probes for curvature inside the tile
+    const int bx0 = max(mnx - 1, 0) & ~3;
+    const int by0 = min(max(mny - 1, p.yorg), p.ylast);
+    const bool use = p.bw > 0 && (mxx + 2 - bx0 < p.bw) && (mxy + 2 - by0 < p.bh);
+    return TileBox{bx0, by0, use ? 1 : 0, 0, 0u, {0, 0, 0}};
+}
+
+// distance of v from the nearest float32 rounding boundary (v > 0 normal in float32)
+__device__ __forceinline__ double dist_to_f32_boundary(double v) {
+    const float f = __double2float_rn(v);
+    const uint32_t fb = (uint32_t)__float_as_int(f);
+    double half_ulp = __hiloint2double((int)(((fb >> 23) & 0xffu) + 1023u - 127u - 24u) << 20, 0);
+    // below a power of two the grid is twice as fine
+    if ((fb & 0x7fffffu) == 0u && v < (double)f) half_ulp *= 0.5;
+    return half_ulp - fabs(v - (double)f);
+}
+
+// Plan builder: one CTA of 8 warps per tile; warp w verifies tile rows w * TH/8 ... (one row at a
+// time: lanes 0..5 evaluate the nodes, every lane then checks its four pixels).
+template <int MAP, int TH>
+__global__ void __launch_bounds__(kThreads)
+    image_plan_kernel(const __grid_constant__ ImageParams p, TilePlan<TH> *__restrict__ plan,
+                      unsigned long long *__restrict__ stats) {
+    __shared__ TileBox sbox;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x;
+    const int txi = t / p.tiles_y, tyi = t - txi * p.tiles_y;
+    const int x_lo = txi * kTileW, y_lo = p.row0 + tyi * TH;
+    const int wmax = p.W - 1, y_end = p.row0 + p.nrows;
+    TilePlan<TH> &out = plan[t];
+    if (warp == 0) {
+        TileBox bx = place_tile_box<MAP, TH>(p, x_lo, y_lo, lane);
+        if (MAP == MAP_RADIAL && p.fast && bx.use && x_lo + kTileW - 1 <= wmax) {
+            // x binade of the tile: the one of its centre pixel
+            const double xu = ((double)x_lo + 63.5) - p.rad.xc;
+            const double yu = ((double)y_lo + (TH - 1) * 0.5) - p.rad.yc;
+            const double xd = fma(radial_f(p.rad, xu, yu), xu, p.rad.xc);
+            const int ex = binade_of(xd);
+            if (xd > 0.0 && ex >= 0 && ex <= 22) {
+                bx.shx = 23 - ex;
+                bx.mhi_x = magic_hi(bx.shx);
+                bx.pad[0] = (1 << bx.shx) - 1;
+                bx.pad[1] = (150 - bx.shx) << 23;
+            }
+        }
+        if (lane == 0) {
+            sbox = bx;
+            out.box = bx;
+        }
+    }
+    __syncthreads();
+    const TileBox box = sbox;
+    const int lim_x = box.use ? min(p.bw - 1, wmax - box.bx0) : 0;
+    const int lim_y = box.use ? min(p.bh - 1, p.ylast - box.by0) : 0;
+    constexpr int RPW = TH / kWarps;
+    unsigned n_full = 0, n_part = 0, n_rows = 0;
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int r = warp * RPW + rr, y = y_lo + r;
+        RowPatch rp;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) rp.c[i] = 0.0;
+        rp.info = 0, rp.mhi_y = 0, rp.mky = 0, rp.e32y = 0;
+        if (MAP == MAP_RADIAL && box.shx != 0 && y < y_end) {   // warp-uniform
+            const double yrow = (double)y;
+            const double yu = __dsub_rn(yrow, p.rad.yc);
+            const double xm = ((double)x_lo + 63.5) - p.rad.xc;   // xu at tau = 0
+            // node values on lanes 0..5, coefficient i on lane i, then broadcast
+            const double fn = radial_f(p.rad, fma(64.0, kPatchNodesX[lane % 6], xm), yu);
+            double ci = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                ci = fma(kPatchVinvX[lane % 6][j], __shfl_sync(0xffffffffu, fn, j), ci);
+            double c[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) c[i] = __shfl_sync(0xffffffffu, ci, i);
+            // y binade of the row: the one of its centre pixel (from the interpolant)
+            const double ydm = fma(c[0], yu, p.rad.yc);
+            const int ey = binade_of(ydm);
+            const bool row_ok = ydm > 0.0 && ey >= 0 && ey <= 22;   // warp-uniform
+            const int shx = box.shx, shy = 23 - (row_ok ? ey : 0);
+            const double Mx = __hiloint2double((int)box.mhi_x, 0);
+            const double My = __hiloint2double((int)magic_hi(shy), 0);
+            const double gx = __hiloint2double((1023 - shx) << 20, 0);   // 2^-shx
+            const double gy = __hiloint2double((1023 - shy) << 20, 0);
+            uint32_t mask = 0;
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) {
+                const int x = x_lo + lane + 32 * k;
+                const double xu = (double)x - p.rad.xc;
+                // the sampling warps' arithmetic, operation for operation
+                const double tau = ((double)(lane + 32 * k) - 63.5) * (1.0 / 64.0);
+                double f = fma(c[5], tau, c[4]);
+                f = fma(f, tau, c[3]);
+                f = fma(f, tau, c[2]);
+                f = fma(f, tau, c[1]);
+                f = fma(f, tau, c[0]);
+                const uint32_t nx = (uint32_t)__double2loint(__dadd_rn(fma(f, xu, p.rad.xc), Mx));
+                const uint32_t ny = (uint32_t)__double2loint(__dadd_rn(fma(f, yu, p.rad.yc), My));
+                // the exact coordinates
+                const double fe = radial_f(p.rad, xu, yu);
+                const double xe = fma(fe, xu, p.rad.xc), ye = fma(fe, yu, p.rad.yc);
+                bool ok = row_ok && xe > 0.0 && ye > 0.0;
+                // same float32 value (this also pins the binade: a float32 of another binade is
+                // not a multiple of the grid or lies outside [2^23, 2^24] grid units)
+                ok = ok && (double)nx * gx == (double)__double2float_rn(xe) &&
+                     (double)ny * gy == (double)__double2float_rn(ye);
+                ok = ok && nx >= (1u << 23) && nx <= (1u << 24) && ny >= (1u << 23) && ny <= (1u << 24);
+                // margin: the exact path's own variants (E/O split, one-ulp sqrt, Horner lengths
+                // known at compile time) differ from this evaluation by a few ulp of F
+                ok = ok && dist_to_f32_boundary(xe) > 0x1p-48 * (fabs(xu) + fabs(xe)) &&
+                     dist_to_f32_boundary(ye) > 0x1p-48 * (fabs(yu) + fabs(ye));
+                // 2x2 footprint inside the staged box and the image
+                const int ix = (int)(nx >> shx) - box.bx0, iy = (int)(ny >> shy) - box.by0;
+                ok = ok && (unsigned)ix < (unsigned)lim_x && (unsigned)iy < (unsigned)lim_y;
+                mask |= __all_sync(0xffffffffu, ok) ? (1u << k) : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) rp.c[i] = c[i];
+            rp.info = mask | ((uint32_t)(shy & 31) << 8);
+            rp.mhi_y = magic_hi(shy);
+            rp.mky = (1u << shy) - 1u;
+            rp.e32y = (uint32_t)(150 - shy) << 23;
+            n_full += mask == 0xfu;
+            n_part += mask != 0xfu && mask != 0u;
+        }
+        n_rows += y < y_end;
+        if (lane == 0) out.rows[r] = rp;
+    }
+    if (stats != nullptr && lane == 0) {
+        atomicAdd(stats + 5, (unsigned long long)n_full);
+        atomicAdd(stats + 6, (unsigned long long)n_part);
+        atomicAdd(stats + 7, (unsigned long long)n_rows);
+    }
+}
+
 template <int ORDER, int BLEND>
 struct ImageKernelTraits {
     // bilinear in fp64: sample from the widened tile; otherwise from the raw
@@ -289,19 +528,37 @@ struct ImageKernelTraits {
 
 // float32 box in raw stage 0 -> float64 tile `buf` (exact); producer warp `part`
 // of kImgProducers converts every kImgProducers-th group of 32 float4.  bw % 4 == 0.
+// Returns whether this part holds a value the certified blend (lerp_fma) does not cover: a set
+// sign bit, Inf / NaN, or a non-zero magnitude below 2^-80 (whose blend could be a float32
+// denormal, where the rounding boundaries are not those of the certificate).
 struct ImageParams;
-__device__ __forceinline__ void widen_part(const ImageParams &p, unsigned char *smem, int buf,
+__device__ __forceinline__ bool widen_part(const ImageParams &p, unsigned char *smem, int buf,
                                            int part, int lane);
 
-constexpr int kBoxRing = 4;       // tile boxes in flight between the producer and the samplers
+constexpr int kRecRing = 3;       // WIDE: plan records in flight (tiles j-1, j being sampled, j+1 landing)
 constexpr int kImgProducers = 2;                             // producer warps
 constexpr int kImgThreads = kThreads + 32 * kImgProducers;   // 8 sampling warps + the producers
 
 // Shared-memory layout (host side must agree, see plan_and_launch_image in api.cu):
 //   WIDE : [raw][wide 0][wide 1][tail]      raw = stage_bytes, wide = 2 * stage_bytes
 //   !WIDE: [raw 0][raw 1][tail]
-//   tail : uint64_t raw_full[2], data_full[2], data_empty[2]; TileBox boxes[kBoxRing]
-__host__ __device__ constexpr size_t image_tail_bytes() { return 48 + kBoxRing * sizeof(TileBox); }
+//   tail : uint64_t raw_full[2], data_full[2], data_empty[2]; uint32_t odd[4] (tile buffer holds
+//          values the certified blend does not cover); TilePlan<TH> rec[WIDE ? kRecRing : 2]
+__host__ __device__ constexpr size_t image_rec_bytes(int th) {
+    return sizeof(TileBox) + (size_t)th * sizeof(RowPatch);
+}
+__host__ __device__ constexpr size_t image_tail_bytes(int th, bool wide) {
+    return 48 + 16 + (wide ? kRecRing : 2) * image_rec_bytes(th);
+}
+
+// 1-D bulk copy global -> shared, completion on an mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes,
+                                          uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
 
 // NT > 0: number of polynomial terms known at compile time (coefficients become
 // constant-bank operands of the DFMAs); NT == 0: any p.rad.n through a switch.
@@ -309,8 +566,9 @@ __host__ __device__ constexpr size_t image_tail_bytes() { return 48 + kBoxRing *
 // allocation is held to.
 //
 // Warp-specialised: warps 0..7 only evaluate coordinates and sample; warp 8 (the
-// producer) places the source boxes, issues the TMA loads and -- for the fp64
-// blends, together with warp 9 -- widens each landed float32 box into one of two
+// producer) walks the plan: per tile one TMA load of the staged box and one bulk copy of the
+// tile's plan record, both completing on the same mbarrier, and -- for the fp64 blends,
+// together with warp 9 -- widens each landed float32 box into one of two
 // float64 tiles (one warp alone could not keep ahead of the samplers: with it
 // they spent 26 % of their time waiting, profiles/r1/ncu_summary_v6.txt).  The
 // hand-over is by mbarriers (data_full: producer -> samplers, data_empty: one
@@ -322,13 +580,18 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     remap_image_kernel(const __grid_constant__ ImageParams p,
                        const __grid_constant__ CUtensorMap tmap) {
     constexpr bool WIDE = ImageKernelTraits<ORDER, BLEND>::kWide;
+    constexpr bool PATCH = (MAP == MAP_RADIAL) && kImgBoxW > 0;   // the patch path exists
     constexpr int RPW = TH / kWarps;  // rows per sampling warp and tile
+    constexpr int NREC = WIDE ? kRecRing : 2;
+    constexpr uint32_t kRecBytes = (uint32_t)sizeof(TilePlan<TH>);
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *tail = smem + (WIDE ? 5 : 2) * (size_t)p.stage_bytes;
     uint64_t *raw_full = reinterpret_cast<uint64_t *>(tail);         // [2] TMA bytes landed
     uint64_t *data_full = raw_full + 2;                              // [2] WIDE: float64 tile ready
     uint64_t *data_empty = raw_full + 4;                             // [2] tile buffer released
-    TileBox *boxes = reinterpret_cast<TileBox *>(tail + 48);         // [kBoxRing]
+    uint32_t *odd = reinterpret_cast<uint32_t *>(tail + 48);         // [2] see widen_part
+    TilePlan<TH> *rec = reinterpret_cast<TilePlan<TH> *>(tail + 64); // [NREC]
+    const TilePlan<TH> *plan = reinterpret_cast<const TilePlan<TH> *>(p.plan);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -336,8 +599,6 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     const int wmax = p.W - 1;
     const int y_end = p.row0 + p.nrows;
 
-    // this CTA's tiles: a contiguous range of the column-major tile order, so
-    // consecutive tiles sit below each other and share their column terms
     // This CTA's tiles.  deal == 0: a contiguous range of the column-major tile order, so that
     // consecutive tiles sit below each other and share their column terms -- 3 % faster when every
     // tile costs the same.  deal == 1 (the host sets it when part of the map is clipped at the
@@ -356,6 +617,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             mbar_init(&raw_full[b], 1);
             mbar_init(&data_full[b], 1);
             mbar_init(&data_empty[b], kWarps);
+            odd[b] = 0;
         }
         fence_mbar_init();
         if (staged) tma_prefetch_desc(&tmap);
@@ -368,14 +630,14 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             uint32_t nraw = 0;
             for (int j = 0; j < n; ++j) {
                 const int b = j & 1;
-                // tile j's box slot was published before its copy was started (see warp 8)
                 if (j >= 2) mbar_wait(&data_empty[b], (uint32_t)((j >> 1) - 1) & 1u);
-                // the leader tells through the named barrier whether this tile is staged
-                asm volatile("bar.sync 1, 64;" ::: "memory");   // (A) box j published / decided
-                if (boxes[j % kBoxRing].use) {
-                    mbar_wait(&raw_full[0], nraw & 1u);
-                    ++nraw;
-                    widen_part(p, smem, b, 1, lane);
+                asm volatile("bar.sync 1, 64;" ::: "memory");   // (A) buffer b is free
+                // tile j's record and box (if staged) have landed
+                mbar_wait(&raw_full[0], nraw & 1u);
+                ++nraw;
+                if (rec[j % NREC].box.use) {
+                    const bool o = widen_part(p, smem, b, 1, lane);
+                    if (PATCH && __any_sync(0xffffffffu, o) && lane == 0) atomicOr(&odd[b], 1u);
                 }
                 asm volatile("bar.sync 1, 64;" ::: "memory");   // (B) both halves written, raw free
             }
@@ -384,71 +646,45 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     }
     if (warp == kWarps) {
         // =========================== producer warp ===================================
-        // place the source box of local tile k from 9 probe points (all 32 lanes)
-        auto place_box = [&](int k) -> bool {
-            const int t = tile_of(k);
-            const int txi = t / p.tiles_y, tyi = t - txi * p.tiles_y;
-            const int x_lo = txi * kTileW, y_lo = p.row0 + tyi * TH;
-            const int x_hi = min(x_lo + kTileW - 1, wmax), y_hi = min(y_lo + TH - 1, y_end - 1);
-            const int q = lane % 9;
-            const int px = x_lo + ((x_hi - x_lo) * (q % 3)) / 2;
-            const int py = y_lo + ((y_hi - y_lo) * (q / 3)) / 2;
-            float xf, yf;
-            map_point<MAP>(p, px, py, xf, yf);
-            const int mnx = __reduce_min_sync(0xffffffffu, (int)xf);
-            const int mny = __reduce_min_sync(0xffffffffu, (int)yf);
-            const int mxx = __reduce_max_sync(0xffffffffu, (int)xf);
-            const int mxy = __reduce_max_sync(0xffffffffu, (int)yf);
-            // one pixel of slack around the probes for curvature inside the tile
-            const int bx0 = max(mnx - 1, 0) & ~3;
-            const int by0 = min(max(mny - 1, p.yorg), p.ylast);
-            const bool use = staged && (mxx + 2 - bx0 < p.bw) && (mxy + 2 - by0 < p.bh);
-            if (lane == 0) boxes[k % kBoxRing] = TileBox{bx0, by0, use ? 1 : 0, 0};
-            __syncwarp();
-            return use;
-        };
-        // lane 0: start the copy of local tile k's box into raw stage `st`
-        auto issue_tma = [&](int k, int st) {
-            const TileBox b = boxes[k % kBoxRing];
-            mbar_expect_tx(&raw_full[st], p.box_bytes);
-            tma_load_3d(smem + (size_t)st * p.stage_bytes, &tmap, b.bx0, b.by0 - p.yorg, 0,
-                        &raw_full[st]);
+        // lane 0: start the copies of local tile k -- its plan record into record slot `rs` and,
+        // when the tile is staged, its box into raw stage `st` -- both completing on raw_full[st]
+        auto issue = [&](int k, int st, int rs) {
+            const TilePlan<TH> *tp = plan + tile_of(k);
+            const int4 bx = __ldg(reinterpret_cast<const int4 *>(&tp->box));   // bx0, by0, use, shx
+            mbar_expect_tx(&raw_full[st], kRecBytes + (bx.z ? p.box_bytes : 0u));
+            bulk_load(&rec[rs], tp, kRecBytes, &raw_full[st]);
+            if (bx.z)
+                tma_load_3d(smem + (size_t)st * p.stage_bytes, &tmap, bx.x, bx.y - p.yorg, 0,
+                            &raw_full[st]);
         };
         if (WIDE) {
-            uint32_t nraw = 0;  // TMA fills consumed from the single raw stage
-            bool use_cur = n > 0 ? place_box(0) : false;
-            if (use_cur && lane == 0) issue_tma(0, 0);
+            uint32_t nraw = 0;  // fills consumed from the single raw stage
+            if (n > 0 && lane == 0) issue(0, 0, 0);
             for (int j = 0; j < n; ++j) {
                 const int b = j & 1;
-                // the next box is placed while this tile's copy is in flight
-                const bool use_next = (j + 1 < n) ? place_box(j + 1) : false;
                 if (j >= 2) mbar_wait(&data_empty[b], (uint32_t)((j >> 1) - 1) & 1u);
+                if (PATCH && lane == 0) odd[b] = 0u;   // buffer b is free: reset its flag
                 asm volatile("bar.sync 1, 64;" ::: "memory");   // (A)
-                if (use_cur) {
-                    mbar_wait(&raw_full[0], nraw & 1u);
-                    ++nraw;
-                    widen_part(p, smem, b, 0, lane);
+                mbar_wait(&raw_full[0], nraw & 1u);
+                ++nraw;
+                if (rec[j % NREC].box.use) {
+                    const bool o = widen_part(p, smem, b, 0, lane);
+                    if (PATCH && __any_sync(0xffffffffu, o) && lane == 0) atomicOr(&odd[b], 1u);
                 }
                 asm volatile("bar.sync 1, 64;" ::: "memory");   // (B) float64 tile complete, raw free
                 if (lane == 0) {
-                    if (use_next) issue_tma(j + 1, 0);
+                    // (the samplers have left tile j-2, whose record slot tile j+1 takes over)
+                    if (j + 1 < n) issue(j + 1, 0, (j + 1) % NREC);
                     mbar_arrive(&data_full[b]);
                 }
-                use_cur = use_next;
             }
         } else {
             // raw stage k&1 doubles as the data buffer: the samplers wait on raw_full[k&1];
             // the producer runs at most two tiles ahead of the slowest sampling warp
             for (int k = 0; k < n; ++k) {
                 const int b = k & 1;
-                const bool use = place_box(k);
                 if (k >= 2) mbar_wait(&data_empty[b], (uint32_t)((k >> 1) - 1) & 1u);
-                if (lane == 0) {
-                    if (use)
-                        issue_tma(k, b);
-                    else
-                        mbar_arrive(&raw_full[b]);
-                }
+                if (lane == 0) issue(k, b, b);
             }
         }
         return;
@@ -463,11 +699,21 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         for (int k = 0; k < kCols; ++k) xs[k] = min(txi * kTileW + lane + 32 * k, wmax);
         ev.set_columns(p, xs);
     }
+    // patch path: the thread's four columns in the tile's variable tau = (x - x_tile - 63.5) / 64
+    // (opaque to the compiler: under the register cap it would otherwise re-derive them from the
+    // lane index -- four I2F and eight fp64 operations -- in every row)
+    double tau[kCols];
+#pragma unroll
+    for (int k = 0; k < kCols; ++k) {
+        tau[k] = ((double)(lane + 32 * k) - 63.5) * (1.0 / 64.0);
+        asm volatile("" : "+d"(tau[k]));
+    }
 
     for (int i = 0; i < n; ++i) {
         // tile i is ready: WIDE -> float64 tile i&1 written by the producer; !WIDE -> raw stage landed
         mbar_wait(WIDE ? &data_full[i & 1] : &raw_full[i & 1], (uint32_t)(i >> 1) & 1u);
-        const TileBox box = boxes[i % kBoxRing];
+        const TilePlan<TH> &trec = rec[i % NREC];
+        const TileBox box = trec.box;
         // ---- sample tile i ---------------------------------------------------------
         {
             const int x_base = txi * kTileW + lane;
@@ -487,9 +733,23 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             // (ordered after the mbarrier wait above: every tap address below depends on it)
             uint32_t wide_s = smem_u32(widet);
             asm volatile("" : "+r"(wide_s)::"memory");
-            const bool full_w = (txi * kTileW + kTileW - 1 <= wmax);  // CTA-uniform
+            // CTA-uniform; through a vote so that the compiler knows it too (the four stores of a
+            // row then sit in uniform control flow and keep their memory descriptor in a uniform
+            // register instead of eight R2UR per row)
+            const bool full_w = __all_sync(0xffffffffu, txi * kTileW + kTileW - 1 <= wmax);
             float *orow = p.dst + (long long)(y_base - p.row0) * p.dst_pitch + x_base;
             double yd = (double)y_base;
+            // patch path, per tile: the x rounding constants and the tap address of image pixel (0, 0)
+            const int shx = box.shx;
+            const uint32_t mkx = (uint32_t)box.pad[0], e32x = (uint32_t)box.pad[1];
+            const double Mx = __hiloint2double((int)box.mhi_x, 0);
+            const int khx = (int)box.mhi_x - 0x80000;
+            const double Kx = __hiloint2double(khx, 0);
+            const uint32_t org = (uint32_t)(box.by0 * bw + box.bx0);
+            const uint32_t base_s = (WIDE ? wide_s : smem_u32(rawt)) - (WIDE ? 8u : 4u) * org;
+            const bool tile_odd = WIDE && BLEND == DCB_BLEND_EXACT && (odd[sb] != 0u);
+            const RowPatch *prow = trec.rows + warp * RPW;
+            unsigned n_bfail = 0;   // diagnostics, see p.stats
 #ifndef DCB_IMG_UNROLL
 #define DCB_IMG_UNROLL 1
 #endif
@@ -500,6 +760,95 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             // 44.0 -- the atomic and the lost incremental row state cost more than the 8 % the
             // warps wait for each other at tile boundaries.)
             for (int j = 0; j < nrow; ++j, yd += 1.0, orow += p.dst_pitch) {
+                float v[kCols];
+                bool done = false;
+                if constexpr (PATCH) if (shx != 0) {
+                    // ------------------- the patch path (see RowPatch) -------------------
+                    const uint4 inf = *reinterpret_cast<const uint4 *>(&prow[j].info);
+                    if ((inf.x & 0xfu) == 0xfu) {
+                        const double2 c01 = *reinterpret_cast<const double2 *>(&prow[j].c[0]);
+                        const double2 c23 = *reinterpret_cast<const double2 *>(&prow[j].c[2]);
+                        const double2 c45 = *reinterpret_cast<const double2 *>(&prow[j].c[4]);
+                        const double yu = __dsub_rn(yd, p.rad.yc);
+                        double xq[kCols], yq[kCols];
+#pragma unroll
+                        for (int k = 0; k < kCols; ++k) {
+                            double f = fma(c45.y, tau[k], c45.x);
+                            f = fma(f, tau[k], c23.y);
+                            f = fma(f, tau[k], c23.x);
+                            f = fma(f, tau[k], c01.y);
+                            f = fma(f, tau[k], c01.x);
+                            xq[k] = fma(f, ev.xu[k], p.rad.xc);
+                            yq[k] = fma(f, yu, p.rad.yc);
+                        }
+                        const int shy = (int)(inf.x >> 8) & 31;
+                        const uint32_t mky = inf.z, e32y = inf.w;
+                        const double My = __hiloint2double((int)inf.y, 0);
+                        const int khy = (int)inf.y - 0x80000;
+                        const double Ky = __hiloint2double(khy, 0);
+                        uint32_t accb = 0xffffffffu;
+                        // ODD: the tile holds values lerp_fma is not certified for -> SciPy's sum
+                        auto sample4 = [&](auto odd_tag) {
+                            constexpr bool ODD = decltype(odd_tag)::value;
+#pragma unroll
+                            for (int k = 0; k < kCols; ++k) {
+                                // round to the float32 grid: the low word is the coordinate in ulp32
+                                const uint32_t nx = (uint32_t)__double2loint(__dadd_rn(xq[k], Mx));
+                                const uint32_t ny = (uint32_t)__double2loint(__dadd_rn(yq[k], My));
+                                if (ORDER == 0) {
+                                    const uint32_t xi = (nx + (1u << (shx - 1))) >> shx;
+                                    const uint32_t yi = (ny + (1u << (shy - 1))) >> shy;
+                                    float t;
+                                    asm("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(base_s + 4u * (yi * bw + xi)));
+                                    v[k] = t;
+                                    continue;
+                                }
+                                const uint32_t xi = nx >> shx, yi = ny >> shy;
+                                const uint32_t fx = nx & mkx, fy = ny & mky;
+                                if (!WIDE) {
+                                    // fraction as a float: exponent 150 - sh puts its ulp at 2^-sh
+                                    const float tx = __uint_as_float(e32x | fx) - __uint_as_float(e32x);
+                                    const float ty = __uint_as_float(e32y | fy) - __uint_as_float(e32y);
+                                    const uint32_t qa = base_s + 4u * (yi * bw + xi);
+                                    float a, b, c, d;
+                                    asm("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(qa));
+                                    asm("ld.shared.f32 %0, [%1+4];" : "=f"(b) : "r"(qa));
+                                    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(c) : "r"(qa), "n"(4 * kImgBoxW));
+                                    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(d) : "r"(qa), "n"(4 * kImgBoxW + 4));
+                                    const float top = fmaf(b - a, tx, a);
+                                    const float bot = fmaf(d - c, tx, c);
+                                    v[k] = fmaf(bot - top, ty, top);
+                                    continue;
+                                }
+                                const double tx = __dsub_rn(__hiloint2double(khx, (int)fx), Kx);   // exact
+                                const double ty = __dsub_rn(__hiloint2double(khy, (int)fy), Ky);
+                                const uint32_t qa = base_s + 8u * (yi * bw + xi);
+                                const double a = lds_f64<0>(qa), b = lds_f64<8>(qa);
+                                const double c = lds_f64<8 * kImgBoxW>(qa), d = lds_f64<8 * kImgBoxW + 8>(qa);
+                                double sd;
+                                if (BLEND == DCB_BLEND_LERP64) {
+                                    const double top = fma(b - a, tx, a);
+                                    const double bot = fma(d - c, tx, c);
+                                    sd = fma(bot - top, ty, top);
+                                } else if (ODD) {
+                                    sd = blend_exact(a, b, c, d, tx, ty);
+                                } else {
+                                    sd = lerp_fma(a, b, c, d, tx, ty);
+                                    accb = min(accb, cert_key(sd, kBlendCertAdd));
+                                }
+                                v[k] = __double2float_rn(sd);
+                            }
+                        };
+                        if (tile_odd)
+                            sample4(std::true_type{});
+                        else
+                            sample4(std::false_type{});
+                        // (a blend within 32 ulp64 of a rounding boundary: the exact row below)
+                        done = !__any_sync(0xffffffffu, accb < kBlendCertLim);
+                        n_bfail += done ? 0u : 1u;
+                    }
+                }
+                if (!done) {
                 float xf[kCols], yf[kCols];
                 ev.row(p, yd, xf, yf);
                 float tfx[kCols], tfy[kCols];
@@ -514,7 +863,6 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                     ok = ok && ((unsigned)ix[k] < (unsigned)lim_x) &&
                          ((unsigned)iy[k] < (unsigned)lim_y);
                 }
-                float v[kCols];
                 if (__all_sync(0xffffffffu, ok)) {
                     double sd[WIDE ? kCols : 1];
 #pragma unroll
@@ -576,6 +924,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                                                               clamp_bits(yf[k], hbits), wmax,
                                                               p.yorg, p.ylast, p.rint);
                 }
+                }
                 if (full_w) {
 #pragma unroll
                     for (int k = 0; k < kCols; ++k) __stcs(orow + 32 * k, v[k]);
@@ -585,8 +934,11 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                         if (x_base + 32 * k <= wmax) __stcs(orow + 32 * k, v[k]);
                 }
             }
+            if (n_bfail != 0 && p.stats != nullptr && lane == 0)
+                atomicAdd(p.stats + 3, (unsigned long long)n_bfail);
+            if (tile_odd && p.stats != nullptr && threadIdx.x == 0) atomicAdd(p.stats + 4, 1ull);
         }
-        // this warp is done with buffer i&1 (and with boxes[i % kBoxRing])
+        // this warp is done with buffer i&1 (and with its plan record)
         __syncwarp();
         if (lane == 0) mbar_arrive(&data_empty[i & 1]);
         // next tile of this CTA
@@ -605,30 +957,37 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     }
 }
 
-__device__ __forceinline__ void widen_part(const ImageParams &p, unsigned char *smem, int buf,
+__device__ __forceinline__ bool widen_part(const ImageParams &p, unsigned char *smem, int buf,
                                            int part, int lane) {
-    const float4 *src4 = reinterpret_cast<const float4 *>(smem);
+    const uint4 *src4 = reinterpret_cast<const uint4 *>(smem);
     double2 *dst2 = reinterpret_cast<double2 *>(smem + (size_t)(1 + 2 * buf) * p.stage_bytes);
     const int n4 = (p.bw * p.bh) >> 2;
     constexpr int kStep = 32 * kImgProducers;
+    // as unsigned integers: hi = largest bit pattern (sign bit or Inf / NaN => >= 0x7f800000),
+    // lo = smallest pattern - 1 (zero wraps to the top, so it is ignored)
+    uint32_t hi = 0u, lo = 0xffffffffu;
+    auto put = [&](int e, const uint4 &u) {
+        dst2[2 * e] = make_double2((double)__uint_as_float(u.x), (double)__uint_as_float(u.y));
+        dst2[2 * e + 1] = make_double2((double)__uint_as_float(u.z), (double)__uint_as_float(u.w));
+        hi = __vimax3_u32(hi, u.x, u.y);
+        hi = __vimax3_u32(hi, u.z, u.w);
+        lo = __vimin3_u32(lo, u.x - 1u, u.y - 1u);
+        lo = __vimin3_u32(lo, u.z - 1u, u.w - 1u);
+    };
     int e = lane + 32 * part;
     for (; e + 3 * kStep < n4; e += 4 * kStep) {
-        const float4 u0 = src4[e], u1 = src4[e + kStep], u2 = src4[e + 2 * kStep],
-                     u3 = src4[e + 3 * kStep];
-        dst2[2 * e] = make_double2((double)u0.x, (double)u0.y);
-        dst2[2 * e + 1] = make_double2((double)u0.z, (double)u0.w);
-        dst2[2 * (e + kStep)] = make_double2((double)u1.x, (double)u1.y);
-        dst2[2 * (e + kStep) + 1] = make_double2((double)u1.z, (double)u1.w);
-        dst2[2 * (e + 2 * kStep)] = make_double2((double)u2.x, (double)u2.y);
-        dst2[2 * (e + 2 * kStep) + 1] = make_double2((double)u2.z, (double)u2.w);
-        dst2[2 * (e + 3 * kStep)] = make_double2((double)u3.x, (double)u3.y);
-        dst2[2 * (e + 3 * kStep) + 1] = make_double2((double)u3.z, (double)u3.w);
+        const uint4 u0 = src4[e], u1 = src4[e + kStep], u2 = src4[e + 2 * kStep],
+                    u3 = src4[e + 3 * kStep];
+        put(e, u0);
+        put(e + kStep, u1);
+        put(e + 2 * kStep, u2);
+        put(e + 3 * kStep, u3);
     }
     for (; e < n4; e += kStep) {
-        const float4 u = src4[e];
-        dst2[2 * e] = make_double2((double)u.x, (double)u.y);
-        dst2[2 * e + 1] = make_double2((double)u.z, (double)u.w);
+        const uint4 u = src4[e];
+        put(e, u);
     }
+    return hi >= 0x7f800000u || lo < 0x17800000u - 1u;
 }
 
 }  // namespace dcb

@@ -317,6 +317,24 @@ def last_plan():
                     [v.value for v in vals]))
 
 
+def image_stats(enable=True, reset=False):
+    """Counters of the single-image kernel's patch path (``dcb_image_stats``); ``enable``
+    switches the counting on or off, the dict holds the counts since the last reset
+    (``rows_*`` come from the plans built while counting was on)."""
+    out = (ctypes.c_uint64 * 8)()
+    _cabi.call("dcb_image_stats", 1 if enable else 0, out, 1 if reset else 0)
+    return {"rows_blend_redo": int(out[3]), "tiles_odd": int(out[4]), "rows_patch": int(out[5]),
+            "rows_partial": int(out[6]), "rows": int(out[7])}
+
+
+def plan_cache_clear():
+    """Drop the cached plans of the single-image kernel; returns how many plans this process has
+    built so far."""
+    n = ctypes.c_uint64()
+    _cabi.call("dcb_plan_cache_clear", ctypes.byref(n))
+    return n.value
+
+
 # --------------------------------------------------------------------------
 # device-resident float32 arrays
 # --------------------------------------------------------------------------

@@ -280,8 +280,10 @@ int dcb_unwarp_image_forward_f32(const float *src, float *dst, int H, int W, siz
                                  size_t dst_pitch, const dcb_radial *model_host,
                                  uint32_t *workspace, void *stream);
 
-/* Number of kernel launches issued by this library in the calling process
- * (all threads) since load / since the last reset. */
+/* Number of compute-kernel launches issued by this library in the calling process
+ * (all threads) since load / since the last reset.  Plan builds of the single-image kernel (one
+ * small kernel the first time a (model, geometry) pair is seen) are counted separately, see
+ * dcb_plan_cache_clear. */
 int dcb_launch_count(uint64_t *count);
 int dcb_launch_count_reset(void);
 
@@ -289,6 +291,22 @@ int dcb_launch_count_reset(void);
  * (enum dcb_path, never AUTO), staged box width/height, grid size, dynamic
  * shared memory bytes. */
 int dcb_last_plan(int *path, int *box_w, int *box_h, int *grid, int *smem_bytes);
+
+/* Drops every cached plan of the single-image kernel (per-tile staged boxes and verified row
+ * patches, built once per (model, geometry) and reused for later frames; csrc/remap_image.cuh,
+ * csrc/api.cu "Plan cache") on all devices; *plans_built, when not NULL, receives the number of
+ * plans built by this process so far.  Environment: DCB_PLAN_CACHE=0 builds a plan per launch,
+ * DCB_PLAN_CACHE_MB bounds the cache (default 512). */
+int dcb_plan_cache_clear(uint64_t *plans_built);
+
+/* Diagnostics of the single-image kernel's patch path (csrc/remap_image.cuh, RowPatch): counting is
+ * switched on with enable != 0 (a small device buffer is allocated on the current device) and off
+ * with 0; out[0..7], when not NULL, receives since the last reset: [3] patch rows redone exactly
+ * because of the blend certificate, [4] tiles holding values the certified blend does not cover,
+ * and from the plans BUILT while counting was on: [5] tile rows verified for the patch path in
+ * full, [6] rows verified in part (such rows take the exact path), [7] rows in total; 0..2
+ * reserved.  reset != 0 clears the counters after reading. */
+int dcb_image_stats(int enable, uint64_t *out, int reset);
 
 /* Device self-test of the custom fp64 square root used by the radial kernels
  * (probe points, Z-stack geometry) against IEEE sqrt on n pseudo-random inputs; *mismatch receives the number
