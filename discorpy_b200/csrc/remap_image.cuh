@@ -76,6 +76,15 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 #ifndef DCB_IMG_LDS32
 #define DCB_IMG_LDS32 1
 #endif
+// output stores: streaming (evict-first) by default; -DDCB_IMG_STCS=0 for A/B builds
+#ifndef DCB_IMG_STCS
+#define DCB_IMG_STCS 1
+#endif
+#if DCB_IMG_STCS
+#define DCB_IMG_STORE(ptr, val) __stcs((ptr), (val))
+#else
+#define DCB_IMG_STORE(ptr, val) (*(ptr) = (val))
+#endif
 
 struct TileBox {
     int bx0, by0;  // image coordinates of box element (0,0)
@@ -425,10 +434,9 @@ __global__ void __launch_bounds__(kThreads)
             if (xd > 0.0 && ex >= 0 && ex <= 22) {
                 bx.shx = 23 - ex;
                 bx.mhi_x = magic_hi(bx.shx);
-                bx.pad[0] = (1 << bx.shx) - 1;
-                bx.pad[1] = (150 - bx.shx) << 23;
             }
         }
+        bx.pad[0] = txi, bx.pad[1] = tyi;   // the sampling warps need no division to find the tile
         if (lane == 0) {
             sbox = bx;
             out.box = bx;
@@ -464,9 +472,7 @@ __global__ void __launch_bounds__(kThreads)
             const int ey = binade_of(ydm);
             const bool row_ok = ydm > 0.0 && ey >= 0 && ey <= 22;   // warp-uniform
             const int shx = box.shx, shy = 23 - (row_ok ? ey : 0);
-            const double Mx = __hiloint2double((int)box.mhi_x, 0);
             const double My = __hiloint2double((int)magic_hi(shy), 0);
-            const double gx = __hiloint2double((1023 - shx) << 20, 0);   // 2^-shx
             const double gy = __hiloint2double((1023 - shy) << 20, 0);
             uint32_t mask = 0;
 #pragma unroll
@@ -480,25 +486,40 @@ __global__ void __launch_bounds__(kThreads)
                 f = fma(f, tau, c[2]);
                 f = fma(f, tau, c[1]);
                 f = fma(f, tau, c[0]);
-                const uint32_t nx = (uint32_t)__double2loint(__dadd_rn(fma(f, xu, p.rad.xc), Mx));
-                const uint32_t ny = (uint32_t)__double2loint(__dadd_rn(fma(f, yu, p.rad.yc), My));
+                const double xp = fma(f, xu, p.rad.xc), yp = fma(f, yu, p.rad.yc);
+                const uint32_t ny = (uint32_t)__double2loint(__dadd_rn(yp, My));
                 // the exact coordinates
                 const double fe = radial_f(p.rad, xu, yu);
                 const double xe = fma(fe, xu, p.rad.xc), ye = fma(fe, yu, p.rad.yc);
-                bool ok = row_ok && xe > 0.0 && ye > 0.0;
-                // same float32 value (this also pins the binade: a float32 of another binade is
-                // not a multiple of the grid or lies outside [2^23, 2^24] grid units)
-                ok = ok && (double)nx * gx == (double)__double2float_rn(xe) &&
-                     (double)ny * gy == (double)__double2float_rn(ye);
-                ok = ok && nx >= (1u << 23) && nx <= (1u << 24) && ny >= (1u << 23) && ny <= (1u << 24);
                 // margin: the exact path's own variants (E/O split, one-ulp sqrt, Horner lengths
                 // known at compile time) differ from this evaluation by a few ulp of F
-                ok = ok && dist_to_f32_boundary(xe) > 0x1p-48 * (fabs(xu) + fabs(xe)) &&
-                     dist_to_f32_boundary(ye) > 0x1p-48 * (fabs(yu) + fabs(ye));
-                // 2x2 footprint inside the staged box and the image
-                const int ix = (int)(nx >> shx) - box.bx0, iy = (int)(ny >> shy) - box.by0;
-                ok = ok && (unsigned)ix < (unsigned)lim_x && (unsigned)iy < (unsigned)lim_y;
-                mask |= __all_sync(0xffffffffu, ok) ? (1u << k) : 0u;
+                bool oky = row_ok && xe > 0.0 && ye > 0.0 && xp > 0.0 &&
+                           dist_to_f32_boundary(xe) > 0x1p-48 * (fabs(xu) + fabs(xe)) &&
+                           dist_to_f32_boundary(ye) > 0x1p-48 * (fabs(yu) + fabs(ye));
+                // same float32 value (this also pins the binade: a float32 of another binade is
+                // not a multiple of the grid or lies outside [2^23, 2^24] grid units)
+                oky = oky && (double)ny * gy == (double)__double2float_rn(ye) && ny >= (1u << 23) &&
+                      ny <= (1u << 24);
+                const int iy = (int)(ny >> shy) - box.by0;
+                oky = oky && (unsigned)iy < (unsigned)lim_y;
+                // x with the tile's binade (variant 0) and with the pixel's own (variant 1)
+#pragma unroll
+                for (int var = 0; var < 2; ++var) {
+                    const uint32_t hx = (uint32_t)__double2hiint(xp);
+                    const int sx = var ? 1046 - (int)(hx >> 20) : shx;
+                    const uint32_t mhx = var ? (hx & 0x7ff00000u) + 0x01d80000u : box.mhi_x;
+                    bool ok = oky && sx >= 1 && sx <= 23;
+                    const int sxc = min(max(sx, 1), 23);
+                    const uint32_t nx =
+                        (uint32_t)__double2loint(__dadd_rn(xp, __hiloint2double((int)mhx, 0)));
+                    const double gxv = __hiloint2double((1023 - sxc) << 20, 0);   // 2^-sx
+                    ok = ok && (double)nx * gxv == (double)__double2float_rn(xe) &&
+                         nx >= (1u << 23) && nx <= (1u << 24);
+                    // 2x2 footprint inside the staged box and the image
+                    const int ix = (int)(nx >> sxc) - box.bx0;
+                    ok = ok && (unsigned)ix < (unsigned)lim_x;
+                    mask |= __all_sync(0xffffffffu, ok) ? (1u << (k + 4 * var)) : 0u;
+                }
             }
 #pragma unroll
             for (int i = 0; i < 6; ++i) rp.c[i] = c[i];
@@ -506,8 +527,8 @@ __global__ void __launch_bounds__(kThreads)
             rp.mhi_y = magic_hi(shy);
             rp.mky = (1u << shy) - 1u;
             rp.e32y = (uint32_t)(150 - shy) << 23;
-            n_full += mask == 0xfu;
-            n_part += mask != 0xfu && mask != 0u;
+            n_full += (mask & 0xfu) == 0xfu || (mask & 0xf0u) == 0xf0u;
+            n_part += !((mask & 0xfu) == 0xfu || (mask & 0xf0u) == 0xf0u) && mask != 0u;
         }
         n_rows += y < y_end;
         if (lane == 0) out.rows[r] = rp;
@@ -594,7 +615,10 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     const TilePlan<TH> *plan = reinterpret_cast<const TilePlan<TH> *>(p.plan);
 
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    // (through a shuffle: the compiler then knows the warp index is warp-uniform and keeps what
+    // derives from it -- row counts, tile addresses, the stores' memory descriptor -- on the
+    // uniform datapath)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const bool staged = p.bw > 0;
     const int wmax = p.W - 1;
     const int y_end = p.row0 + p.nrows;
@@ -691,14 +715,8 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     }
 
     // ============================== sampling warps ====================================
-    int txi = t0 / p.tiles_y, tyi = t0 - txi * p.tiles_y;
+    int txi = -1;   // tile column the per-thread column terms are set for
     MapEval<MAP, NT> ev;
-    {
-        int xs[kCols];
-#pragma unroll
-        for (int k = 0; k < kCols; ++k) xs[k] = min(txi * kTileW + lane + 32 * k, wmax);
-        ev.set_columns(p, xs);
-    }
     // patch path: the thread's four columns in the tile's variable tau = (x - x_tile - 63.5) / 64
     // (opaque to the compiler: under the register cap it would otherwise re-derive them from the
     // lane index -- four I2F and eight fp64 operations -- in every row)
@@ -714,6 +732,14 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         mbar_wait(WIDE ? &data_full[i & 1] : &raw_full[i & 1], (uint32_t)(i >> 1) & 1u);
         const TilePlan<TH> &trec = rec[i % NREC];
         const TileBox box = trec.box;
+        const int tyi = box.pad[1];
+        if (box.pad[0] != txi) {   // CTA-uniform: a new tile column
+            txi = box.pad[0];
+            int xs[kCols];
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) xs[k] = min(txi * kTileW + lane + 32 * k, wmax);
+            ev.set_columns(p, xs);
+        }
         // ---- sample tile i ---------------------------------------------------------
         {
             const int x_base = txi * kTileW + lane;
@@ -733,18 +759,12 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             // (ordered after the mbarrier wait above: every tap address below depends on it)
             uint32_t wide_s = smem_u32(widet);
             asm volatile("" : "+r"(wide_s)::"memory");
-            // CTA-uniform; through a vote so that the compiler knows it too (the four stores of a
-            // row then sit in uniform control flow and keep their memory descriptor in a uniform
-            // register instead of eight R2UR per row)
-            const bool full_w = __all_sync(0xffffffffu, txi * kTileW + kTileW - 1 <= wmax);
+            const bool full_w = __all_sync(0xffffffffu, txi * kTileW + kTileW - 1 <= wmax);  // CTA-uniform
             float *orow = p.dst + (long long)(y_base - p.row0) * p.dst_pitch + x_base;
             double yd = (double)y_base;
             // patch path, per tile: the x rounding constants and the tap address of image pixel (0, 0)
-            const int shx = box.shx;
-            const uint32_t mkx = (uint32_t)box.pad[0], e32x = (uint32_t)box.pad[1];
-            const double Mx = __hiloint2double((int)box.mhi_x, 0);
-            const int khx = (int)box.mhi_x - 0x80000;
-            const double Kx = __hiloint2double(khx, 0);
+            const int shx_t = box.shx;
+            const uint32_t mkx_t = (1u << shx_t) - 1u, e32x_t = (uint32_t)(150 - shx_t) << 23;
             const uint32_t org = (uint32_t)(box.by0 * bw + box.bx0);
             const uint32_t base_s = (WIDE ? wide_s : smem_u32(rawt)) - (WIDE ? 8u : 4u) * org;
             const bool tile_odd = WIDE && BLEND == DCB_BLEND_EXACT && (odd[sb] != 0u);
@@ -754,6 +774,13 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
 #define DCB_IMG_UNROLL 1
 #endif
             constexpr int kRowUnroll = DCB_IMG_UNROLL;   // A/B builds; 1 measured best
+            // The row loop exists twice: for tiles that are 128 pixels wide (all but the last
+            // column of an image whose width is not a multiple of 128) the four stores of a row
+            // are unconditional -- predicated, ptxas moved their memory descriptor from a vector
+            // register pair to uniform registers eight times per row (2 of 70 instructions per
+            // pixel).
+            auto tile_rows = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll kRowUnroll
             // (Rows claimed one at a time from a shared counter by whichever sampling warp is free,
             // instead of this static split, were measured: 61.5 / 59.4 / 49.4 us against 57.4 / 53.8 /
@@ -762,10 +789,12 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             for (int j = 0; j < nrow; ++j, yd += 1.0, orow += p.dst_pitch) {
                 float v[kCols];
                 bool done = false;
-                if constexpr (PATCH) if (shx != 0) {
+                if constexpr (PATCH) if (shx_t != 0) {
                     // ------------------- the patch path (see RowPatch) -------------------
                     const uint4 inf = *reinterpret_cast<const uint4 *>(&prow[j].info);
-                    if ((inf.x & 0xfu) == 0xfu) {
+                    // bits 0..3: verified with the tile's x binade; bits 4..7: verified with the
+                    // x binade taken per pixel (rows crossing a power of two in x)
+                    if ((inf.x & 0xfu) == 0xfu || (inf.x & 0xf0u) == 0xf0u) {
                         const double2 c01 = *reinterpret_cast<const double2 *>(&prow[j].c[0]);
                         const double2 c23 = *reinterpret_cast<const double2 *>(&prow[j].c[2]);
                         const double2 c45 = *reinterpret_cast<const double2 *>(&prow[j].c[4]);
@@ -788,10 +817,21 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                         const double Ky = __hiloint2double(khy, 0);
                         uint32_t accb = 0xffffffffu;
                         // ODD: the tile holds values lerp_fma is not certified for -> SciPy's sum
-                        auto sample4 = [&](auto odd_tag) {
+                        // GENX: the x binade (shift, rounding constant, masks) from each pixel's own
+                        // exponent instead of the tile's: 8 more integer operations per pixel
+                        auto sample4 = [&](auto odd_tag, auto genx_tag) {
                             constexpr bool ODD = decltype(odd_tag)::value;
+                            constexpr bool GENX = decltype(genx_tag)::value;
 #pragma unroll
                             for (int k = 0; k < kCols; ++k) {
+                                const uint32_t hx = (uint32_t)__double2hiint(xq[k]);
+                                const int shx = GENX ? 1046 - (int)(hx >> 20) : shx_t;
+                                const uint32_t mhx = GENX ? (hx & 0x7ff00000u) + 0x01d80000u : box.mhi_x;
+                                const uint32_t mkx = GENX ? (1u << shx) - 1u : mkx_t;
+                                const uint32_t e32x = GENX ? (uint32_t)(150 - shx) << 23 : e32x_t;
+                                const int khx = (int)mhx - 0x80000;
+                                const double Mx = __hiloint2double((int)mhx, 0);
+                                const double Kx = __hiloint2double(khx, 0);
                                 // round to the float32 grid: the low word is the coordinate in ulp32
                                 const uint32_t nx = (uint32_t)__double2loint(__dadd_rn(xq[k], Mx));
                                 const uint32_t ny = (uint32_t)__double2loint(__dadd_rn(yq[k], My));
@@ -839,10 +879,17 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                                 v[k] = __double2float_rn(sd);
                             }
                         };
-                        if (tile_odd)
-                            sample4(std::true_type{});
-                        else
-                            sample4(std::false_type{});
+                        if ((inf.x & 0xfu) == 0xfu) {
+                            if (tile_odd)
+                                sample4(std::true_type{}, std::false_type{});
+                            else
+                                sample4(std::false_type{}, std::false_type{});
+                        } else {
+                            if (tile_odd)
+                                sample4(std::true_type{}, std::true_type{});
+                            else
+                                sample4(std::false_type{}, std::true_type{});
+                        }
                         // (a blend within 32 ulp64 of a rounding boundary: the exact row below)
                         done = !__any_sync(0xffffffffu, accb < kBlendCertLim);
                         n_bfail += done ? 0u : 1u;
@@ -925,15 +972,20 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                                                               p.yorg, p.ylast, p.rint);
                 }
                 }
-                if (full_w) {
+                if (FULL) {
 #pragma unroll
-                    for (int k = 0; k < kCols; ++k) __stcs(orow + 32 * k, v[k]);
+                    for (int k = 0; k < kCols; ++k) DCB_IMG_STORE(orow + 32 * k, v[k]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < kCols; ++k)
-                        if (x_base + 32 * k <= wmax) __stcs(orow + 32 * k, v[k]);
+                        if (x_base + 32 * k <= wmax) DCB_IMG_STORE(orow + 32 * k, v[k]);
                 }
             }
+            };
+            if (full_w)
+                tile_rows(std::true_type{});
+            else
+                tile_rows(std::false_type{});
             if (n_bfail != 0 && p.stats != nullptr && lane == 0)
                 atomicAdd(p.stats + 3, (unsigned long long)n_bfail);
             if (tile_odd && p.stats != nullptr && threadIdx.x == 0) atomicAdd(p.stats + 4, 1ull);
@@ -941,19 +993,6 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         // this warp is done with buffer i&1 (and with its plan record)
         __syncwarp();
         if (lane == 0) mbar_arrive(&data_empty[i & 1]);
-        // next tile of this CTA
-        if (i + 1 < n) {
-            const int tn = tile_of(i + 1);
-            const int txn = tn / p.tiles_y;
-            tyi = tn - txn * p.tiles_y;
-            if (txn != txi) {
-                txi = txn;
-                int xs[kCols];
-#pragma unroll
-                for (int k = 0; k < kCols; ++k) xs[k] = min(txi * kTileW + lane + 32 * k, wmax);
-                ev.set_columns(p, xs);
-            }
-        }
     }
 }
 
