@@ -480,9 +480,12 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
         need_h = std::min<long long>(need_h, src_rows);
         bw = (int)((need_w + 3) / 4 * 4);
         bh = (int)need_h;
-        // 5 stages + tail, x 2 CTAs (each + 1 KB reserved) within the SM's 228 KB
+        // 5 stages (fp64 blends: one raw + two float64 tiles) or 4 raw stages + tail, x 2 CTAs
+        // (each + 1 KB reserved) within the SM's 228 KB
+        const int nst = sel.wide ? 5 : kRawStages;
         const int max_stage =
-            TH >= 32 ? (int)((116736 - 1024 - image_tail_bytes(TH, true)) / 5 / 128 * 128) : 14 * 1024;
+            TH >= 32 ? (int)((116736 - 1024 - image_tail_bytes(TH, sel.wide)) / nst / 128 * 128)
+                     : 14 * 1024;
         if (bw > 256 || bh > 256 || (long long)bw * bh * 4 > max_stage) {
             // strong magnification somewhere: stage a modest box, tiles whose
             // probes do not fit are gathered straight from global memory
@@ -533,7 +536,7 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
     p.bh = bh;
     p.box_bytes = (unsigned)(bw * bh * 4);
     p.stage_bytes = (p.box_bytes + 127u) / 128u * 128u;
-    const size_t smem = (size_t)(sel.wide ? 5 : 2) * p.stage_bytes + image_tail_bytes(TH, sel.wide);
+    const size_t smem = (size_t)(sel.wide ? 5 : kRawStages) * p.stage_bytes + image_tail_bytes(TH, sel.wide);
     if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute((const void *)sel.kern,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

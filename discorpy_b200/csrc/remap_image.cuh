@@ -556,20 +556,21 @@ struct ImageParams;
 __device__ __forceinline__ bool widen_part(const ImageParams &p, unsigned char *smem, int buf,
                                            int part, int lane);
 
+constexpr int kRawStages = 4;     // !WIDE: raw float32 stages = tile buffers
 constexpr int kRecRing = 3;       // WIDE: plan records in flight (tiles j-1, j being sampled, j+1 landing)
 constexpr int kImgProducers = 2;                             // producer warps
 constexpr int kImgThreads = kThreads + 32 * kImgProducers;   // 8 sampling warps + the producers
 
 // Shared-memory layout (host side must agree, see plan_and_launch_image in api.cu):
 //   WIDE : [raw][wide 0][wide 1][tail]      raw = stage_bytes, wide = 2 * stage_bytes
-//   !WIDE: [raw 0][raw 1][tail]
-//   tail : uint64_t raw_full[2], data_full[2], data_empty[2]; uint32_t odd[4] (tile buffer holds
-//          values the certified blend does not cover); TilePlan<TH> rec[WIDE ? kRecRing : 2]
+//   !WIDE: [raw 0] .. [raw 3][tail]
+//   tail : uint64_t raw_full[4], data_empty[4], data_full[2]; uint32_t odd[4] (tile buffer holds
+//          values the certified blend does not cover); TilePlan<TH> rec[WIDE ? kRecRing : 4]
 __host__ __device__ constexpr size_t image_rec_bytes(int th) {
     return sizeof(TileBox) + (size_t)th * sizeof(RowPatch);
 }
 __host__ __device__ constexpr size_t image_tail_bytes(int th, bool wide) {
-    return 48 + 16 + (wide ? kRecRing : 2) * image_rec_bytes(th);
+    return 96 + (wide ? kRecRing : kRawStages) * image_rec_bytes(th);
 }
 
 // 1-D bulk copy global -> shared, completion on an mbarrier (16-byte aligned, size % 16 == 0)
@@ -603,15 +604,18 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     constexpr bool WIDE = ImageKernelTraits<ORDER, BLEND>::kWide;
     constexpr bool PATCH = (MAP == MAP_RADIAL) && kImgBoxW > 0;   // the patch path exists
     constexpr int RPW = TH / kWarps;  // rows per sampling warp and tile
-    constexpr int NREC = WIDE ? kRecRing : 2;
+    constexpr int NBUF = WIDE ? 2 : kRawStages;   // tile buffers the samplers read from
+    constexpr int LOGB = WIDE ? 1 : 2;
+    static_assert((1 << LOGB) == NBUF, "buffer count");
+    constexpr int NREC = WIDE ? kRecRing : NBUF;
     constexpr uint32_t kRecBytes = (uint32_t)sizeof(TilePlan<TH>);
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *tail = smem + (WIDE ? 5 : 2) * (size_t)p.stage_bytes;
-    uint64_t *raw_full = reinterpret_cast<uint64_t *>(tail);         // [2] TMA bytes landed
-    uint64_t *data_full = raw_full + 2;                              // [2] WIDE: float64 tile ready
-    uint64_t *data_empty = raw_full + 4;                             // [2] tile buffer released
-    uint32_t *odd = reinterpret_cast<uint32_t *>(tail + 48);         // [2] see widen_part
-    TilePlan<TH> *rec = reinterpret_cast<TilePlan<TH> *>(tail + 64); // [NREC]
+    unsigned char *tail = smem + (WIDE ? 5 : kRawStages) * (size_t)p.stage_bytes;
+    uint64_t *raw_full = reinterpret_cast<uint64_t *>(tail);         // [4] TMA bytes landed
+    uint64_t *data_empty = raw_full + 4;                             // [4] tile buffer released
+    uint64_t *data_full = raw_full + 8;                              // [2] WIDE: float64 tile ready
+    uint32_t *odd = reinterpret_cast<uint32_t *>(tail + 80);         // [2] see widen_part
+    TilePlan<TH> *rec = reinterpret_cast<TilePlan<TH> *>(tail + 96); // [NREC]
     const TilePlan<TH> *plan = reinterpret_cast<const TilePlan<TH> *>(p.plan);
 
     const int lane = threadIdx.x & 31;
@@ -637,10 +641,12 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     auto tile_of = [&](int k) -> int { return t0 + k * tstep; };   // local tile k -> tile index
 
     if (threadIdx.x == 0) {
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             mbar_init(&raw_full[b], 1);
-            mbar_init(&data_full[b], 1);
             mbar_init(&data_empty[b], kWarps);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&data_full[b], 1);
             odd[b] = 0;
         }
         fence_mbar_init();
@@ -703,11 +709,13 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                 }
             }
         } else {
-            // raw stage k&1 doubles as the data buffer: the samplers wait on raw_full[k&1];
-            // the producer runs at most two tiles ahead of the slowest sampling warp
+            // raw stage k % 4 doubles as the data buffer: the samplers wait on raw_full[k % 4];
+            // the producer runs at most four tiles ahead of the slowest sampling warp (with two
+            // stages the samplers waited 11 % of their time for copies issued only one tile
+            // earlier, profiles/r2/ncu_img_r2h_lerp32.txt)
             for (int k = 0; k < n; ++k) {
-                const int b = k & 1;
-                if (k >= 2) mbar_wait(&data_empty[b], (uint32_t)((k >> 1) - 1) & 1u);
+                const int b = k & (NBUF - 1);
+                if (k >= NBUF) mbar_wait(&data_empty[b], (uint32_t)((k >> LOGB) - 1) & 1u);
                 if (lane == 0) issue(k, b, b);
             }
         }
@@ -729,7 +737,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
 
     for (int i = 0; i < n; ++i) {
         // tile i is ready: WIDE -> float64 tile i&1 written by the producer; !WIDE -> raw stage landed
-        mbar_wait(WIDE ? &data_full[i & 1] : &raw_full[i & 1], (uint32_t)(i >> 1) & 1u);
+        mbar_wait(WIDE ? &data_full[i & 1] : &raw_full[i & (NBUF - 1)], (uint32_t)(i >> LOGB) & 1u);
         const TilePlan<TH> &trec = rec[i % NREC];
         const TileBox box = trec.box;
         const int tyi = box.pad[1];
@@ -751,7 +759,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             const int lim_x = box.use ? min(p.bw - 1, wmax - box.bx0) : 0;
             const int lim_y = box.use ? min(p.bh - 1, p.ylast - box.by0) : 0;
             const int bw = kImgBoxW > 0 ? kImgBoxW : p.bw;
-            const int sb = i & 1;
+            const int sb = i & (NBUF - 1);
             const float *rawt =
                 reinterpret_cast<const float *>(smem + (size_t)sb * p.stage_bytes);
             const double *widet = reinterpret_cast<const double *>(
@@ -992,7 +1000,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         }
         // this warp is done with buffer i&1 (and with its plan record)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&data_empty[i & 1]);
+        if (lane == 0) mbar_arrive(&data_empty[i & (NBUF - 1)]);
     }
 }
 

@@ -427,3 +427,65 @@ def test_synthetic_fill_matches_host_restatement():
     arr = dcb.DeviceArray((64, 256)).fill_synthetic(seed=4, offset=1000)
     got = arr.to_host().ravel()
     assert np.array_equal(got, synthetic_host(64 * 256, 4, 1000))
+
+
+def test_patch_path_equals_exact_path_and_plans_are_cached():
+    """The single-image kernel's plan (csrc/remap_image.cuh: verified row patches) is built once
+    per (model, geometry) and reused; the patch path must give the very bytes of the exact path
+    (DCB_IMG_FAST=0 switches it off) for every blend and order, on a geometry where most rows
+    are verified and on one where few are."""
+    import os
+    rng = np.random.default_rng(77)
+    for shape, xc, yc, fact in (((1000, 1408), 700.3, 512.9, FACT5),
+                                ((700, 900), 120.7, 655.1, [1.0, 3e-4, -2e-7])):
+        mat = dcb.DeviceArray.from_host(rng.random(shape, dtype=np.float32) * 100.0)
+        for order, blend in ((1, dcb.BLEND_EXACT), (1, dcb.BLEND_LERP64), (1, dcb.BLEND_LERP32),
+                             (0, dcb.BLEND_EXACT)):
+            post.config["blend"] = blend
+            try:
+                dcb.plan_cache_clear()
+                built0 = dcb.plan_cache_clear()
+                dcb.image_stats(True, reset=True)
+                cold = post.unwarp_image_backward(mat, xc, yc, fact, order=order).to_host()
+                st = dcb.image_stats(False, reset=True)
+                before = dcb.launch_count()
+                warm = post.unwarp_image_backward(mat, xc, yc, fact, order=order).to_host()
+                assert dcb.launch_count() == before + 1
+                assert dcb.plan_cache_clear() == built0 + 1          # one build, reused
+                os.environ["DCB_IMG_FAST"] = "0"
+                try:
+                    exact = post.unwarp_image_backward(mat, xc, yc, fact, order=order).to_host()
+                finally:
+                    del os.environ["DCB_IMG_FAST"]
+            finally:
+                post.config["blend"] = dcb.BLEND_EXACT
+            assert np.array_equal(cold, warm)
+            if blend != dcb.BLEND_LERP32:          # lerp32: same coordinates, float32 blend differs
+                assert np.array_equal(cold, exact), (shape, order, blend)
+            else:
+                assert np.max(np.abs(cold - exact)) <= 1e-5 * 100.0
+            assert st["rows"] == shape[0]
+    # the first geometry is mostly verified rows
+    dcb.plan_cache_clear()
+    dcb.image_stats(True, reset=True)
+    post.unwarp_image_backward(dcb.DeviceArray.from_host(rng.random((1000, 1408), dtype=np.float32)),
+                               700.3, 512.9, FACT5)
+    st = dcb.image_stats(False, reset=True)
+    assert st["rows_patch"] > 0.8 * st["rows"] * (1408 // 128), st
+
+
+def test_patch_path_with_odd_values_in_the_image():
+    """Negative values, Inf, NaN, zeros and tiny magnitudes switch single tiles to SciPy's own
+    summation inside the patch path; bytes must equal the oracle's (equal NaN positions)."""
+    rng = np.random.default_rng(78)
+    mat = rng.random((640, 1152), dtype=np.float32)
+    mat[100:140, 200:260] *= -1.0
+    mat[300, 500] = np.inf
+    mat[301, 777] = np.nan
+    mat[400:420, :] = 0.0
+    mat[500:520, 100:400] *= 1e-38
+    want = orc.unwarp_image_backward(mat, 580.2, 318.6, FACT5)
+    got = post.unwarp_image_backward(mat, 580.2, 318.6, FACT5)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(got[ok], want[ok])
