@@ -119,6 +119,15 @@ SIGNATURES = {
     "dcb_last_plan": [ctypes.POINTER(_i)] * 5,
     "dcb_image_stats": [_i, ctypes.POINTER(_u64), _i],
     "dcb_plan_cache_clear": [ctypes.POINTER(_u64)],
+    "dcb_mg_unique_id": [_vp, ctypes.POINTER(_i)],
+    "dcb_mg_init": [_vp, _i, _i],
+    "dcb_mg_info": [ctypes.POINTER(_i), ctypes.POINTER(_i)],
+    "dcb_mg_bcast": [_vp, _sz, _i, _vp],
+    "dcb_mg_bcast_host": [_vp, _sz, _i],
+    "dcb_mg_allgather": [_vp, _vp, _sz, _vp],
+    "dcb_mg_allreduce_max_f64": [ctypes.POINTER(ctypes.c_double), _i],
+    "dcb_mg_barrier": [],
+    "dcb_mg_finalize": [],
     "dcb_selftest_sqrt": [_sz, _u64, ctypes.POINTER(_u64)],
     "dcb_selftest_sqrt_fast": [_sz, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_u64)],
     "dcb_selftest_tma": [_vp, _i, _i, _i, _sz, _sz, _i, _i, _i, _i, _i, _vp,

@@ -1,0 +1,26 @@
+// api_common.hpp -- error plumbing shared by the translation units of libdiscorpy_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/discorpy_b200.h"
+
+namespace dcb {
+// records a printf-style message for dcb_last_error() on this thread and returns `code`
+int fail(int code, const char *fmt, ...);
+// adds n to the launch counter behind dcb_launch_count()
+void count_launches(int n);
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda), or NULL
+void *tma_encode_fn();
+}  // namespace dcb
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return dcb::fail(DCB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                           \
+    } while (0)
+
+#define REQUIRE(cond, ...)                                   \
+    do {                                                     \
+        if (!(cond)) return dcb::fail(DCB_ERR_ARG, __VA_ARGS__); \
+    } while (0)

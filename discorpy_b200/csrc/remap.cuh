@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------
 // synthetic input generator (bench only): splitmix64 counter hash -> [0,1)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
     fill_synthetic_kernel(float *__restrict__ dst, size_t n, uint64_t seed, uint64_t offset) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x) {

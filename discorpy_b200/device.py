@@ -31,6 +31,10 @@ def _default_device():
 def set_device(index):
     """Bind the calling thread (and by default later threads) to a GPU."""
     _cabi.call("dcb_init", int(index))
+    if getattr(_state, "device", None) != int(index):
+        # the per-thread stream belongs to the device it was created on
+        _state.streams = getattr(_state, "streams", {})
+        _state.stream = _state.streams.get(int(index))
     _state.device = int(index)
     with _init_lock:
         _initialised.add(int(index))
@@ -100,7 +104,7 @@ class DeviceBuffer:
     """Owning handle of ``nbytes`` of device memory."""
 
     def __init__(self, nbytes):
-        ensure_init()
+        self.device = ensure_init()
         ptr = ctypes.c_void_p()
         _cabi.call("dcb_malloc", ctypes.byref(ptr), int(nbytes))
         self.ptr = ptr.value
@@ -118,11 +122,22 @@ class DeviceBuffer:
             pass
 
 
-class _Pool:
-    """Size-bucketed free list; avoids a cudaMalloc/cudaFree per call."""
+def _pool_key():
+    """Buffers are recycled only on the device they were allocated on."""
+    return getattr(_state, "device", None)
 
-    def __init__(self, factory, max_bytes):
+
+class _Pool:
+    """Size-bucketed free list per device; avoids a cudaMalloc/cudaFree per call.
+
+    A buffer handed back may still be read or written by work queued on the stream of the thread
+    that used it; before it goes to another thread (another stream) the pool drains the device
+    (``sync`` hook), same-thread reuse is ordered by the stream itself."""
+
+    def __init__(self, factory, max_bytes, keyfn=lambda: None, sync=None):
         self._factory = factory
+        self._keyfn = keyfn
+        self._sync = sync
         self._free = {}
         self._held = 0
         self._max = max_bytes
@@ -138,25 +153,34 @@ class _Pool:
 
     def take(self, nbytes):
         b = self._bucket(nbytes)
+        key = (self._keyfn(), b)
+        me = threading.get_ident()
+        got = None
         with self._lock:
-            lst = self._free.get(b)
+            lst = self._free.get(key)
             if lst:
                 self._held -= b
-                return lst.pop()
-        return self._factory(b)
+                got = lst.pop()
+        if got is None:
+            return self._factory(b)
+        buf, owner = got
+        if owner != me and self._sync is not None:
+            self._sync()        # another thread's stream may still be using it
+        return buf
 
     def give(self, buf):
         b = buf.nbytes
+        key = (getattr(buf, "device", None), b)
         with self._lock:
             if self._held + b <= self._max:
-                self._free.setdefault(b, []).append(buf)
+                self._free.setdefault(key, []).append((buf, threading.get_ident()))
                 self._held += b
                 return
         buf.free()
 
     def clear(self):
         with self._lock:
-            bufs = [b for lst in self._free.values() for b in lst]
+            bufs = [b for lst in self._free.values() for b, _ in lst]
             self._free.clear()
             self._held = 0
         for b in bufs:
@@ -164,7 +188,8 @@ class _Pool:
 
 
 _pool_bytes = int(os.environ.get("DCB_POOL_BYTES", str(8 << 30)))
-device_pool = _Pool(DeviceBuffer, _pool_bytes)
+device_pool = _Pool(DeviceBuffer, _pool_bytes, keyfn=_pool_key,
+                    sync=lambda: _cabi.call("dcb_device_sync"))
 
 
 class borrowed:
@@ -297,6 +322,10 @@ def current_stream():
     s = getattr(_state, "stream", None)
     if s is None:
         s = _state.stream = Stream()
+        streams = getattr(_state, "streams", None)
+        if streams is None:
+            streams = _state.streams = {}
+        streams[getattr(_state, "device", None)] = s
     return s
 
 
@@ -414,6 +443,28 @@ class DeviceArray:
                        ctypes.c_void_p(stream.handle))
         stream.sync()
         return out
+
+    def fill(self, value=0.0, stream=None):
+        """Set every byte to zero (the only fill the path needs: padding of uneven shards)."""
+        if value != 0:
+            raise ValueError("DeviceArray.fill supports 0 only")
+        stream = stream or current_stream()
+        _cabi.call("dcb_memset", ctypes.c_void_p(self.ptr), 0, self.nbytes,
+                   ctypes.c_void_p(stream.handle))
+        return self
+
+    def copy_rows_from(self, src, src_row, nrows, dst_row=0, stream=None):
+        """Device-to-device copy of ``nrows`` rows of the 2-D array ``src`` (same width and
+        pitch) starting at ``src_row`` into rows ``dst_row...`` of this 2-D array."""
+        if self.ndim != 2 or src.ndim != 2 or src.shape[1] != self.shape[1] or src.pitch != self.pitch:
+            raise ValueError("copy_rows_from needs two 2-D arrays of equal width and pitch")
+        if src_row < 0 or dst_row < 0 or src_row + nrows > src.shape[0] or dst_row + nrows > self.shape[0]:
+            raise ValueError("row range outside the arrays")
+        stream = stream or current_stream()
+        _cabi.call("dcb_d2d", ctypes.c_void_p(self.ptr + dst_row * self.pitch),
+                   ctypes.c_void_p(src.ptr + src_row * src.pitch), nrows * self.pitch,
+                   ctypes.c_void_p(stream.handle))
+        return self
 
     def fill_synthetic(self, seed, offset=0, stream=None):
         """Fill with the stateless splitmix64 stream (bench inputs)."""

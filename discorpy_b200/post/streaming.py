@@ -134,6 +134,9 @@ def unwarp_chunk_slices_backward_stream(mat3D, xcenter, ycenter, list_fact,
     pitch_in = _dev._pitch_for(width)
     dense = pitch_in == width * 4
     in_pin = out_pin = None
+    # the pooled buffers below are used on three private streams: anything the calling thread
+    # queued earlier on its own stream against a buffer the pool hands back must have finished
+    _dev.current_stream().sync()
     d_in = [_dev.DeviceArray((nb, wrows, width)) for _ in range(2)]
     d_out = [_dev.DeviceArray((nb, nrows, width)) for _ in range(2)]
     ev_up = [_dev.Event() for _ in range(2)]       # block uploaded

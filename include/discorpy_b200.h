@@ -292,6 +292,34 @@ int dcb_launch_count_reset(void);
  * shared memory bytes. */
 int dcb_last_plan(int *path, int *box_w, int *box_h, int *grid, int *smem_bytes);
 
+/* ---- multi-GPU plumbing: one process per GPU, NCCL (csrc/mg.cu) --------------------------
+ * The path shards without a data-plane collective (every slice / image is independent); the
+ * ranks exchange the parameter block (one broadcast; reference: the scalars every call of
+ * postprocessing.py:111, :188, :255 takes), optionally the rows of one assembled sinogram
+ * (postprocessing.py:224-229 on a sharded stack), and benchmark scalars.  NCCL is loaded at run
+ * time (libnccl.so.2, or $DCB_NCCL_LIB); DCB_ERR_UNSUPPORTED when it cannot be found.
+ *   dcb_mg_unique_id  rank 0: a fresh NCCL unique id (128 bytes) to hand to the other ranks by
+ *                     whatever the launcher offers (discorpy_b200/multigpu.py: a TCP exchange
+ *                     on MASTER_ADDR); *nccl_version, when not NULL, the library version
+ *   dcb_mg_init       every rank, after dcb_init(local device): ncclCommInitRank
+ *   dcb_mg_bcast      device buffer, asynchronous on `stream`
+ *   dcb_mg_bcast_host <= 4096 host bytes, synchronous (the parameter block)
+ *   dcb_mg_allgather  nbytes_per_rank from every rank, rank order, asynchronous on `stream`
+ *   dcb_mg_allreduce_max_f64  up to 8 host doubles, in place, synchronous (max over ranks of a
+ *                     device-timed duration)
+ *   dcb_mg_barrier    device idle on every rank (cudaDeviceSynchronize + a 1-element all-reduce)
+ *   dcb_mg_finalize   destroys the communicator */
+#define DCB_MG_UNIQUE_ID_BYTES 128
+int dcb_mg_unique_id(void *id_out, int *nccl_version);
+int dcb_mg_init(const void *id, int world, int rank);
+int dcb_mg_info(int *world, int *rank);
+int dcb_mg_bcast(void *dev_buf, size_t nbytes, int root, void *stream);
+int dcb_mg_bcast_host(void *host_buf, size_t nbytes, int root);
+int dcb_mg_allgather(const void *send_dev, void *recv_dev, size_t nbytes_per_rank, void *stream);
+int dcb_mg_allreduce_max_f64(double *host_values, int count);
+int dcb_mg_barrier(void);
+int dcb_mg_finalize(void);
+
 /* Drops every cached plan of the single-image kernel (per-tile staged boxes and verified row
  * patches, built once per (model, geometry) and reused for later frames; csrc/remap_image.cuh,
  * csrc/api.cu "Plan cache") on all devices; *plans_built, when not NULL, receives the number of

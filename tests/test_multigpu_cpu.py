@@ -1,7 +1,8 @@
-"""N > 1 host logic on CPU: two gloo ranks broadcast the coefficient block, shard a
-stack and run the collective form of the optional sinogram exchange:
-gather_rows with uneven shards, broadcast_bytes (the IPC-handle exchange of the fused
-form; the peer mapping itself needs two GPUs: tests/two_rank_sinogram_check.py)."""
+"""N > 1 host logic on CPU: two gloo ranks (tests/gloo_comm.py stands in for the NCCL
+communicator of the C ABI) broadcast the coefficient block, shard a stack and run the
+collective form of the optional sinogram exchange: gather_rows with uneven
+shards, broadcast_bytes (the IPC-handle exchange of the fused form; the peer mapping itself
+needs two GPUs: tests/two_rank_sinogram_check.py), and the unique-id rendezvous of NcclComm."""
 import os
 import socket
 import subprocess
@@ -43,11 +44,12 @@ def test_param_block_roundtrip():
 WORKER = r"""
 import os, sys, json
 sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
 import numpy as np
-import torch.distributed as dist
 from discorpy_b200 import multigpu
-dist.init_process_group("gloo")
-rank, world = dist.get_rank(), dist.get_world_size()
+from gloo_comm import GlooComm
+comm = multigpu.set_default_comm(GlooComm())
+rank, world = comm.rank, comm.world
 params = dict(xcenter=1283.4, ycenter=1275.9,
               list_fact=[1.0, -2e-5, 6e-8, -1e-10, 5e-14]) if rank == 0 else None
 got = multigpu.broadcast_params(params, src=0)
@@ -63,11 +65,12 @@ except ValueError:
     pass
 blob = multigpu.broadcast_bytes(bytes(range(72)) if rank == 1 else b"", 72, src=1)
 assert blob == bytes(range(72))
+assert comm.allreduce_max([float(rank), 5.0 - rank]) == [float(world - 1), 5.0]
 # one file per rank: two ranks writing to the shared stdout pipe can interleave
 with open(os.path.join(%(out)r, "rank%%d.json" %% rank), "w") as f:
     json.dump(dict(rank=rank, world=world, params=got, shard=[lo, hi]), f)
-dist.barrier()
-dist.destroy_process_group()
+comm.barrier()
+comm.close()
 """
 
 
@@ -100,3 +103,32 @@ def test_two_gloo_ranks_broadcast_and_shard(tmp_path):
         assert r["params"] == want        # bit-identical on every rank
     shards = sorted(tuple(r["shard"]) for r in rows)
     assert shards == [(0, 6), (6, 11)]
+
+
+def test_unique_id_rendezvous_over_tcp():
+    """NcclComm.from_env hands the 128-byte NCCL unique id from rank 0 to the others over a TCP
+    connection on MASTER_ADDR; here three 'ranks' as threads with a fake id maker."""
+    import threading
+    port = _free_port()
+    uid = bytes(range(128))
+    got = {}
+
+    def run(rank):
+        got[rank] = multigpu._exchange_unique_id(rank, 3, lambda: uid, "127.0.0.1", port, timeout=30)
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in (2, 1, 0)]   # clients first
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    assert got == {0: uid, 1: uid, 2: uid}
+
+
+def test_package_does_not_import_torch():
+    import re
+    pkg = os.path.join(ROOT, "discorpy_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith(".py"):
+                text = open(os.path.join(dirpath, name)).read()
+                assert not re.search(r"^\s*(import|from)\s+torch", text, re.M), name

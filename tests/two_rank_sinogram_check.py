@@ -1,4 +1,5 @@
-"""Sinogram exchange over N ranks, run under torchrun with one rank per GPU:
+"""Sinogram exchange over N ranks, run under torchrun (used as a launcher only: the
+collectives are NCCL through the C ABI, discorpy_b200.multigpu.NcclComm) with one rank per GPU:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29611 tests/two_rank_sinogram_check.py [--depth 257] [--size 2560] [--time]
@@ -18,8 +19,6 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-import torch
-import torch.distributed as dist
 
 import discorpy_b200 as dcb
 from discorpy_b200 import multigpu
@@ -35,11 +34,8 @@ ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--no-check", action="store_true", help="timing only (large stacks: no host copy for the oracle)")
 args = ap.parse_args()
 
-local = int(os.environ.get("LOCAL_RANK", 0))
-torch.cuda.set_device(local)
-dcb.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-rank, world = dist.get_rank(), dist.get_world_size()
+comm = multigpu.NcclComm.from_env()          # binds LOCAL_RANK's device, NCCL through the C ABI
+rank, world = comm.rank, comm.world
 
 D, H, W = args.depth, args.size, args.size
 params = multigpu.broadcast_params(
@@ -61,37 +57,34 @@ for index in indices:
     multigpu.unwarp_slice_backward_sharded(shard, params, index, window)
     window.fence()
     # collective: local rows, then an NCCL all-gather
-    rows = torch.empty((hi - lo, W), dtype=torch.float32, device="cuda")
+    rows = DeviceArray((hi - lo, W))
     post._unwarp_slice_into(shard, params["xcenter"], params["ycenter"], params["list_fact"], index,
-                            multigpu._Rows(rows.data_ptr(), W * 4, rows.shape))
-    dcb.current_stream().sync()
+                            multigpu._Rows(rows.ptr, rows.pitch, rows.shape))
     gathered = multigpu.gather_rows(rows, D)
     if rank == 0:
         want = oracle_np.unwarp_slice_backward(full_host, params["xcenter"], params["ycenter"],
                                                params["list_fact"], index)
         fused = window.array.to_host()
-        coll = gathered.cpu().numpy()
+        coll = gathered.to_host()
         report["cases"].append(dict(index=index,
                                     fused_mismatches=int(np.count_nonzero(fused != want)),
                                     collective_mismatches=int(np.count_nonzero(coll != want))))
-    dist.barrier()
+    comm.barrier()
 
 
 def timed(fn, reps):
     fn()
-    torch.cuda.synchronize(); dist.barrier()
+    comm.barrier()
     t0 = time.perf_counter()
     for _ in range(reps):
         fn()
-    torch.cuda.synchronize(); dist.barrier()
-    t = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item()) * 1e3
+    comm.barrier()
+    return comm.allreduce_max([(time.perf_counter() - t0) / reps])[0] * 1e3
 
 
 if args.time:
     index = H // 2
-    rows = torch.empty((hi - lo, W), dtype=torch.float32, device="cuda")
+    rows = DeviceArray((hi - lo, W))
 
     def fused():
         multigpu.unwarp_slice_backward_sharded(shard, params, index, window)
@@ -99,14 +92,13 @@ if args.time:
 
     def collective():
         post._unwarp_slice_into(shard, params["xcenter"], params["ycenter"], params["list_fact"],
-                                index, multigpu._Rows(rows.data_ptr(), W * 4, rows.shape))
-        dcb.current_stream().sync()
+                                index, multigpu._Rows(rows.ptr, rows.pitch, rows.shape))
         multigpu.gather_rows(rows, D)
-        torch.cuda.synchronize()
+        dcb.current_stream().sync()
 
     def local_only():
         post._unwarp_slice_into(shard, params["xcenter"], params["ycenter"], params["list_fact"],
-                                index, multigpu._Rows(rows.data_ptr(), W * 4, rows.shape))
+                                index, multigpu._Rows(rows.ptr, rows.pitch, rows.shape))
         dcb.current_stream().sync()
 
     report["ms"] = dict(fused_peer_stores=timed(fused, args.reps),
@@ -120,5 +112,5 @@ if rank == 0:
     ok = all(c["fused_mismatches"] == 0 and c["collective_mismatches"] == 0 for c in report["cases"])
     report["ok"] = ok
     print(json.dumps(report))
-dist.destroy_process_group()
+comm.close()
 sys.exit(0 if ok else 1)
