@@ -7,7 +7,7 @@ bench.py -- BASELINE.json's metric on BASELINE.json's config.
 Metric : Mpixels/s of backward unwarp, 4096 x 4096 float32, 5-term polynomial,
          order 1 (BASELINE configs[1]), whole job over N GPUs (weak scaling:
          every rank unwarps its own batch of independent images; the only
-         collective is the broadcast of the <=160-byte coefficient block).
+         collective is the broadcast of the <=256-byte coefficient block).
 Step   : one pass of the hot path over one batch of IMAGES_PER_STEP distinct
          synthetic images per GPU (each its own kernel launch through the C
          ABI).  The batch is 2 x IMAGES_PER_STEP x 64 MiB >> the 126 MB L2, so
@@ -18,17 +18,26 @@ e2e    : the same metric through the public Python API
          dcb_unwarp_image_backward_host_f32) with host buffers: per image a
          64 MiB host->device copy from pinned memory, the kernel, and a 64 MiB
          device->host copy of the result, all inside the timed region (the
-         library pipelines the three in row bands).
-extras : secondary device-timed figures that explain the headline: the other
-         blend modes of the single-image kernel and the Z-stack kernel on the
-         same 4096^2 geometry (geometry evaluated once per tile and reused for
-         every slice -- the path unwarp_chunk_slices_backward takes).
+         library pipelines the three in row bands).  `e2e_pageable` is the same
+         call with ordinary (pageable) NumPy arrays in and out -- what a drop-in
+         caller passes; `pcie` holds the copy rates measured on the spot.
+extras : secondary device-timed figures: the other blend modes of the
+         single-image kernel, the Z-stack kernel on the same 4096^2 geometry,
+         config 3 (2048^2 radial -> perspective), and on every N the two
+         sharded workloads north_star names -- config 4 (2048 x 2560^2 stack,
+         slice semantics, Z-sharded: strong scaling) and config 5 (64 x 8192^2,
+         9 terms, 64/N images per rank) -- each with an on-device parity spot
+         check against the oracle.  For N > 1 `exchange` runs the one optional
+         exchange step (one sinogram assembled from all ranks) in its fused
+         (peer stores) and collective (NCCL all-gather) forms against the oracle.
 --impl reference : the reference's own CPU code path (NumPy float64
          coordinate temporaries + scipy.ndimage.map_coordinates, restated in
          oracle/oracle_np.py because /root/reference does not travel to the GPU
          box), split over row blocks on all host cores; one image per step.
 
-PyTorch is used only for torch.distributed plumbing when N > 1.
+No PyTorch: for N > 1 the launcher's environment (RANK, LOCAL_RANK, WORLD_SIZE,
+MASTER_ADDR, MASTER_PORT) is read by discorpy_b200.multigpu.NcclComm, NCCL
+through the C ABI.
 """
 import argparse
 import json
@@ -54,6 +63,15 @@ UNIT = "Mpixels/s"
 WORKLOAD = ("configs[1]: single 4096x4096 fp32 synthetic image, 5-term backward "
             "polynomial, order 1, 1xB200 per rank")
 ALGO_BYTES_PER_PX = 8.0          # read each source pixel once + write each output pixel once
+
+
+def config_dict(blend="exact"):
+    """The `config` object -- identical in both arms so that the driver can compare them."""
+    return {"workload": WORKLOAD, "order": 1, "blend": blend,
+            "l2": "GPU arm: inputs larger than L2 (%d distinct 64 MiB source/destination pairs "
+                  "per step per GPU = %.1f GiB, vs 126 MB L2); reference arm: host CPU only"
+                  % (IMAGES_PER_STEP, 2 * IMAGES_PER_STEP * 64 / 1024.0),
+            "collective": "one broadcast of the coefficient block (NCCL through the C ABI)"}
 
 
 def measured_peak():
@@ -201,7 +219,8 @@ def run_reference_arm(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_step": 1,
+        "config": config_dict(),
+        "detail": {"images_per_step": 1,
                    "note": "host CPU only; N GPUs are not used by the reference"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port",
                          "sample": "%d x one 4096x4096 image, NumPy coordinates + "
@@ -218,20 +237,65 @@ def run_reference_arm(args, rank, world):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+FACT3 = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]                          # SURVEY.md 8d, cfg 3 / 4
+PERS3 = [1.02, 0.01, -15.0, 0.005, 1.01, -8.0, 8e-6, -5e-6]
+FACT9 = [1.0, -1e-5, 3e-8, -2e-11, 5e-15, -8e-19, 6e-23, -2e-27, 3e-32]   # cfg 5
+
+
+def _event_ms(dcb, stream, fn, reps):
+    fn()
+    a, b = dcb.Event(), dcb.Event()
+    a.record(stream)
+    for _ in range(reps):
+        fn()
+    b.record(stream)
+    b.sync()
+    return a.elapsed_ms(b) / reps
+
+
+def pcie_probe(dcb, _cabi, ctypes, nbytes=64 << 20, reps=6):
+    """Pinned host <-> device copy rates on this box: each direction alone and both at once."""
+    h_in = dcb.pinned_empty((nbytes // 4,), np.float32)
+    h_out = dcb.pinned_empty((nbytes // 4,), np.float32)
+    h_in[:] = 1.0
+    d_a, d_b = dcb.DeviceArray((1, nbytes // 4)), dcb.DeviceArray((1, nbytes // 4))
+    s1, s2 = dcb.Stream(), dcb.Stream()
+
+    def h2d(st):
+        _cabi.call("dcb_h2d", ctypes.c_void_p(d_a.ptr), ctypes.c_void_p(h_in.ctypes.data), nbytes,
+                   ctypes.c_void_p(st.handle))
+
+    def d2h(st):
+        _cabi.call("dcb_d2h", ctypes.c_void_p(h_out.ctypes.data), ctypes.c_void_p(d_b.ptr), nbytes,
+                   ctypes.c_void_p(st.handle))
+
+    def wall(fn):
+        fn()
+        dcb.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        dcb.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    t_up = wall(lambda: h2d(s1))
+    t_dn = wall(lambda: d2h(s1))
+    t_both = wall(lambda: (h2d(s1), d2h(s2)))
+    return {"h2d_gbs": nbytes / t_up / 1e9, "d2h_gbs": nbytes / t_dn / 1e9,
+            "duplex_gbs_each_way": nbytes / t_both / 1e9, "bytes_per_copy": nbytes}
+
+
 def run_gpu_arm(args, rank, local_rank, world):
     import ctypes
     import discorpy_b200 as dcb
     from discorpy_b200 import _cabi, multigpu
     import discorpy_b200.post.postprocessing as post
 
-    dist = None
+    comm = None
     if world > 1:
-        import torch
-        import torch.distributed as tdist
-        torch.cuda.set_device(local_rank)
-        tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist = tdist
-    dcb.set_device(local_rank)
+        comm = multigpu.NcclComm.from_env()       # binds LOCAL_RANK's device, ncclCommInitRank
+    else:
+        dcb.set_device(local_rank)
     numa_cores = dcb.bind_host_to_device(local_rank) if world > 1 else None   # before any pinned allocation
     post.config["blend"] = {"exact": dcb.BLEND_EXACT, "lerp64": dcb.BLEND_LERP64,
                             "lerp32": dcb.BLEND_LERP32}[args.blend]
@@ -240,27 +304,18 @@ def run_gpu_arm(args, rank, local_rank, world):
 
     # the one collective of the path: coefficient block from rank 0 (NCCL / NVLink)
     params = dict(xcenter=XC, ycenter=YC, list_fact=FACT) if rank == 0 else None
-    if dist is not None:
-        params = multigpu.broadcast_params(params, src=0)
-    else:
-        params = multigpu.unpack_params(multigpu.pack_params(**params))
+    params = multigpu.broadcast_params(params, src=0, comm=comm)
     xc, yc, fact = params["xcenter"], params["ycenter"], params["list_fact"]
 
     def barrier():
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
+        if comm is not None:
+            comm.barrier()
         dcb.synchronize()
 
     def max_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return x if comm is None else comm.allreduce_max([x])[0]
 
+    peak, peak_kind = measured_peak()
     stream = dcb.current_stream()
     nimg = args.images_per_step
     srcs = [dcb.DeviceArray((H, W)).fill_synthetic(seed=2 + rank, offset=i * H * W)
@@ -277,6 +332,16 @@ def run_gpu_arm(args, rank, local_rank, world):
                     ctypes.byref(model), ctypes.byref(opt), sh)
             if rc != 0:
                 _cabi.check(rc)
+
+    # the very first launch of a (model, geometry) pair also builds its plan (remap_image.cuh):
+    # time that cold call apart, it is not part of the steady-state metric
+    dcb.plan_cache_clear()
+    dcb.synchronize()
+    t0 = time.perf_counter()
+    _cabi.check(fn(ctypes.c_void_p(srcs[0].ptr), ctypes.c_void_p(dsts[0].ptr), H, W, srcs[0].pitch,
+                   dsts[0].pitch, ctypes.byref(model), ctypes.byref(opt), sh))
+    dcb.synchronize()
+    cold_call_us = (time.perf_counter() - t0) * 1e6
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
@@ -300,29 +365,39 @@ def run_gpu_arm(args, rank, local_rank, world):
 
     # ---- end to end through the public API, host buffers ----------------------
     e2e_n = args.e2e_images_per_step
-    host_in = []
-    for i in range(min(e2e_n, 4)):
-        a = dcb.pinned_empty((H, W), np.float32)
-        srcs[i % nimg].to_host(out=a)
-        host_in.append(a)
-    # warm-up in the timed loop's own pattern: one result is still referenced while the next
-    # call runs, so BOTH pinned output blocks the loop alternates between exist before the
-    # clock starts (a cold cudaHostAlloc of 64 MiB takes ~28 ms, tools/e2e_probe.py)
-    out = None
-    for i in range(max(3, args.warmup)):
-        out = post.unwarp_image_backward(host_in[i % len(host_in)], xc, yc, fact)
-    barrier()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    t0 = time.perf_counter()
-    checksum = 0.0
-    for s in range(e2e_steps):
-        for i in range(e2e_n):
-            out = post.unwarp_image_backward(host_in[(s * e2e_n + i) % len(host_in)], xc, yc, fact)
-            checksum += float(out[17, 33])
-    dcb.synchronize()
-    e2e_s_local = time.perf_counter() - t0
-    e2e_s = max_over_ranks(e2e_s_local)
-    barrier()
+    e2e = {}
+    if args.e2e_steps > 0:
+        pinned_in, page_in = [], []
+        for i in range(min(e2e_n, 4)):
+            a = dcb.pinned_empty((H, W), np.float32)
+            srcs[i % nimg].to_host(out=a)
+            pinned_in.append(a)
+            page_in.append(np.array(a))                   # an ordinary (pageable) copy
+
+        def e2e_run(inputs):
+            # warm-up in the timed loop's own pattern: one result is still referenced while the
+            # next call runs, so the output blocks the loop alternates between exist before the
+            # clock starts (a cold cudaHostAlloc of 64 MiB takes ~28 ms, tools/e2e_probe.py)
+            out = None
+            for i in range(max(3, args.warmup)):
+                out = post.unwarp_image_backward(inputs[i % len(inputs)], xc, yc, fact)
+            barrier()
+            t0 = time.perf_counter()
+            checksum = 0.0
+            for s in range(e2e_steps):
+                for i in range(e2e_n):
+                    out = post.unwarp_image_backward(inputs[(s * e2e_n + i) % len(inputs)], xc, yc, fact)
+                    checksum += float(out[17, 33])
+            dcb.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            return world * e2e_n * e2e_steps * (H * W / 1e6) / dt
+
+        e2e["pinned"] = e2e_run(pinned_in)
+        e2e["pageable"] = e2e_run(page_in)
+        del pinned_in, page_in
+    pcie = pcie_probe(dcb, _cabi, ctypes) if (rank == 0 and args.e2e_steps > 0) else None
 
     # ---- secondary device-timed figures (explain the headline, do not replace it) ----
     extras = {}
@@ -333,17 +408,11 @@ def run_gpu_arm(args, rank, local_rank, world):
                 for s_, d_ in zip(srcs, dsts):
                     _cabi.check(fn(ctypes.c_void_p(s_.ptr), ctypes.c_void_p(d_.ptr), H, W, s_.pitch,
                                    d_.pitch, ctypes.byref(model), ctypes.byref(o), sh))
-            once()
-            a, b = dcb.Event(), dcb.Event()
-            a.record(stream)
-            for _ in range(reps):
-                once()
-            b.record(stream)
-            b.sync()
-            return a.elapsed_ms(b) * 1e3 / (reps * nimg)        # us per image
+            return _event_ms(dcb, stream, once, reps) * 1e3 / nimg        # us per image
         extras["single_image_kernel_us"] = {
             "exact": time_images(dcb.BLEND_EXACT), "lerp64": time_images(dcb.BLEND_LERP64),
             "lerp32": time_images(dcb.BLEND_LERP32), "order0": time_images(dcb.BLEND_EXACT, 0)}
+        extras["single_image_cold_call_us"] = cold_call_us
         # the same 4096^2 geometry as a Z-stack of slices sharing the model (a3, the path
         # unwarp_chunk_slices_backward takes): geometry evaluated once per tile
         depth = args.stack_depth
@@ -358,51 +427,45 @@ def run_gpu_arm(args, rank, local_rank, world):
                 _cabi.check(sfn(ctypes.c_void_p(stack.ptr), ctypes.c_void_p(sout.ptr), depth, H, W, 0,
                                 H, stack.pitch, stack.slice_stride, sout.pitch, sout.slice_stride, 0,
                                 H, 1, ctypes.byref(model), ctypes.byref(o), sh))
-            once()
-            a, b = dcb.Event(), dcb.Event()
-            a.record(stream)
-            for _ in range(3):
-                once()
-            b.record(stream)
-            b.sync()
-            stack_us[name] = a.elapsed_ms(b) * 1e3 / (3 * depth)  # us per 4096^2 slice
+            stack_us[name] = _event_ms(dcb, stream, once, 3) * 1e3 / depth   # us per 4096^2 slice
         extras["stack_kernel_us_per_slice"] = stack_us
         extras["stack_depth"] = depth
-        peak_, _ = measured_peak()
         extras["roofline_frac"] = {
-            "single_image": {k: ALGO_BYTES_PER_PX * H * W / (v * 1e-6) / 1e9 / peak_
+            "single_image": {k: ALGO_BYTES_PER_PX * H * W / (v * 1e-6) / 1e9 / peak
                              for k, v in extras["single_image_kernel_us"].items()},
-            "stack": {k: ALGO_BYTES_PER_PX * H * W / (v * 1e-6) / 1e9 / peak_
+            "stack": {k: ALGO_BYTES_PER_PX * H * W / (v * 1e-6) / 1e9 / peak
                       for k, v in stack_us.items()}}
         del stack, sout
+        extras["cfg3"] = bench_cfg3(dcb, _cabi, ctypes, stream, peak)
+    del srcs, dsts
+    dcb.device_pool_clear()
+    if not args.no_extras:
+        extras["cfg4"] = bench_cfg4(dcb, _cabi, ctypes, stream, peak, rank, world, comm, args)
+        dcb.device_pool_clear()
+        extras["cfg5"] = bench_cfg5(dcb, _cabi, ctypes, stream, peak, rank, world, comm, args)
+        dcb.device_pool_clear()
+    exchange = bench_exchange(dcb, multigpu, post, comm, rank, world) if world > 1 else None
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        if comm is not None:
+            comm.close()
         return
 
     mpix_img = H * W / 1e6
     value = world * nimg * args.steps * mpix_img / (ms * 1e-3)
     kernel_s = (ms_local * 1e-3) / (nimg * args.steps)
-    peak, peak_kind = measured_peak()
     achieved = ALGO_BYTES_PER_PX * H * W / kernel_s / 1e9
-    e2e_value = world * e2e_n * e2e_steps * mpix_img / e2e_s
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_step_per_gpu": nimg,
-                   "l2": "inputs larger than L2: %d distinct 64 MiB source/destination pairs "
-                         "per step (%.1f GiB) vs 126 MB L2" % (nimg, 2 * nimg * 64 / 1024.0),
-                   "blend": args.blend, "path": args.path,
-                   "plan": plan, "collective": "one broadcast of the coefficient block"},
+        "config": config_dict(args.blend),
+        "detail": {"images_per_step_per_gpu": nimg, "path": args.path, "plan": plan,
+                   "plan_cache": "per-tile boxes and verified row patches are built once per "
+                                 "(model, geometry) and reused (remap_image.cuh); the cold call "
+                                 "is in extras.single_image_cold_call_us"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": e2e_n * H * W * 4, "d2h_bytes_per_step": e2e_n * H * W * 4,
-                "steps": e2e_steps, "images_per_step_per_gpu": e2e_n,
-                "host_cores_bound_per_rank": len(numa_cores) if numa_cores else None,
-                "api": "discorpy_b200.post.postprocessing.unwarp_image_backward(pinned ndarray)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
@@ -410,10 +473,29 @@ def run_gpu_arm(args, rank, local_rank, world):
                      "peak_kind": peak_kind,
                      "kernel": "remap_image_kernel<RADIAL, order 1, blend %s, 5 terms>" % args.blend,
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * H * W,
-                     "kernel_us": kernel_s * 1e6},
+                     "kernel_us": kernel_s * 1e6,
+                     "colimit": COLIMIT},
     }
+    if e2e:
+        bytes_each_way = e2e_n * H * W * 4
+        line["e2e"] = {"value": e2e["pinned"], "unit": UNIT,
+                       "h2d_bytes_per_step": bytes_each_way, "d2h_bytes_per_step": bytes_each_way,
+                       "steps": e2e_steps, "images_per_step_per_gpu": e2e_n,
+                       "host_cores_bound_per_rank": len(numa_cores) if numa_cores else None,
+                       "api": "discorpy_b200.post.postprocessing.unwarp_image_backward(pinned ndarray)"}
+        line["e2e_pageable"] = {"value": e2e["pageable"], "unit": UNIT,
+                                "api": "the same call with ordinary (pageable) numpy arrays in and out",
+                                "ratio_to_pinned": e2e["pageable"] / e2e["pinned"]}
+        if pcie:
+            # one image = 64 MiB each way; the duplex rate bounds the pipelined call
+            pcie["e2e_gbs_each_way"] = e2e["pinned"] / world * 1e6 * 4 / 1e9
+            pcie["frac"] = pcie["e2e_gbs_each_way"] / pcie["duplex_gbs_each_way"]
+            pcie["bytes_per_step"] = 2 * bytes_each_way
+            line["pcie"] = pcie
     if extras:
         line["extras"] = extras
+    if exchange:
+        line["exchange"] = exchange
     if world == 1 and not args.no_cpu_baseline:
         ref = CpuReference()
         ref.run_once()
@@ -423,23 +505,234 @@ def run_gpu_arm(args, rank, local_rank, world):
             times.append(ref.run_once())
         ref.close()
         best = min(times)
+        one = CpuReference(cores=1)                      # the reference as shipped: one thread
+        t_single = min(one.run_once() for _ in range(2))
+        one.close()
         line["cpu_baseline"] = {
             "value": mpix_img / best, "unit": UNIT, "cores": ref.cores, "kind": "port",
+            "single_process_value": mpix_img / t_single,
             "sample": "%d x one 4096x4096 image (best taken), NumPy coordinates + "
-                      "scipy.ndimage.map_coordinates over %d row blocks in a %d-process pool; %s"
+                      "scipy.ndimage.map_coordinates over %d row blocks in a %d-process pool; "
+                      "single_process_value: the same image in one process (the reference is "
+                      "single-threaded), best of 2; %s"
                       % (len(times), len(ref.blocks), ref.cores, cpu_model_name())}
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    if comm is not None:
+        comm.close()
+
+
+# ---------------------------------------------------------------------------
+# the other BASELINE configs (extras)
+# ---------------------------------------------------------------------------
+def bench_cfg3(dcb, _cabi, ctypes, stream, peak):
+    """configs[2]: radial -> perspective on 2048^2 (demo_05.py:127,147), device-timed over 12
+    rotating buffer sets (576 MB >> L2), against the 8 B/px a fused kernel would move."""
+    from oracle import oracle_c
+    n, S = 12, 2048
+    srcs = [dcb.DeviceArray((S, S)).fill_synthetic(seed=3, offset=i * S * S) for i in range(n)]
+    tmps = [dcb.DeviceArray((S, S)) for _ in range(n)]
+    dsts = [dcb.DeviceArray((S, S)) for _ in range(n)]
+    rad = _cabi.make_radial(1030.2, 1019.6, FACT3)
+    per = _cabi.make_persp(PERS3)
+    opt = _cabi.make_options(1, dcb.BLEND_EXACT, dcb.PATH_AUTO)
+    fn = _cabi.load().dcb_unwarp_image_backward_perspective_f32
+    sh = ctypes.c_void_p(stream.handle)
+
+    def once():
+        for s, t, d in zip(srcs, tmps, dsts):
+            _cabi.check(fn(ctypes.c_void_p(s.ptr), ctypes.c_void_p(d.ptr), ctypes.c_void_p(t.ptr), S, S,
+                           s.pitch, d.pitch, t.pitch, ctypes.byref(rad), ctypes.byref(per),
+                           ctypes.byref(opt), sh))
+    us = _event_ms(dcb, stream, once, 3) * 1e3 / n
+    src0 = srcs[0].to_host()
+    want = oracle_c.correct_perspective_image(
+        oracle_c.unwarp_image_backward(src0, 1030.2, 1019.6, FACT3, 1), PERS3, 1)
+    bad = int(np.count_nonzero(dsts[0].to_host() != want))
+    return {"workload": "configs[2]: perspective+radial combined unwarp, 2048x2048 fp32",
+            "kernel_us_per_image": us, "Mpixels_per_s": S * S / us,
+            "roofline_frac_vs_8B_per_px": ALGO_BYTES_PER_PX * S * S / (us * 1e-6) / 1e9 / peak,
+            "launches_per_image": 2, "hbm_bytes_per_px_moved": 16,
+            "parity_ok": bad == 0, "pixels_differing_from_oracle": bad}
+
+
+def bench_cfg4(dcb, _cabi, ctypes, stream, peak, rank, world, comm, args):
+    """configs[3]: 2048 slices x 2560^2, unwarp_slice_backward semantics (float64 coordinates),
+    every output row of every slice, the stack Z-sharded over the ranks (strong scaling); the
+    shard is generated on the device (stateless hash), nothing crosses PCIe or NVLink."""
+    from discorpy_b200 import multigpu
+    from oracle import oracle_np
+    D, S = args.cfg4_depth, 2560
+    xc, yc = 1283.4, 1275.9
+    lo, hi = multigpu.shard_range(D, rank, world)
+    nz = hi - lo
+    stack = dcb.DeviceArray((nz, S, S)).fill_synthetic(seed=4, offset=lo * S * S)
+    out = dcb.DeviceArray((nz, S, S))
+    model = _cabi.make_radial(xc, yc, FACT3)
+    opt = _cabi.make_options(1, dcb.BLEND_EXACT, dcb.PATH_AUTO)
+    sfn = _cabi.load().dcb_unwarp_stack_backward_f32
+    sh = ctypes.c_void_p(stream.handle)
+
+    def once():
+        _cabi.check(sfn(ctypes.c_void_p(stack.ptr), ctypes.c_void_p(out.ptr), nz, S, S, 0, S,
+                        stack.pitch, stack.slice_stride, out.pitch, out.slice_stride, 0, S, 0,
+                        ctypes.byref(model), ctypes.byref(opt), sh))
+    if comm is not None:
+        comm.barrier()
+    ms_local = _event_ms(dcb, stream, once, 2)
+    ms = ms_local if comm is None else comm.allreduce_max([ms_local])[0]
+    # parity: D' = 8 slices of this rank's shard on the host, three sinograms against the oracle
+    dsub = min(8, nz)
+    sub = dcb.DeviceArray((dsub, S, S))
+    _cabi.call("dcb_d2d", ctypes.c_void_p(sub.ptr), ctypes.c_void_p(stack.ptr), dsub * stack.slice_stride, sh)
+    osub = dcb.DeviceArray((dsub, S, S))
+    _cabi.call("dcb_d2d", ctypes.c_void_p(osub.ptr), ctypes.c_void_p(out.ptr), dsub * out.slice_stride, sh)
+    host, got = sub.to_host(), osub.to_host()
+    worst, cpu_s = 0.0, 0.0
+    for index in (3, S // 2 + 7, S - 2):
+        t0 = time.perf_counter()
+        want = oracle_np.unwarp_slice_backward(host, xc, yc, FACT3, index)
+        cpu_s += time.perf_counter() - t0
+        worst = max(worst, float(np.max(np.abs(got[:, index, :] - want))))
+    worst = worst if comm is None else comm.allreduce_max([worst])[0]
+    res = {"workload": "configs[3]: 3D stack %d slices x 2560x2560 fp32, unwarp_slice_backward "
+                       "semantics, every row, Z-sharded over %d GPU(s)" % (D, world),
+           "scaling": "strong", "slices_per_gpu": nz, "ms": ms,
+           "Mpixels_per_s": D * S * S / 1e6 / (ms * 1e-3),
+           "roofline_frac_per_gpu": ALGO_BYTES_PER_PX * nz * S * S / (ms_local * 1e-3) / 1e9 / peak,
+           "parity_ok": worst <= 1e-5, "max_abs_diff_vs_oracle": worst,
+           "parity_sample": "3 sinograms x %d slices per rank, tolerance 1e-5" % dsub}
+    if world == 1:
+        # the reference loops `depth` times per index (postprocessing.py:226-228): linear in both
+        res["cpu_scaled_s"] = cpu_s / (3 * dsub) * D * S
+        res["cpu_scaling"] = ("oracle unwarp_slice_backward on %d slices x 3 indices, one process, "
+                              "scaled by (D / %d) x (2560 / 3)" % (dsub, dsub))
+    return res
+
+
+def bench_cfg5(dcb, _cabi, ctypes, stream, peak, rank, world, comm, args):
+    """configs[4]: 64 images of 8192^2, 9-term fisheye-strength model, 64/N images per rank
+    through the Z-stack kernel (the images of a batch share the model)."""
+    from discorpy_b200 import multigpu
+    from oracle import oracle_c
+    B, S = args.cfg5_batch, 8192
+    xc, yc = 4100.3, 4090.8
+    lo, hi = multigpu.shard_range(B, rank, world)
+    nz = hi - lo
+    batch = dcb.DeviceArray((nz, S, S)).fill_synthetic(seed=5, offset=lo * S * S)
+    out = dcb.DeviceArray((nz, S, S))
+    model = _cabi.make_radial(xc, yc, FACT9)
+    opt = _cabi.make_options(1, dcb.BLEND_EXACT, dcb.PATH_AUTO)
+    sfn = _cabi.load().dcb_unwarp_stack_backward_f32
+    sh = ctypes.c_void_p(stream.handle)
+
+    def once():
+        _cabi.check(sfn(ctypes.c_void_p(batch.ptr), ctypes.c_void_p(out.ptr), nz, S, S, 0, S,
+                        batch.pitch, batch.slice_stride, out.pitch, out.slice_stride, 0, S, 1,
+                        ctypes.byref(model), ctypes.byref(opt), sh))
+    if comm is not None:
+        comm.barrier()
+    ms_local = _event_ms(dcb, stream, once, 2)
+    ms = ms_local if comm is None else comm.allreduce_max([ms_local])[0]
+    # parity: this rank's first image against the C oracle, bit for bit
+    one_in, one_out = dcb.DeviceArray((S, S)), dcb.DeviceArray((S, S))
+    _cabi.call("dcb_d2d", ctypes.c_void_p(one_in.ptr), ctypes.c_void_p(batch.ptr), batch.slice_stride, sh)
+    _cabi.call("dcb_d2d", ctypes.c_void_p(one_out.ptr), ctypes.c_void_p(out.ptr), out.slice_stride, sh)
+    src = one_in.to_host()
+    t0 = time.perf_counter()
+    want = oracle_c.unwarp_image_backward(src, xc, yc, FACT9, 1, nthreads=max(1, _host_cores() // world))
+    cpu_s = time.perf_counter() - t0
+    bad = float(np.count_nonzero(one_out.to_host() != want))
+    bad = bad if comm is None else comm.allreduce_max([bad])[0]
+    res = {"workload": "configs[4]: fisheye-strength 9-term polynomial, 8192x8192 fp32 batch=%d, "
+                       "%d image(s) per GPU over %d GPU(s)" % (B, nz, world),
+           "scaling": "strong", "images_per_gpu": nz, "ms": ms,
+           "Mpixels_per_s": B * S * S / 1e6 / (ms * 1e-3),
+           "roofline_frac_per_gpu": ALGO_BYTES_PER_PX * nz * S * S / (ms_local * 1e-3) / 1e9 / peak,
+           "parity_ok": bad <= 16, "pixels_differing_from_oracle": int(bad),
+           "parity_sample": "first image of every rank, bit for bit (<= 16 float32-coordinate "
+                            "flips per 67 Mpixel allowed, tests/test_gpu_parity.py)"}
+    if world == 1:
+        res["cpu_scaled_s"] = cpu_s * B
+        res["cpu_scaling"] = ("C restatement of the reference arithmetic (oracle_c, %d threads) on "
+                              "one image x %d" % (max(1, _host_cores() // world), B))
+    return res
+
+
+def bench_exchange(dcb, multigpu, post, comm, rank, world):
+    """The one optional exchange step: ONE sinogram of a Z-sharded stack on rank 0,
+    fused (every rank's remap kernel stores into rank 0's buffer over NVLink) and collective
+    (local rows + NCCL all-gather through the C ABI), both against the oracle on rank 0."""
+    from discorpy_b200.device import DeviceArray, synthetic_host
+    from oracle import oracle_np
+    D, S = 8 * world + 5, 640                  # uneven shards on purpose
+    scale = 2560.0 / S
+    params = dict(xcenter=S / 2 + 3.4, ycenter=S / 2 - 4.1,
+                  list_fact=[FACT3[i] * scale ** i for i in range(5)], list_coef=[])
+    lo, hi = multigpu.shard_range(D, rank, world)
+    shard = DeviceArray((hi - lo, S, S)).fill_synthetic(seed=4, offset=lo * S * S)
+    window = multigpu.SinogramWindow(D, S, owner=0, comm=comm)
+    full = synthetic_host(D * S * S, seed=4).reshape(D, S, S) if rank == 0 else None
+    fused_bad = coll_bad = 0
+    rows = DeviceArray((hi - lo, S))
+    for index in (0, S // 3, S - 1):
+        multigpu.unwarp_slice_backward_sharded(shard, params, index, window)
+        window.fence()
+        post._unwarp_slice_into(shard, params["xcenter"], params["ycenter"], params["list_fact"],
+                                index, multigpu._Rows(rows.ptr, rows.pitch, rows.shape))
+        gathered = multigpu.gather_rows(rows, D, comm=comm)
+        if rank == 0:
+            want = oracle_np.unwarp_slice_backward(full, params["xcenter"], params["ycenter"],
+                                                   params["list_fact"], index)
+            fused_bad += int(np.count_nonzero(window.array.to_host() != want))
+            coll_bad += int(np.count_nonzero(gathered.to_host() != want))
+        comm.barrier()
+
+    def timed(fn, reps=20):
+        fn()
+        comm.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        comm.barrier()
+        return comm.allreduce_max([(time.perf_counter() - t0) / reps])[0] * 1e3
+
+    def fused():
+        multigpu.unwarp_slice_backward_sharded(shard, params, S // 2, window)
+        window.fence()
+
+    def collective():
+        post._unwarp_slice_into(shard, params["xcenter"], params["ycenter"], params["list_fact"],
+                                S // 2, multigpu._Rows(rows.ptr, rows.pitch, rows.shape))
+        multigpu.gather_rows(rows, D, comm=comm)
+        dcb.current_stream().sync()
+
+    res = {"fused_ms": timed(fused), "collective_ms": timed(collective),
+           "fused_ok": fused_bad == 0, "collective_ok": coll_bad == 0,
+           "stack": "%d slices of %dx%d over %d ranks, 3 indices checked bit for bit against the "
+                    "oracle on rank 0" % (D, S, S, world)}
+    window.close()
+    return res
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant
 # kernel, from the committed `ncu --set full` capture (profiles/); None until
 # a capture exists for the current kernel.
-TRAFFIC_BYTES_PER_LAUNCH = 69821696 + 17368832
-TRAFFIC_SOURCE = ("profiles/r1/ncu_image_v14.txt: dram__bytes_read.sum 69.8 MB + "
-                  "dram__bytes_write.sum 17.4 MB of one launch (most of the 64 MiB output is "
+TRAFFIC_BYTES_PER_LAUNCH = 79433216 + 22320640
+TRAFFIC_SOURCE = ("profiles/r2/ncu_image_r2i_exact.txt: dram__bytes_read.sum 79.4 MB + "
+                  "dram__bytes_write.sum 22.3 MB of one launch (most of the 64 MiB output is "
                   "still dirty in the 126 MB L2 when the profiled launch ends)")
+# What the SM side of one launch costs at 100 % of each pipe (us), from the instruction mix of
+# the committed capture (profiles/r2/ncu_image_r2i_exact.txt: thread instructions per pixel by
+# pipe) and the pipe rates measured in round 1 (profiles/r1/microbench_*.txt: fp64 60.1 and XU
+# 15.6 thread-ops per clock per SM, issue 128): 16.78 Mpx / 148 SMs / 1.965 GHz x ops / rate.
+def _colimit(ops_per_px, rate):
+    return H * W / 148.0 / 1965.0 * ops_per_px / rate          # us
+
+
+COLIMIT = {"fp64_us": _colimit(18.6, 60.1), "xu_us": _colimit(2.9, 15.6),
+           "issue_us": _colimit(66.0, 128.0),
+           "source": "profiles/r2/ncu_image_r2i_exact.txt instruction mix; pipe rates "
+                     "profiles/r1/microbench_v1.txt"}
 
 
 def main():
@@ -457,6 +750,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the secondary figures (blend variants, Z-stack kernel)")
     ap.add_argument("--stack-depth", type=int, default=32)
+    ap.add_argument("--cfg4-depth", type=int, default=2048)
+    ap.add_argument("--cfg5-batch", type=int, default=64)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -466,13 +761,15 @@ def main():
         run_reference_arm(args, rank, world)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
-        # plain `python bench.py --gpus N`: relaunch under torchrun
+        # plain `python bench.py --gpus N`: one process per GPU, the launcher's environment by hand
         import subprocess
         port = 29500 + (os.getpid() % 2000)
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
-               "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
-               "--master-port", str(port)] + sys.argv
-        sys.exit(subprocess.call(cmd))
+        procs = []
+        for r in range(args.gpus):
+            env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(args.gpus),
+                       MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+            procs.append(subprocess.Popen([sys.executable] + sys.argv, env=env))
+        sys.exit(max(p.wait() for p in procs))
     run_gpu_arm(args, rank, local_rank, world)
 
 

@@ -20,14 +20,15 @@ from ._cabi import (DcbError, BLEND_EXACT, BLEND_LERP64, BLEND_LERP32,
                     PATH_AUTO, PATH_DIRECT, PATH_TMA)
 from .device import (DeviceArray, pinned_empty, pinned_copy, is_pinned,
                      set_device, device_count, device_info, synchronize, bind_host_to_device,
-                     launch_count, last_plan, image_stats, plan_cache_clear, current_stream, Stream,
+                     launch_count, last_plan, image_stats, plan_cache_clear, device_pool_clear,
+                     current_stream, Stream,
                      Event)
 
 __version__ = "0.1.0"
 
 __all__ = ["DeviceArray", "pinned_empty", "pinned_copy", "is_pinned",
            "set_device", "device_count", "device_info", "synchronize", "bind_host_to_device",
-           "launch_count", "last_plan", "image_stats", "plan_cache_clear", "current_stream", "Stream", "Event",
+           "launch_count", "last_plan", "image_stats", "plan_cache_clear", "device_pool_clear", "current_stream", "Stream", "Event",
            "DcbError", "install_as_discorpy", "library_path"]
 
 

@@ -192,6 +192,11 @@ device_pool = _Pool(DeviceBuffer, _pool_bytes, keyfn=_pool_key,
                     sync=lambda: _cabi.call("dcb_device_sync"))
 
 
+def device_pool_clear():
+    """Free the device buffers the pool is holding (large benchmarks between phases)."""
+    device_pool.clear()
+
+
 class borrowed:
     """``with borrowed(nbytes) as buf:`` -- a pooled device buffer."""
 
