@@ -95,6 +95,52 @@ __device__ __forceinline__ void split_floor(double c, int &i, double &t) {
     t = __dsub_rn(c, __dsub_rn(m, 4503599627370496.0));
 }
 
+// SciPy's order-1 value  sum_ij  rn(rn(m_ij * wy_i) * wx_j)  accumulated first
+// tap to last (DCB_BLEND_EXACT), with fewer operations but the same roundings:
+//   * wy_i and wx_j are fp32 fractions widened to fp64 (<= 24 significant
+//     bits), so m * wy (24 + 24 bits) is exact and rn(rn(m wy) wx) equals
+//     rn(m * W_ij) with W_ij = wy_i * wx_j, itself exact (<= 48 bits);
+//   * W11 = ty*tx is one multiplication; W10 = ty - W11, W01 = tx - W11 and
+//     W00 = (1 - ty) - W01 are exact because their results are the <= 48-bit
+//     products ty(1-tx), (1-ty)tx, (1-ty)(1-tx).
+// 5 + 4 + 3 = 12 fp64 operations instead of 13, every one of them rounding
+// exactly where SciPy's does.
+__device__ __forceinline__ double blend_exact(double a, double b, double c, double d, double tx,
+                                              double ty) {
+    const double w11 = __dmul_rn(ty, tx);
+    const double w10 = __dsub_rn(ty, w11);
+    const double w01 = __dsub_rn(tx, w11);
+    const double w00 = __dsub_rn(__dsub_rn(1.0, ty), w01);
+    double s = __dmul_rn(a, w00);
+    s = __dadd_rn(s, __dmul_rn(b, w01));
+    s = __dadd_rn(s, __dmul_rn(c, w10));
+    s = __dadd_rn(s, __dmul_rn(d, w11));
+    return s;
+}
+
+// ---------------------------------------------------------------------------
+// certified blend (round 2): a cheaper evaluation of SciPy's order-1 sum plus one integer test
+// that proves the float32 result is the same
+// ---------------------------------------------------------------------------
+// distance test of a double's low mantissa word from the float32 rounding boundary (bit 28 set,
+// bits 27..0 clear): the shifted word is 0x80000000 there
+__device__ __forceinline__ uint32_t cert_key(double v, uint32_t add) {
+    return ((uint32_t)__double2loint(v) << 3) + add;
+}
+// blend certificate: 32 ulp64 around the boundary (the FMA form below is within 10 ulp64 of
+// SciPy's sum for taps of one sign, see lerp_fma)
+constexpr uint32_t kBlendCertAdd = 0x80000000u + 8u * 32u, kBlendCertLim = 16u * 32u;
+
+// (1-ty)((1-tx) a + tx b) + ty ((1-tx) c + tx d) with six FMAs, every intermediate a positive
+// combination of the taps: for taps of one sign nothing cancels, the result is within 2^-51
+// relative of the exact value, SciPy's rn-sum of rn-products (blend_exact) within 2^-51 too.
+__device__ __forceinline__ double lerp_fma(double a, double b, double c, double d, double tx,
+                                           double ty) {
+    const double top = fma(tx, b, fma(-tx, a, a));
+    const double bot = fma(tx, d, fma(-tx, c, c));
+    return fma(ty, bot, fma(-ty, top, top));
+}
+
 // ---------------------------------------------------------------------------
 // one output pixel: the arithmetic of scipy.ndimage.map_coordinates(order 0|1)
 // for a coordinate that already lies in [0, W-1] x [0, H-1]
