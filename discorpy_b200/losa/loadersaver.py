@@ -28,7 +28,7 @@ def _prepare(file_path, suffixes, default, overwrite):
     os.makedirs(os.path.dirname(path), exist_ok=True)
     if not overwrite and os.path.exists(path):
         root, ext = os.path.splitext(path)
-        n = 1
+        n = 0                                   # the reference starts at _0000 (:397-407)
         while os.path.exists("%s_%04d%s" % (root, n, ext)):
             n += 1
         path = "%s_%04d%s" % (root, n, ext)

@@ -268,13 +268,16 @@ def _unwarp_slice_into(mat3D, xcenter, ycenter, list_fact, index, dst):
     yd = _row_yd(height, width, xcenter, ycenter, list_fact, index)
     yd_min = int(np.int16(np.floor(np.amin(yd))))
     yd_max = int(np.int16(np.ceil(np.amax(yd)))) + 1
-    if int(index) != index:
-        raise NotImplementedError("fractional slice index %r" % (index,))
+    if (int(index) != index or not 0 <= int(index) < height
+            or (not on_device and np.dtype(mat3D.dtype) == np.float64)):
+        # (also float64 stacks: SciPy samples them in float64, the result is rounded once into
+        # the float32 sinogram -- the float64 sampler of the spline path does the same)
+        # the reference takes any number (:214-220: the row coordinate is just clipped); the
+        # tiled kernel works on output rows of the image, so such a row goes through the
+        # explicit-coordinate kernel, one launch per slice
+        return _unwarp_slice_any_index(mat3D, xcenter, ycenter, list_fact, index, yd,
+                                       yd_min, yd_max, dst)
     index = int(index)
-    if not 0 <= index < height:
-        raise NotImplementedError(
-            "index %d outside the image is not supported by the CUDA path"
-            % index)
     model = _cabi.make_radial(xcenter, ycenter, list_fact)
     stream = _dev.current_stream()
     if dst is None:
@@ -297,6 +300,29 @@ def _unwarp_slice_into(mat3D, xcenter, ycenter, list_fact, index, dst):
     return dst
 
 
+def _unwarp_slice_any_index(mat3D, xcenter, ycenter, list_fact, index, yd, yd_min, yd_max, dst):
+    """``unwarp_slice_backward`` for a row index that is fractional or lies outside the image
+    (reference ``:214-228`` verbatim in its arithmetic: float64 coordinates, window crop, order 1,
+    'reflect'); rare, one explicit-coordinate launch per slice."""
+    (depth, height, width) = mat3D.shape
+    xu = np.arange(0, width) - xcenter
+    yu = index - ycenter
+    flist = _radial_factor_1d(np.sqrt(xu ** 2 + yu ** 2), list_fact)
+    xd = np.clip(xcenter + flist * xu, 0, width - 1)
+    ydw = yd - yd_min
+    host = mat3D.to_host() if isinstance(mat3D, DeviceArray) else mat3D
+    sino = np.zeros((depth, width), dtype=np.float32)
+    for i in range(depth):
+        sino[i] = _map_coordinates(np.asarray(host[i, yd_min:yd_max, :]), ydw, xd, 1, "reflect")
+    if dst is None:
+        dst = DeviceArray((depth, width))
+    stream = _dev.current_stream()
+    _cabi.call("dcb_h2d_2d", _vp(dst.ptr), dst.pitch, _vp(sino.ctypes.data), width * 4,
+               width * 4, depth, _vp(stream.handle))
+    stream.sync()           # `sino` is an ordinary array: do not outlive it
+    return dst
+
+
 class _SliceRows:
     """Destination of the one-row-per-slice launch: rows ``pitch`` bytes apart."""
 
@@ -307,16 +333,74 @@ class _SliceRows:
 def _mapping(mat, xmat, ymat):
     """
     Apply a geometric transformation to a 2D array (reference ``:232-252``):
-    bilinear sampling of ``mat`` at the given coordinates.  Coordinates are
-    expected inside the image (every caller in the reference clips them);
-    out-of-range values raise, because clamping is not what SciPy's 'reflect'
-    does there.
+    bilinear sampling of ``mat`` at the given coordinates; coordinates outside the
+    image are reflected like SciPy's default boundary does (``_fold_coordinate``).
     """
     xmat = np.asarray(xmat)
     ymat = np.asarray(ymat)
     out = _map_coordinates(np.asarray(mat), ymat.ravel(), xmat.ravel(), 1,
                            "reflect")
     return out.reshape(xmat.shape)
+
+
+def _fold_coordinate(cc, n, mode):
+    """SciPy's ``map_coordinate`` (``ni_interpolation.c``) for a float64 coordinate array and an
+    axis of length ``n``: where the boundary mode sends a coordinate that lies outside
+    ``[0, n-1]``.  Restated for 'reflect' / 'grid-mirror', 'mirror' and 'wrap' and pinned to the
+    installed SciPy bit for bit (tests/test_host_api.py); after it, sampling with clamped taps
+    (what the explicit-coordinate kernel does) gives SciPy's value for orders 0 and 1."""
+    cc = np.array(cc, dtype=np.float64, copy=True)
+    if n <= 1:
+        cc[:] = 0.0
+        return cc
+    neg = cc < 0
+    pos = cc > n - 1
+    if mode in ("reflect", "grid-mirror"):
+        sz2 = 2.0 * n
+        v = cc[neg]
+        far = v < -sz2
+        v[far] = sz2 * np.trunc(-v[far] / sz2) + v[far]
+        cc[neg] = np.where(v < -n, v + sz2, -v - 1.0)
+        v = cc[pos]
+        v = v - sz2 * np.trunc(v / sz2)
+        cc[pos] = np.where(v >= n, sz2 - v - 1.0, v)
+    elif mode == "mirror":
+        sz2 = 2.0 * n - 2.0
+        v = cc[neg]
+        v = sz2 * np.trunc(-v / sz2) + v
+        v = np.where(v <= 1 - n, v + sz2, -v)
+        cc[neg] = np.where(v > n - 1, sz2 - v, v)      # (n-1, n): the mirrored twin inside
+        v = cc[pos]
+        v = v - sz2 * np.trunc(v / sz2)
+        cc[pos] = np.where(v > n - 1, sz2 - v, v)
+    elif mode == "wrap":
+        sz = n - 1.0
+        v = cc[neg]
+        cc[neg] = v + sz * (np.trunc(-v / sz) + 1)
+        v = cc[pos]
+        cc[pos] = v - sz * np.trunc(v / sz)
+    else:
+        raise NotImplementedError(mode)
+    return cc
+
+
+def _explicit_coordinates(yd, xd, height, width, order, mode):
+    """Explicit coordinates as SciPy would read them for order 0 / 1: inside the image nothing
+    changes (and float32 arrays stay float32); outside, the boundary mode decides.  Returns
+    ``(yd, xd, zero_mask)`` -- ``zero_mask`` marks the samples 'constant' answers with cval = 0."""
+    outside = (yd < 0) | (yd > height - 1) | (xd < 0) | (xd > width - 1)
+    outside |= np.isnan(yd) | np.isnan(xd)
+    if mode == "nearest" or not outside.any():
+        return yd, xd, None
+    if mode == "constant":
+        return yd, xd, outside
+    if mode in ("grid-constant", "grid-wrap"):
+        raise NotImplementedError(
+            "%d coordinates lie outside the image and mode %r interpolates across the border "
+            "(SciPy pads / wraps the grid there); the CUDA path implements 'reflect', "
+            "'grid-mirror', 'mirror', 'wrap', 'nearest' and 'constant' for such coordinates"
+            % (int(outside.sum()), mode))
+    return (_fold_coordinate(yd, height, mode), _fold_coordinate(xd, width, mode), None)
 
 
 def _map_coordinates(mat, yd, xd, order, mode):
@@ -329,12 +413,14 @@ def _map_coordinates(mat, yd, xd, order, mode):
                 "which equals SciPy only for mode='nearest' (got %r)" % (n_oob, mode))
         return out
     src_np, flags, out_dtype = _as_f32_image(mat)
+    yd, xd = np.asarray(yd).ravel(), np.asarray(xd).ravel()
+    if yd.size != xd.size:
+        raise RuntimeError("invalid shape for coordinate array")
+    yd, xd, zero_mask = _explicit_coordinates(yd, xd, height, width, order, mode)
     kind = np.result_type(yd.dtype, xd.dtype)
     ctype = np.float32 if kind == np.float32 else np.float64
     yd = np.ascontiguousarray(yd, dtype=ctype).ravel()
     xd = np.ascontiguousarray(xd, dtype=ctype).ravel()
-    if yd.size != xd.size:
-        raise RuntimeError("invalid shape for coordinate array")
     n = yd.size
     stream = _dev.current_stream()
     src = DeviceArray.from_host(src_np, stream)
@@ -356,11 +442,11 @@ def _map_coordinates(mat, yd, xd, order, mode):
         _cabi.call("dcb_d2h", _vp(out.ctypes.data), _vp(dout.ptr), n * 4, sh)
         _cabi.call("dcb_d2h", _vp(flag.ctypes.data), _vp(dflag.ptr), 16, sh)
         stream.sync()
-    if flag[0] != 0 and mode != "nearest":
-        raise NotImplementedError(
-            "%d coordinates lie outside the image; the CUDA path clamps them, "
-            "which equals SciPy only for mode='nearest' (got %r)"
-            % (int(flag[0]), mode))
+    # (coordinates still outside here are 'nearest', 'constant' -- zeroed next -- or the
+    # (-1, 0) / (n-1, n) band of a folded 'reflect' coordinate: clamping is SciPy's value)
+    if zero_mask is not None:
+        out = np.array(out)
+        out[zero_mask] = 0.0
     return _narrow(out, out_dtype)
 
 
@@ -394,26 +480,6 @@ def _rows_leave_window(height, width, xcenter, ycenter, list_fact, start, stop,
     return bool(lo.min() < yd_min or hi.max() > yd_max - 1)
 
 
-def _reflect_coordinate(cc, n):
-    """SciPy's coordinate mapping for mode 'reflect' (``ni_interpolation.c``
-    ``map_coordinate``), float64 in and out; identity inside ``[0, n-1]``."""
-    cc = np.array(cc, dtype=np.float64, copy=True)
-    if n <= 1:
-        cc[(cc < 0) | (cc > n - 1)] = 0.0
-        return cc
-    sz2 = 2.0 * n
-    neg = cc < 0
-    v = cc[neg]
-    far = v < -sz2
-    v[far] = sz2 * np.trunc(-v[far] / sz2) + v[far]
-    cc[neg] = np.where(v < -n, v + sz2, -v - 1.0)
-    pos = (cc > n - 1) & ~neg
-    v = cc[pos]
-    v = v - sz2 * np.trunc(v / sz2)
-    cc[pos] = np.where(v >= n, sz2 - v - 1.0, v)
-    return cc
-
-
 def _chunk_outside_window(mat3D, xcenter, ycenter, list_fact, start, stop,
                           yd_min, yd_max):
     """``unwarp_chunk_slices_backward`` when some rows of the chunk sample
@@ -431,7 +497,7 @@ def _chunk_outside_window(mat3D, xcenter, ycenter, list_fact, start, stop,
     xd = np.float32(np.clip(xcenter + fmat * xu_mat, 0, width - 1))
     yd = np.float32(np.clip(ycenter + fmat * yu_mat, 0, height - 1))
     yd = yd - np.int16(yd_min)                     # float32, like :308-309
-    yd = _reflect_coordinate(yd, yd_max - yd_min)  # float64
+    yd = _fold_coordinate(yd, yd_max - yd_min, "reflect")  # float64
     # a mapped coordinate in (-1, 0) or (n-1, n) has both taps on the edge row: clamping
     # (mode 'nearest' of the explicit-coordinate kernel) gives SciPy's value
     xd = xd.astype(np.float64)
@@ -476,15 +542,18 @@ def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
                          "chunk above the first one (the reference's result is undefined "
                          "here)" % (yd_min, yd_max))
     model = _cabi.make_radial(xcenter, ycenter, list_fact)
-    if _rows_leave_window(height, width, xcenter, ycenter, list_fact,
-                          start_index, stop_index, yd_min, yd_max):
+    is_f64 = (not on_device) and np.dtype(mat3D.dtype) == np.float64
+    if is_f64 or _rows_leave_window(height, width, xcenter, ycenter, list_fact,
+                                    start_index, stop_index, yd_min, yd_max):
+        # (float64 stacks -- e.g. flat-field-normalised projections -- keep float64 in and out
+        # like in the reference: per slice through the float64 sampler of the spline path)
         host = mat3D.to_host() if on_device else mat3D
         res = _chunk_outside_window(host, xcenter, ycenter, list_fact,
                                     start_index, stop_index, yd_min, yd_max)
         return DeviceArray.from_host(res) if on_device else res
     stream = _dev.current_stream()
-    dst = DeviceArray((depth, nrows, width))
     if on_device:
+        dst = DeviceArray((depth, nrows, width))
         src_ptr = mat3D.ptr + yd_min * mat3D.pitch
         _stack_call(src_ptr, dst, depth, height, width, yd_min,
                     yd_max - yd_min, mat3D.pitch, mat3D.slice_stride,
@@ -494,10 +563,11 @@ def unwarp_chunk_slices_backward(mat3D, xcenter, ycenter, list_fact,
     if (np.dtype(mat3D.dtype) == np.float32 and depth >= 4
             and win_bytes >= config["stream_bytes"]):
         from . import streaming
-        del dst
         return streaming.unwarp_chunk_slices_backward_stream(
             mat3D, xcenter, ycenter, list_fact, start_index, stop_index,
             block_bytes=int(min(256 << 20, max(32 << 20, win_bytes // 8))))
+    # (the output is allocated only now: a stack that streams never needs it whole on the device)
+    dst = DeviceArray((depth, nrows, width))
     win, flags, out_dtype = _upload_native(mat3D[:, yd_min:yd_max, :], stream)
     _stack_call(win.ptr, dst, depth, height, width, yd_min, yd_max - yd_min,
                 win.pitch, win.slice_stride, start_index, nrows, 1, model,
@@ -642,9 +712,12 @@ def correct_perspective_image(mat, list_coef, order=1, mode="reflect",
     (height, width) = mat.shape
     order = _check_order_mode(order, mode)
     if map_index is not None:
-        if on_device:
-            raise NotImplementedError("map_index with a DeviceArray input")
         yd, xd = map_index
+        if on_device:
+            # the coordinate arrays are host arrays in the reference's signature; the image
+            # makes one round trip (this path is not tuned) and the result stays on the device
+            out = _map_coordinates(mat.to_host(), np.asarray(yd), np.asarray(xd), order, mode)
+            return DeviceArray.from_host(out.reshape((height, width)))
         out = _map_coordinates(mat, np.asarray(yd), np.asarray(xd), order,
                                mode)
         return out.reshape((height, width))

@@ -73,10 +73,11 @@ def unwarp_color_image_backward(mat, xcenter, ycenter, list_fact, order=1,
     list_fact : list of float
         Polynomial coefficients of the backward model.
     order : int, optional
-        0 or 1 (2..5 raise ``NotImplementedError``).
+        Spline order 0..5; 0 and 1 take the tuned float32 kernels (all channels in one launch),
+        2..5 SciPy's float64 prefilter + sampler on the GPU, one channel at a time.
     mode : str, optional
-        Accepted for signature parity (coordinates are clipped before
-        sampling, so it does not matter for order 0/1).
+        SciPy boundary mode; the coordinates are clipped before sampling, so it only matters
+        for orders >= 2 (the prefilter's boundary condition).
     pad : bool, int, or tuple of int
         Keeps the original view; see the reference.
     pad_mode : str

@@ -373,3 +373,29 @@ def unwarp_color_image_backward(mat, xcenter, ycenter, list_fact, order=1,
     planes = [sample(mat_pad[:, :, i], yd, xd, order)
               for i in range(mat_pad.shape[-1])]
     return np.moveaxis(np.asarray(planes), 0, 2)
+
+
+def unwarp_image_forward(mat, xcenter, ycenter, list_fact):
+    """Forward-model scatter (reference ``postprocessing.py:151-185``): every source pixel is
+    written to its rounded, clipped target; vacant targets stay 0 and, where several sources
+    land on one target, the last one in C order wins (what NumPy's ``out[yu, xu] = mat`` does).
+    Restated with an explicit winner table instead of the fancy assignment."""
+    mat = np.asarray(mat)
+    (height, width) = mat.shape
+    xd = np.arange(width) - xcenter
+    yd = np.arange(height) - ycenter
+    xd_mat, yd_mat = np.meshgrid(xd, yd)
+    rd = np.sqrt(xd_mat ** 2 + yd_mat ** 2)
+    fact = None
+    for i, a in enumerate(list_fact):                      # :176-177, summed first to last
+        term = a * rd ** i
+        fact = term if fact is None else fact + term
+    xu = np.intp(np.round(np.clip(xcenter + fact * xd_mat, 0, width - 1)))
+    yu = np.intp(np.round(np.clip(ycenter + fact * yd_mat, 0, height - 1)))
+    target = (yu * width + xu).ravel()
+    winner = np.full(height * width, -1, dtype=np.int64)
+    np.maximum.at(winner, target, np.arange(height * width, dtype=np.int64))
+    out = np.zeros(height * width, dtype=mat.dtype)
+    hit = winner >= 0
+    out[hit] = mat.ravel()[winner[hit]]
+    return out.reshape(height, width)

@@ -489,3 +489,90 @@ def test_patch_path_with_odd_values_in_the_image():
     assert np.array_equal(np.isnan(got), np.isnan(want))
     ok = ~np.isnan(want)
     assert np.array_equal(got[ok], want[ok])
+
+
+def test_forward_unwarp_on_device_equals_the_oracle_and_the_reference_golden():
+    """dcb_unwarp_image_forward_f32 (csrc/forward.cuh) against the real reference's outputs
+    (tests/golden/forward.npz) and the oracle -- not against the product's own host code."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "forward.npz"))
+    k = 0
+    while "in%d" % k in z:
+        par = z["par%d" % k]
+        mat, xc, yc, fact = z["in%d" % k], par[0], par[1], list(par[2:])
+        got = post.unwarp_image_forward(dcb.DeviceArray.from_host(mat), xc, yc, fact).to_host()
+        assert np.array_equal(got, z["out%d" % k]), k
+        assert np.array_equal(got, orc.unwarp_image_forward(mat, xc, yc, fact)), k
+        k += 1
+    assert k == 4
+
+
+def test_baseline_config1_on_the_reference_image():
+    """BASELINE config 1 as the reference runs it (examples/unwarp.py:189): its own
+    data/dot_pattern_01.jpg with data/coef_dot_05.txt.  The full 2160 x 2560 result must have
+    the SHA-256 of the real reference's (tests/golden/cfg1/meta.json), orders 1 and 0."""
+    import hashlib
+    import json
+    import os
+    from PIL import Image
+    from discorpy_b200.losa import loadersaver as losa
+    d = os.path.join(os.path.dirname(__file__), "golden", "cfg1")
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    mat = np.array(Image.open(os.path.join(d, "dot_pattern_01.jpg")), dtype=np.float32)
+    if hashlib.sha256(mat.tobytes()).hexdigest() != meta["input_sha256"]:
+        pytest.skip("this PIL / libjpeg decodes the JPEG differently from the build container")
+    xc, yc, fact = losa.load_metadata_txt(os.path.join(d, "coef_dot_05.txt"))
+    assert (xc, yc, list(fact)) == (meta["xcenter"], meta["ycenter"], meta["list_fact"])
+    sub = np.load(os.path.join(d, "reference_subsample.npz"))
+    for order in (1, 0):
+        got = post.unwarp_image_backward(mat, xc, yc, fact, order=order)
+        assert got.dtype == np.float32 and got.shape == (2160, 2560)
+        assert np.array_equal(got[::7, ::7], sub["order%d" % order])
+        sha = hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest()
+        assert sha == meta["output_sha256_order%d" % order], order
+    # the same frame as uint8 (what the JPEG holds): SciPy's integer rounding on the device
+    got8 = post.unwarp_image_backward(mat.astype(np.uint8), xc, yc, fact)
+    want8 = orc.unwarp_image_backward(mat.astype(np.uint8), xc, yc, fact)
+    assert got8.dtype == np.uint8 and np.array_equal(got8, want8)
+
+
+def test_explicit_coordinates_outside_the_image_follow_scipys_modes():
+    """_mapping / map_index= with coordinates outside the image (reference :250-251, :489-491
+    hand them to SciPy): 'reflect', 'grid-mirror', 'mirror', 'wrap', 'nearest', 'constant' on the
+    device, bit-identical to scipy.ndimage.map_coordinates; the two grid-interpolating modes raise."""
+    from scipy.ndimage import map_coordinates
+    rng = np.random.default_rng(5)
+    mat = rng.random((37, 53), dtype=np.float32)
+    yd = rng.uniform(-90, 130, (37, 53))
+    xd = rng.uniform(-120, 170, (37, 53))
+    yd[::5, ::3] = np.round(yd[::5, ::3])
+    got = post._mapping(mat, xd, yd)
+    assert np.array_equal(got, map_coordinates(mat, (yd.ravel(), xd.ravel()), order=1,
+                                               mode="reflect").reshape(yd.shape))
+    coef = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0]
+    for mode in ("reflect", "grid-mirror", "mirror", "wrap", "nearest", "constant"):
+        for order in (0, 1):
+            for cast in (np.float64, np.float32):
+                idx = (yd.astype(cast).reshape(-1, 1), xd.astype(cast).reshape(-1, 1))
+                want = map_coordinates(mat, idx, order=order, mode=mode).reshape(mat.shape)
+                got = post.correct_perspective_image(mat, coef, order=order, mode=mode, map_index=idx)
+                assert np.array_equal(got, want), (mode, order, cast)
+    dev = post.correct_perspective_image(dcb.DeviceArray.from_host(mat), coef, map_index=idx)
+    assert isinstance(dev, dcb.DeviceArray)
+    for mode in ("grid-wrap", "grid-constant"):
+        with pytest.raises(NotImplementedError):
+            post.correct_perspective_image(mat, coef, mode=mode, map_index=idx)
+
+
+def test_unwarp_slice_backward_takes_any_numeric_index():
+    """The reference accepts fractional indices and indices outside the image (:214-220 clips the
+    row coordinate); so does the drop-in, bit-identical to the oracle."""
+    rng = np.random.default_rng(6)
+    stack = rng.random((5, 96, 200), dtype=np.float32)
+    for index in (40.5, -3, 97, 120.25, 95.999):
+        got = post.unwarp_slice_backward(stack, 101.3, 47.1, FACT5, index)
+        want = orc.unwarp_slice_backward(stack, 101.3, 47.1, FACT5, index)
+        assert got.dtype == np.float32 and got.shape == (5, 200)
+        assert np.max(np.abs(got - want)) <= 1e-5, index
+        dev = post.unwarp_slice_backward(dcb.DeviceArray.from_host(stack), 101.3, 47.1, FACT5, index)
+        assert np.array_equal(dev.to_host(), got)

@@ -172,3 +172,30 @@ def test_install_as_discorpy_shadows_only_post(monkeypatch):
     assert p2 is post
     assert proc.post is post
     assert "reference" in proc.__file__
+
+
+def test_fold_coordinate_is_scipys_boundary_mapping():
+    """post._fold_coordinate (+ clamped taps) against the installed SciPy, orders 0 and 1, the
+    modes the explicit-coordinate path implements for coordinates outside the image."""
+    from scipy.ndimage import map_coordinates
+    import discorpy_b200.post.postprocessing as post
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        h, w = int(rng.integers(2, 40)), int(rng.integers(2, 40))
+        img = rng.random((h, w)).astype(np.float32)
+        yd = rng.uniform(-3.5 * h, 4.5 * h, 400)
+        xd = rng.uniform(-3.5 * w, 4.5 * w, 400)
+        yd[:40], xd[:40] = np.round(yd[:40]), np.round(xd[:40])
+        if trial % 2:
+            yd, xd = yd.astype(np.float32), xd.astype(np.float32)
+        for order in (0, 1):
+            for mode in ("reflect", "grid-mirror", "mirror", "wrap", "nearest", "constant"):
+                want = map_coordinates(img, (yd, xd), order=order, mode=mode)
+                fy, fx, zero = post._explicit_coordinates(yd, xd, h, w, order, mode)
+                got = map_coordinates(img, (np.clip(fy, 0, h - 1), np.clip(fx, 0, w - 1)),
+                                      order=order, mode="nearest")
+                if zero is not None:
+                    got = np.where(zero, np.float32(0), got)
+                assert np.array_equal(got, want), (trial, order, mode)
+    with pytest.raises(NotImplementedError):
+        post._explicit_coordinates(np.array([-2.0]), np.array([1.0]), 8, 8, 1, "grid-wrap")

@@ -191,3 +191,36 @@ def test_oracle_against_the_real_reference_randomised():
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
     assert "0 not bit-identical" in res.stdout
+
+
+def test_forward_oracle_equals_reference_golden():
+    """oracle_np.unwarp_image_forward against the real reference's outputs
+    (oracle/make_golden_forward.py, postprocessing.py:151-185)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "forward.npz"))
+    k = 0
+    while "in%d" % k in z:
+        par = z["par%d" % k]
+        got = orc.unwarp_image_forward(z["in%d" % k], par[0], par[1], list(par[2:]))
+        assert np.array_equal(got, z["out%d" % k]), k
+        k += 1
+    assert k == 4
+
+
+def test_cfg1_real_image_oracle_equals_reference_golden():
+    """BASELINE config 1 on the reference's own files (tests/golden/cfg1, written by
+    oracle/make_golden_cfg1.py with the real reference): the oracle reproduces the full result
+    (SHA-256) and the stored subsample."""
+    import hashlib
+    import json
+    import os
+    from PIL import Image
+    d = os.path.join(os.path.dirname(__file__), "golden", "cfg1")
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    mat = np.array(Image.open(os.path.join(d, "dot_pattern_01.jpg")), dtype=np.float32)
+    if hashlib.sha256(mat.tobytes()).hexdigest() != meta["input_sha256"]:
+        pytest.skip("this PIL / libjpeg decodes the JPEG differently from the build container")
+    sub = np.load(os.path.join(d, "reference_subsample.npz"))
+    got = orc.unwarp_image_backward(mat, meta["xcenter"], meta["ycenter"], meta["list_fact"], order=1)
+    assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == meta["output_sha256_order1"]
+    assert np.array_equal(got[::7, ::7], sub["order1"])
