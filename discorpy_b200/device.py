@@ -253,6 +253,61 @@ def pinned_empty(shape, dtype=np.float32):
     return arr
 
 
+# Page-locking a caller's array in place.  A pageable source costs the host pipeline a staging
+# copy (64 MiB through a pool of host threads: ~1.7 ms on top of the 1.8 ms the pinned call
+# takes); page-locking 64 MiB costs ~10x that once, after which the DMA engine reads the caller's
+# pages directly.  So an array is registered the SECOND time the same buffer is seen (loops that
+# refill a preallocated frame buffer -- the usual acquisition pattern -- run at the pinned rate,
+# one-shot calls never pay for a registration), and unregistered when the array object dies.
+_seen_once = {}
+_registered = {}
+_reg_lock = threading.Lock()
+_REG_MIN_BYTES = 8 << 20
+_REG_MAX_BYTES = int(os.environ.get("DCB_REGISTER_BYTES", str(2 << 30)))
+
+
+def _unregister(addr):
+    with _reg_lock:
+        if _registered.pop(addr, None) is not None:
+            try:
+                _cabi.load().dcb_host_unregister(ctypes.c_void_p(addr))
+            except Exception:
+                pass
+
+
+def maybe_register(array):
+    """See above; ``array``: C-contiguous ndarray about to be read by a host-buffer entry point.
+    Returns True when its pages are (now) page-locked."""
+    if os.environ.get("DCB_REGISTER", "1") == "0":
+        return False
+    nbytes = array.nbytes
+    if nbytes < _REG_MIN_BYTES or not array.flags.c_contiguous or not array.flags.writeable:
+        return False
+    addr = array.ctypes.data
+    with _reg_lock:
+        if addr in _registered:
+            return _registered[addr] >= nbytes
+        if _seen_once.get(addr) != nbytes:
+            if len(_seen_once) > 64:
+                _seen_once.clear()
+            _seen_once[addr] = nbytes
+            return False
+        if sum(_registered.values()) + nbytes > _REG_MAX_BYTES:
+            return False
+        del _seen_once[addr]
+        try:
+            _cabi.call("dcb_host_register", ctypes.c_void_p(addr), nbytes)
+        except _cabi.DcbError:
+            return False                # e.g. pages that cannot be locked: keep staging
+        _registered[addr] = nbytes
+    try:
+        weakref.finalize(array, _unregister, addr)
+    except TypeError:
+        _unregister(addr)
+        return False
+    return True
+
+
 def pinned_copy(array):
     out = pinned_empty(np.shape(array), np.asarray(array).dtype)
     out[...] = array

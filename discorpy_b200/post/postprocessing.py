@@ -175,6 +175,8 @@ def unwarp_image_backward(mat, xcenter, ycenter, list_fact, order=1,
         opt = _opts(order, flags)
         _dev.ensure_init()
         out = _dev.pinned_empty((height, width), np.float32)
+        if src is mat:
+            _dev.maybe_register(src)      # a frame buffer seen before: page-lock it in place
         _cabi.call("dcb_unwarp_image_backward_host_f32", _vp(src.ctypes.data),
                    _vp(out.ctypes.data), height, width, width * 4, width * 4,
                    ctypes.byref(model), ctypes.byref(opt), config["bands"])

@@ -156,7 +156,7 @@ def test_chunk_rows_outside_the_reference_window():
         assert post._rows_leave_window(h, w, xc, yc, fact, a, b, y0, y1)
     cc = np.linspace(-200, 200, 9001).astype(np.float32)
     for n in (1, 2, 5, 30):
-        assert np.array_equal(post._reflect_coordinate(cc, n), orc.reflect_coordinate(cc, n))
+        assert np.array_equal(post._fold_coordinate(cc, n, "reflect"), orc.reflect_coordinate(cc, n))
     # the BASELINE config-4 model keeps every row inside its window
     f4 = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]
     assert not post._rows_leave_window(2560, 2560, 1283.4, 1275.9, f4, 100, 300,
