@@ -729,9 +729,9 @@ def bench_exchange(dcb, multigpu, post, comm, rank, world):
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant
 # kernel, from the committed `ncu --set full` capture (profiles/); None until
 # a capture exists for the current kernel.
-TRAFFIC_BYTES_PER_LAUNCH = 79433216 + 22320640
-TRAFFIC_SOURCE = ("profiles/r2/ncu_image_r2i_exact.txt: dram__bytes_read.sum 79.4 MB + "
-                  "dram__bytes_write.sum 22.3 MB of one launch (most of the 64 MiB output is "
+TRAFFIC_BYTES_PER_LAUNCH = 79762432 + 21441280
+TRAFFIC_SOURCE = ("profiles/r2/ncu_image_r2i_exact.txt: dram__bytes_read.sum 79.8 MB + "
+                  "dram__bytes_write.sum 21.4 MB of one launch (most of the 64 MiB output is "
                   "still dirty in the 126 MB L2 when the profiled launch ends)")
 # What the SM side of one launch costs at 100 % of each pipe (us), from the instruction mix of
 # the committed capture (profiles/r2/ncu_image_r2i_exact.txt: thread instructions per pixel by
@@ -741,7 +741,7 @@ def _colimit(ops_per_px, rate):
     return H * W / 148.0 / 1965.0 * ops_per_px / rate          # us
 
 
-COLIMIT = {"fp64_us": _colimit(18.6, 60.1), "xu_us": _colimit(2.9, 15.6),
+COLIMIT = {"fp64_us": _colimit(17.8, 60.1), "xu_us": _colimit(2.4, 15.6),
            "issue_us": _colimit(66.0, 128.0),
            "source": "profiles/r2/ncu_image_r2i_exact.txt instruction mix; pipe rates "
                      "profiles/r1/microbench_v1.txt"}

@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             // raw stage k % 4 doubles as the data buffer: the samplers wait on raw_full[k % 4];
             // the producer runs at most four tiles ahead of the slowest sampling warp (with two
             // stages the samplers waited 11 % of their time for copies issued only one tile
-            // earlier, profiles/r2/ncu_img_r2h_lerp32.txt)
+            // earlier, profiles/r2/ncu_image_r2h_lerp32_two_stages.txt)
             for (int k = 0; k < n; ++k) {
                 const int b = k & (NBUF - 1);
                 if (k >= NBUF) mbar_wait(&data_empty[b], (uint32_t)((k >> LOGB) - 1) & 1u);

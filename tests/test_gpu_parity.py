@@ -200,8 +200,10 @@ def test_perspective_map_index_route_and_mapping():
     x64 = rng.random(5000) * 420
     got = post._mapping(mat, x64, y64)
     assert np.array_equal(got, orc.sample(mat, y64, x64, 1))
-    with pytest.raises(NotImplementedError, match="outside the image"):
-        post._mapping(mat, x64 + 1000.0, y64)
+    # coordinates outside the image: SciPy's 'reflect' (what _mapping hands them to, :251)
+    from scipy.ndimage import map_coordinates
+    got = post._mapping(mat, x64 + 1000.0, y64)
+    assert np.array_equal(got, map_coordinates(mat, (y64, x64 + 1000.0), order=1, mode="reflect"))
 
 
 def test_stack_paths_against_oracle():
