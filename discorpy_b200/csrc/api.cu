@@ -557,7 +557,8 @@ static ImageKernelSel pick_image_kernel_nt(int order, int blend) {
         case DCB_BLEND_LERP32:
             return {remap_image_kernel<MAP, 1, DCB_BLEND_LERP32, NT, TH, MINB>, false, TH};
         default:
-            return {remap_image_kernel<MAP, 1, DCB_BLEND_EXACT, NT, TH, MINB>, true, TH};
+            return {remap_image_kernel<MAP, 1, DCB_BLEND_EXACT, NT, TH, MINB>,
+                    ImageKernelTraits<1, DCB_BLEND_EXACT>::kWide, TH};
     }
 }
 

@@ -76,6 +76,9 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 #ifndef DCB_IMG_LDS32
 #define DCB_IMG_LDS32 1
 #endif
+#ifndef DCB_IMG_EXACT_RAW
+#define DCB_IMG_EXACT_RAW 0
+#endif
 // output stores: streaming (evict-first) by default; -DDCB_IMG_STCS=0 for A/B builds
 #ifndef DCB_IMG_STCS
 #define DCB_IMG_STCS 1
@@ -502,7 +505,12 @@ template <int ORDER, int BLEND>
 struct ImageKernelTraits {
     // bilinear in fp64: sample from the widened tile; otherwise from the raw
     // float32 box (two stages, no widening pass)
-    static constexpr bool kWide = (ORDER == 1 && BLEND != DCB_BLEND_LERP32);
+    // (-DDCB_IMG_EXACT_RAW=1: the exact blend also samples the raw float32 box and converts its
+    // four taps per pixel itself -- no widening pass, no float64 tiles, four stages in flight.
+    // Measured 54.4 us against 53.3 us with the float64 tiles (profiles/r2/ab_exact_raw_r2n.txt:
+    // XU 40 % busy with 5 conversions per pixel, same 64 instructions per pixel), so off.)
+    static constexpr bool kWide = (ORDER == 1 && (BLEND == DCB_BLEND_LERP64 ||
+                                                  (BLEND == DCB_BLEND_EXACT && !DCB_IMG_EXACT_RAW)));
 };
 
 // float32 box in raw stage 0 -> float64 tile `buf` (exact); producer warp `part`
@@ -781,7 +789,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                         const double My = __hiloint2double((int)inf.y, 0);
                         const int khy = (int)inf.y - 0x80000;
                         const double Ky = __hiloint2double(khy, 0);
-                        uint32_t accb = 0xffffffffu;
+                        uint32_t accb = 0xffffffffu, tapmax = 0u;
                         // ODD: the tile holds values lerp_fma is not certified for -> SciPy's sum
                         // GENX: the x binade (shift, rounding constant, masks) from each pixel's own
                         // exponent instead of the tile's: 8 more integer operations per pixel
@@ -811,6 +819,25 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                                 }
                                 const uint32_t xi = nx >> shx, yi = ny >> shy;
                                 const uint32_t fx = nx & mkx, fy = ny & mky;
+                                if (!WIDE && BLEND != DCB_BLEND_LERP32) {
+                                    // fp64 blend from the raw float32 box: four conversions per pixel
+                                    const double tx = __dsub_rn(__hiloint2double(khx, (int)fx), Kx);   // exact
+                                    const double ty = __dsub_rn(__hiloint2double(khy, (int)fy), Ky);
+                                    const uint32_t qa = base_s + 4u * (yi * bw + xi);
+                                    float a, b, c, d;
+                                    asm("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(qa));
+                                    asm("ld.shared.f32 %0, [%1+4];" : "=f"(b) : "r"(qa));
+                                    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(c) : "r"(qa), "n"(4 * kImgBoxW));
+                                    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(d) : "r"(qa), "n"(4 * kImgBoxW + 4));
+                                    // a set sign bit, Inf or NaN among the taps: not what lerp_fma is
+                                    // certified for (largest bit pattern >= 0x7f800000)
+                                    tapmax = __vimax3_u32(tapmax, __float_as_uint(a), __float_as_uint(b));
+                                    tapmax = __vimax3_u32(tapmax, __float_as_uint(c), __float_as_uint(d));
+                                    const double sd = lerp_fma((double)a, (double)b, (double)c, (double)d, tx, ty);
+                                    accb = min(accb, cert_key(sd, kBlendCertAdd));
+                                    v[k] = __double2float_rn(sd);
+                                    continue;
+                                }
                                 if (!WIDE) {
                                     // fraction as a float: exponent 150 - sh puts its ulp at 2^-sh
                                     const float tx = __uint_as_float(e32x | fx) - __uint_as_float(e32x);
@@ -857,7 +884,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                                 sample4(std::false_type{}, std::true_type{});
                         }
                         // (a blend within 32 ulp64 of a rounding boundary: the exact row below)
-                        done = !__any_sync(0xffffffffu, accb < kBlendCertLim);
+                        done = !__any_sync(0xffffffffu, accb < kBlendCertLim || tapmax >= 0x7f800000u);
                         n_bfail += done ? 0u : 1u;
                     }
                 }
@@ -886,6 +913,11 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                         if (ORDER == 0) {
                             const int sel = idx + (tx >= 0.5f ? 1 : 0) + (ty >= 0.5f ? bw : 0);
                             v[k] = rawt[sel];
+                        } else if (!WIDE && BLEND != DCB_BLEND_LERP32) {
+                            const float *q = rawt + idx;
+                            const double a = q[0], b = q[1];
+                            const double c = q[bw], d = q[bw + 1];
+                            v[k] = finish_f64(blend_exact(a, b, c, d, (double)tx, (double)ty), p.rint);
                         } else if (!WIDE) {
                             const float *q = rawt + idx;
                             const float a = q[0], b = q[1];
@@ -923,7 +955,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                         }
 #pragma unroll
                         for (int k = 0; k < kCols; ++k) v[k] = __double2float_rn(sd[WIDE ? k : 0]);
-                    } else if (ORDER == 1 && p.rint) {
+                    } else if (ORDER == 1 && BLEND == DCB_BLEND_LERP32 && p.rint) {
 #pragma unroll
                         for (int k = 0; k < kCols; ++k) v[k] = finish_f32(v[k], 1);
                     }
