@@ -787,8 +787,6 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                         const int shy = (int)(inf.x >> 8) & 31;
                         const uint32_t mky = inf.z, e32y = inf.w;
                         const double My = __hiloint2double((int)inf.y, 0);
-                        const int khy = (int)inf.y - 0x80000;
-                        const double Ky = __hiloint2double(khy, 0);
                         uint32_t accb = 0xffffffffu, tapmax = 0u;
                         // ODD: the tile holds values lerp_fma is not certified for -> SciPy's sum
                         // GENX: the x binade (shift, rounding constant, masks) from each pixel's own
@@ -803,12 +801,11 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                                 const uint32_t mhx = GENX ? (hx & 0x7ff00000u) + 0x01d80000u : box.mhi_x;
                                 const uint32_t mkx = GENX ? (1u << shx) - 1u : mkx_t;
                                 const uint32_t e32x = GENX ? (uint32_t)(150 - shx) << 23 : e32x_t;
-                                const int khx = (int)mhx - 0x80000;
                                 const double Mx = __hiloint2double((int)mhx, 0);
-                                const double Kx = __hiloint2double(khx, 0);
                                 // round to the float32 grid: the low word is the coordinate in ulp32
-                                const uint32_t nx = (uint32_t)__double2loint(__dadd_rn(xq[k], Mx));
-                                const uint32_t ny = (uint32_t)__double2loint(__dadd_rn(yq[k], My));
+                                const double ux = __dadd_rn(xq[k], Mx), uy = __dadd_rn(yq[k], My);
+                                const uint32_t nx = (uint32_t)__double2loint(ux);
+                                const uint32_t ny = (uint32_t)__double2loint(uy);
                                 if (ORDER == 0) {
                                     const uint32_t xi = (nx + (1u << (shx - 1))) >> shx;
                                     const uint32_t yi = (ny + (1u << (shy - 1))) >> shy;
@@ -821,8 +818,8 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                                 const uint32_t fx = nx & mkx, fy = ny & mky;
                                 if (!WIDE && BLEND != DCB_BLEND_LERP32) {
                                     // fp64 blend from the raw float32 box: four conversions per pixel
-                                    const double tx = __dsub_rn(__hiloint2double(khx, (int)fx), Kx);   // exact
-                                    const double ty = __dsub_rn(__hiloint2double(khy, (int)fy), Ky);
+                                    const double tx = __dsub_rn(__hiloint2double(__double2hiint(ux), (int)fx), Mx);
+                                    const double ty = __dsub_rn(__hiloint2double(__double2hiint(uy), (int)fy), My);
                                     const uint32_t qa = base_s + 4u * (yi * bw + xi);
                                     float a, b, c, d;
                                     asm("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(qa));
@@ -853,8 +850,10 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                                     v[k] = fmaf(bot - top, ty, top);
                                     continue;
                                 }
-                                const double tx = __dsub_rn(__hiloint2double(khx, (int)fx), Kx);   // exact
-                                const double ty = __dsub_rn(__hiloint2double(khy, (int)fy), Ky);
+                                // fraction: the sum with its integer bits masked off, minus the rounding
+                                // constant (exact; the masked pair keeps the sum's own high word)
+                                const double tx = __dsub_rn(__hiloint2double(__double2hiint(ux), (int)fx), Mx);
+                                const double ty = __dsub_rn(__hiloint2double(__double2hiint(uy), (int)fy), My);
                                 const uint32_t qa = base_s + 8u * (yi * bw + xi);
                                 const double a = lds_f64<0>(qa), b = lds_f64<8>(qa);
                                 const double c = lds_f64<8 * kImgBoxW>(qa), d = lds_f64<8 * kImgBoxW + 8>(qa);
