@@ -522,7 +522,10 @@ struct ImageParams;
 __device__ __forceinline__ bool widen_part(const ImageParams &p, unsigned char *smem, int buf,
                                            int part, int lane);
 
-constexpr int kRawStages = 4;     // !WIDE: raw float32 stages = tile buffers
+#ifndef DCB_IMG_STAGES
+#define DCB_IMG_STAGES 4
+#endif
+constexpr int kRawStages = DCB_IMG_STAGES;   // !WIDE: raw float32 stages = tile buffers (2 or 4)
 constexpr int kRecRing = 3;       // WIDE: plan records in flight (tiles j-1, j being sampled, j+1 landing)
 constexpr int kImgProducers = 2;                             // producer warps
 constexpr int kImgThreads = kThreads + 32 * kImgProducers;   // 8 sampling warps + the producers
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     constexpr bool PATCH = (MAP == MAP_RADIAL) && kImgBoxW > 0;   // the patch path exists
     constexpr int RPW = TH / kWarps;  // rows per sampling warp and tile
     constexpr int NBUF = WIDE ? 2 : kRawStages;   // tile buffers the samplers read from
-    constexpr int LOGB = WIDE ? 1 : 2;
+    constexpr int LOGB = (WIDE || kRawStages == 2) ? 1 : 2;
     static_assert((1 << LOGB) == NBUF, "buffer count");
     constexpr int NREC = WIDE ? kRecRing : NBUF;
     constexpr uint32_t kRecBytes = (uint32_t)sizeof(TilePlan<TH>);
