@@ -15,7 +15,7 @@ import discorpy_b200 as dcb                                    # noqa: E402
 from discorpy_b200 import _cabi                                # noqa: E402
 import discorpy_b200.post.postprocessing as post               # noqa: E402
 
-PEAK = 6542.1
+PEAK = 6451.5
 
 
 def timed(fn, reps=10):

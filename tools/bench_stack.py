@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--orders", default="1")
     args = ap.parse_args()
     dcb.set_device(0)
-    peak = 6542.1
+    peak = 6451.5
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
