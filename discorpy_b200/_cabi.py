@@ -118,6 +118,7 @@ SIGNATURES = {
     "dcb_launch_count_reset": [],
     "dcb_last_plan": [ctypes.POINTER(_i)] * 5,
     "dcb_image_stats": [_i, ctypes.POINTER(_u64), _i],
+    "dcb_image_timeline": [ctypes.POINTER(_u64), _i],
     "dcb_plan_cache_clear": [ctypes.POINTER(_u64)],
     "dcb_mg_unique_id": [_vp, ctypes.POINTER(_i)],
     "dcb_mg_init": [_vp, _i, _i],

@@ -540,7 +540,26 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
     void *transient = nullptr;
     rc = get_image_plan(map_kind, TH, p, stream, &transient);
     if (rc != DCB_OK) return rc;
-    sel.kern<<<grid, kImgThreads, smem, stream>>>(p, tmap);
+    {
+        // programmatic stream serialization: see the griddepcontrol pair in remap_image_kernel
+        // (DCB_IMG_PDL=0 launches the ordinary way, for A/B runs)
+        static const bool pdl = [] {
+            const char *e = getenv("DCB_IMG_PDL");
+            return !(e != nullptr && e[0] == '0');
+        }();
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kImgThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, sel.kern, (const ImageParams)p, (const CUtensorMap)tmap));
+    }
     CUDA_TRY(cudaGetLastError());
     if (transient != nullptr) CUDA_TRY(cudaFreeAsync(transient, stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -587,8 +606,12 @@ static ImageKernelSel pick_image_kernel(int order, int blend, int nterms, int fl
 #define DCB_NT(N) \
     case N:       \
         return pick_image_kernel_nt<MAP, N, kImgTileH, kImgMinBlocks>(order, blend);
+#ifdef DCB_NT_ONLY   // quick A/B builds (tools/build_ab.sh): one compile-time Horner length
+            DCB_NT(DCB_NT_ONLY)
+#else
             DCB_NT(1) DCB_NT(2) DCB_NT(3) DCB_NT(4) DCB_NT(5) DCB_NT(6) DCB_NT(7) DCB_NT(8)
             DCB_NT(9) DCB_NT(10)
+#endif
 #undef DCB_NT
             default:
                 break;
@@ -1481,11 +1504,14 @@ int dcb_plan_cache_clear(uint64_t *plans_built) {
     return DCB_OK;
 }
 
+static unsigned long long *g_image_stats_buf = nullptr;
+constexpr size_t kImageStatsWords = 8 + 8 * (size_t)kTimelineCtas + (size_t)kLogCtas * 10 * kLogEvents;
+
 int dcb_image_stats(int enable, uint64_t *out, int reset) {
-    static unsigned long long *buf = nullptr;
+    unsigned long long *&buf = g_image_stats_buf;
     if (enable && buf == nullptr) {
-        CUDA_TRY(cudaMalloc((void **)&buf, 8 * sizeof(unsigned long long)));
-        CUDA_TRY(cudaMemset(buf, 0, 8 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc((void **)&buf, kImageStatsWords * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(buf, 0, kImageStatsWords * sizeof(unsigned long long)));
     }
     if (buf != nullptr && (out != nullptr || reset)) {
         CUDA_TRY(cudaDeviceSynchronize());
@@ -1496,6 +1522,21 @@ int dcb_image_stats(int enable, uint64_t *out, int reset) {
         memset(out, 0, 8 * sizeof(uint64_t));
     }
     g_image_stats = enable ? buf : nullptr;
+    return DCB_OK;
+}
+
+int dcb_image_timeline(uint64_t *out, int nctas) {
+    // nctas < 0: the per-warp event log of the first CTAs instead (kLogCtas x 10 warps x kLogEvents)
+    REQUIRE(out != nullptr && nctas >= -1 && nctas <= kTimelineCtas, "bad arguments");
+    const size_t words = nctas < 0 ? (size_t)kLogCtas * 10 * kLogEvents : 8 * (size_t)nctas;
+    const size_t first = nctas < 0 ? 8 + 8 * (size_t)kTimelineCtas : 8;
+    if (g_image_stats_buf == nullptr) {
+        memset(out, 0, words * sizeof(uint64_t));
+        return DCB_OK;
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out, g_image_stats_buf + first, words * sizeof(uint64_t),
+                        cudaMemcpyDeviceToHost));
     return DCB_OK;
 }
 

@@ -79,6 +79,11 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 #ifndef DCB_IMG_EXACT_RAW
 #define DCB_IMG_EXACT_RAW 0
 #endif
+// Ablations of the patch path for attribution runs (A/B builds only, results are WRONG):
+// 1 no stores, 2 every tap read from one address, 4 F = c0 (no Horner chain), 8 no blend (first tap)
+#ifndef DCB_ABL
+#define DCB_ABL 0
+#endif
 // output stores: streaming (evict-first) by default; -DDCB_IMG_STCS=0 for A/B builds
 #ifndef DCB_IMG_STCS
 #define DCB_IMG_STCS 1
@@ -183,6 +188,22 @@ struct __align__(16) RowPatch {   // one per tile row (64 bytes)
     uint32_t mky;       // (1 << shy) - 1
     uint32_t e32y;      // (150 - shy) << 23: float exponent whose ulp is 2^-shy
 };
+
+// A non-negative finite float32 v with bit pattern u, read as the 64-bit integer u * 2^29 (high word
+// u >> 3, low word u << 29), IS the double v * 2^-896: the float's exponent field lands in the low
+// eight bits of the double's, its fraction in the top 23 bits of the double's fraction -- exactly,
+// for zero, denormals (they become denormal doubles of the same relative value) and normals alike.
+// One IMAD.WIDE on the FMA pipe instead of an F2F on the 16-lane XU pipe, no special cases; what
+// it does not cover is a set sign bit, Inf and NaN (callers test the largest bit pattern).  Sums
+// and products of such values by weights in [0, 1] are the true results times 2^-896 with the
+// same roundings (a power-of-two scale commutes with every rounding; where a scaled intermediate
+// is a denormal double its error is at most 2^-1075 absolute, i.e. 2^-179 of the unscaled value,
+// far inside the blend certificate's 32 ulp).
+__device__ __forceinline__ double scaled_f64(uint32_t u) {
+    unsigned long long w;
+    asm("mul.wide.u32 %0, %1, 536870912;" : "=l"(w) : "r"(u));
+    return __longlong_as_double((long long)w);
+}
 
 // high word of 1.5 * 2^(52 - sh); the same constant with mantissa 1.0 is 2^(52 - sh) (0x80000 less)
 __device__ __forceinline__ uint32_t magic_hi(int sh) { return ((uint32_t)(1075 - sh) << 20) | 0x80000u; }
@@ -542,6 +563,21 @@ __host__ __device__ constexpr size_t image_tail_bytes(int th, bool wide) {
     return 96 + (wide ? kRecRing : kRawStages) * image_rec_bytes(th);
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr int kLogCtas = 4, kLogEvents = 64;   // per-warp event log of the first CTAs (timeline builds)
+#ifdef DCB_IMG_TIMELINE
+#define DCB_LOG(idx) \
+    do { if (p.stats != nullptr && blockIdx.x < kLogCtas && lane == 0 && (idx) < kLogEvents) \
+        p.stats[8 + 8 * 1024 + ((blockIdx.x * 10 + warp) * kLogEvents) + (idx)] = global_ns(); } while (0)
+#else
+#define DCB_LOG(idx) do { } while (0)
+#endif
+constexpr int kTimelineCtas = 1024;   // diagnostics: p.stats[8 + 8 b ..] = start, first tile, end, SM, waits of CTA b
+
 // 1-D bulk copy global -> shared, completion on an mbarrier (16-byte aligned, size % 16 == 0)
 __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes,
                                           uint64_t *bar) {
@@ -603,13 +639,32 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     // row path): tiles dealt round-robin, otherwise whole CTAs own nothing but slow tiles -- the
     // config-1 geometry (19.9 % clipped) took 166 us instead of 100, the config-3 perspective 93
     // instead of 70 (profiles/r1/bench_tile_dealing.txt).
+    //
+    // The contiguous ranges are cut in units of one ROW GROUP (kWarps rows, one per sampling warp;
+    // RPW groups per tile), not of whole tiles: 4096 tiles over 296 CTAs are 13.84 tiles each, and
+    // with whole tiles the CTAs holding 13 sat idle for a tile's time (3.2 us of 53, the per-CTA
+    // timeline in profiles/r2/timeline_r2t.txt).  The first and the last tile of a range are
+    // sampled in part (row groups g_first.. and ..g_last); the neighbouring CTA stages the same box.
     const int tstep = p.deal ? (int)gridDim.x : 1;
-    const int t0 = p.deal ? (int)blockIdx.x : (int)((long long)blockIdx.x * p.ntiles / gridDim.x);
-    const int n = p.deal ? (p.ntiles - t0 + tstep - 1) / tstep
-                         : (int)((long long)(blockIdx.x + 1) * p.ntiles / gridDim.x) - t0;
+    int t0, n, g_first = 0, g_last = RPW;
+    if (p.deal) {
+        t0 = (int)blockIdx.x;
+        n = (p.ntiles - t0 + tstep - 1) / tstep;
+    } else {
+        const long long units = (long long)p.ntiles * RPW;
+        const long long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+        t0 = (int)(u0 / RPW);
+        g_first = (int)(u0 - (long long)t0 * RPW);
+        const int tl = (int)((u1 - 1) / RPW);
+        n = u1 > u0 ? tl - t0 + 1 : 0;
+        g_last = (int)(u1 - 1 - (long long)tl * RPW) + 1;
+    }
     auto tile_of = [&](int k) -> int { return t0 + k * tstep; };   // local tile k -> tile index
 
     if (threadIdx.x == 0) {
+#ifdef DCB_IMG_TIMELINE
+        if (p.stats != nullptr && blockIdx.x < kTimelineCtas) p.stats[8 + 8 * blockIdx.x] = global_ns();
+#endif
         for (int b = 0; b < 4; ++b) {
             mbar_init(&raw_full[b], 1);
             mbar_init(&data_empty[b], kWarps);
@@ -622,6 +677,13 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         if (staged) tma_prefetch_desc(&tmap);
     }
     __syncthreads();
+    // Programmatic dependent launch (api.cu launches with programmatic stream serialization): the
+    // CTAs of the next launch in the stream may take the SM slots this grid's CTAs free, and run
+    // everything above, before this grid has finished; nothing below -- no read of the plan or the
+    // source, no store -- happens before the preceding grid has completed and flushed.  Without
+    // the launch attribute both instructions do nothing.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp > kWarps) {
         // ====================== second producer warp: widening only =====================
@@ -630,14 +692,17 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             for (int j = 0; j < n; ++j) {
                 const int b = j & 1;
                 if (j >= 2) mbar_wait(&data_empty[b], (uint32_t)((j >> 1) - 1) & 1u);
+                DCB_LOG(3 * j);
                 asm volatile("bar.sync 1, 64;" ::: "memory");   // (A) buffer b is free
                 // tile j's record and box (if staged) have landed
                 mbar_wait(&raw_full[0], nraw & 1u);
                 ++nraw;
+                DCB_LOG(3 * j + 1);
                 if (rec[j % NREC].box.use) {
                     const bool o = widen_part(p, smem, b, 1, lane);
                     if (PATCH && __any_sync(0xffffffffu, o) && lane == 0) atomicOr(&odd[b], 1u);
                 }
+                DCB_LOG(3 * j + 2);
                 asm volatile("bar.sync 1, 64;" ::: "memory");   // (B) both halves written, raw free
             }
         }
@@ -662,14 +727,17 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             for (int j = 0; j < n; ++j) {
                 const int b = j & 1;
                 if (j >= 2) mbar_wait(&data_empty[b], (uint32_t)((j >> 1) - 1) & 1u);
+                DCB_LOG(3 * j);
                 if (PATCH && lane == 0) odd[b] = 0u;   // buffer b is free: reset its flag
                 asm volatile("bar.sync 1, 64;" ::: "memory");   // (A)
                 mbar_wait(&raw_full[0], nraw & 1u);
                 ++nraw;
+                DCB_LOG(3 * j + 1);
                 if (rec[j % NREC].box.use) {
                     const bool o = widen_part(p, smem, b, 0, lane);
                     if (PATCH && __any_sync(0xffffffffu, o) && lane == 0) atomicOr(&odd[b], 1u);
                 }
+                DCB_LOG(3 * j + 2);
                 asm volatile("bar.sync 1, 64;" ::: "memory");   // (B) float64 tile complete, raw free
                 if (lane == 0) {
                     // (the samplers have left tile j-2, whose record slot tile j+1 takes over)
@@ -685,6 +753,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             for (int k = 0; k < n; ++k) {
                 const int b = k & (NBUF - 1);
                 if (k >= NBUF) mbar_wait(&data_empty[b], (uint32_t)((k >> LOGB) - 1) & 1u);
+                DCB_LOG(k);
                 if (lane == 0) issue(k, b, b);
             }
         }
@@ -704,9 +773,24 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         asm volatile("" : "+d"(tau[k]));
     }
 
+#ifdef DCB_IMG_TIMELINE   // -DDCB_IMG_TIMELINE builds only (tools/timeline_probe.py)
+    unsigned long long dbg_t = 0, dbg_wait = 0, dbg_wmax = 0;
+#endif
     for (int i = 0; i < n; ++i) {
         // tile i is ready: WIDE -> float64 tile i&1 written by the producer; !WIDE -> raw stage landed
         mbar_wait(WIDE ? &data_full[i & 1] : &raw_full[i & (NBUF - 1)], (uint32_t)(i >> LOGB) & 1u);
+        DCB_LOG(2 * i);
+#ifdef DCB_IMG_TIMELINE
+        if (p.stats != nullptr && threadIdx.x == 0 && blockIdx.x < kTimelineCtas) {
+            const unsigned long long now = global_ns();
+            if (i == 0) {
+                p.stats[8 + 8 * blockIdx.x + 1] = now;
+            } else {   // time warp 0 waited for tile i after finishing tile i - 1
+                dbg_wait += now - dbg_t;
+                dbg_wmax = max(dbg_wmax, now - dbg_t);
+            }
+        }
+#endif
         const TilePlan<TH> &trec = rec[i % NREC];
         const TileBox box = trec.box;
         const int tyi = box.pad[1];
@@ -720,8 +804,11 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         // ---- sample tile i ---------------------------------------------------------
         {
             const int x_base = txi * kTileW + lane;
-            const int y_base = p.row0 + tyi * TH + warp * RPW;
-            const int nrow = min(RPW, y_end - y_base);  // warp-uniform, may be <= 0
+            // this warp's rows of the tile: warp + kWarps g for the row groups g of this CTA's share
+            const int ga = i == 0 ? g_first : 0, gb = i == n - 1 ? g_last : RPW;
+            const int y_base = p.row0 + tyi * TH + ga * kWarps + warp;
+            const int rows_left = y_end - y_base;   // rows y_base + kWarps j exist for kWarps j < rows_left
+            const int nrow = min(gb - ga, (rows_left + kWarps - 1) / kWarps);  // warp-uniform, may be <= 0
             // bits(2^23 + n) - magic = n - box origin
             const int magic_x = 0x4B000000 + box.bx0, magic_y = 0x4B000000 + box.by0;
             // fast-path window: footprint inside the box and strictly inside the image
@@ -745,7 +832,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             const uint32_t org = (uint32_t)(box.by0 * bw + box.bx0);
             const uint32_t base_s = (WIDE ? wide_s : smem_u32(rawt)) - (WIDE ? 8u : 4u) * org;
             const bool tile_odd = WIDE && BLEND == DCB_BLEND_EXACT && (odd[sb] != 0u);
-            const RowPatch *prow = trec.rows + warp * RPW;
+            const RowPatch *prow = trec.rows + ga * kWarps + warp;
             unsigned n_bfail = 0;   // diagnostics, see p.stats
 #ifndef DCB_IMG_UNROLL
 #define DCB_IMG_UNROLL 1
@@ -763,27 +850,31 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             // instead of this static split, were measured: 61.5 / 59.4 / 49.4 us against 57.4 / 53.8 /
             // 44.0 -- the atomic and the lost incremental row state cost more than the 8 % the
             // warps wait for each other at tile boundaries.)
-            for (int j = 0; j < nrow; ++j, yd += 1.0, orow += p.dst_pitch) {
+            for (int j = 0; j < nrow; ++j, yd += (double)kWarps, orow += kWarps * p.dst_pitch, prow += kWarps) {
                 float v[kCols];
                 bool done = false;
                 if constexpr (PATCH) if (shx_t != 0) {
                     // ------------------- the patch path (see RowPatch) -------------------
-                    const uint4 inf = *reinterpret_cast<const uint4 *>(&prow[j].info);
+                    const uint4 inf = *reinterpret_cast<const uint4 *>(&prow->info);
                     // bits 0..3: verified with the tile's x binade; bits 4..7: verified with the
                     // x binade taken per pixel (rows crossing a power of two in x)
                     if ((inf.x & 0xfu) == 0xfu || (inf.x & 0xf0u) == 0xf0u) {
-                        const double2 c01 = *reinterpret_cast<const double2 *>(&prow[j].c[0]);
-                        const double2 c23 = *reinterpret_cast<const double2 *>(&prow[j].c[2]);
-                        const double2 c45 = *reinterpret_cast<const double2 *>(&prow[j].c[4]);
+                        const double2 c01 = *reinterpret_cast<const double2 *>(&prow->c[0]);
+                        const double2 c23 = *reinterpret_cast<const double2 *>(&prow->c[2]);
+                        const double2 c45 = *reinterpret_cast<const double2 *>(&prow->c[4]);
                         const double yu = __dsub_rn(yd, p.rad.yc);
                         double xq[kCols], yq[kCols];
 #pragma unroll
                         for (int k = 0; k < kCols; ++k) {
                             double f = fma(c45.y, tau[k], c45.x);
+                            if (DCB_ABL & 4) {
+                                f = c01.x + c45.y;
+                            } else {
                             f = fma(f, tau[k], c23.y);
                             f = fma(f, tau[k], c23.x);
                             f = fma(f, tau[k], c01.y);
                             f = fma(f, tau[k], c01.x);
+                            }
                             xq[k] = fma(f, ev.xu[k], p.rad.xc);
                             yq[k] = fma(f, yu, p.rad.yc);
                         }
@@ -819,6 +910,41 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                                 }
                                 const uint32_t xi = nx >> shx, yi = ny >> shy;
                                 const uint32_t fx = nx & mkx, fy = ny & mky;
+                                if (!WIDE && BLEND == DCB_BLEND_EXACT && DCB_IMG_EXACT_RAW == 2) {
+                                    // The exact blend in the SCALED domain (see scaled_f64): taps are
+                                    // widened by one integer multiply-wide each (no conversion, no
+                                    // float64 tile), the certified FMA blend runs on v * 2^-896, and the
+                                    // float32 result is the sum's bit pattern shifted back with a
+                                    // half-ulp added -- the certificate excludes ties, and the float32
+                                    // rounding boundary sits at bit 28 of the low word whether the
+                                    // result is a float32 normal or denormal.
+                                    const double tx = __dsub_rn(__hiloint2double(__double2hiint(ux), (int)fx), Mx);
+                                    const double ty = __dsub_rn(__hiloint2double(__double2hiint(uy), (int)fy), My);
+                                    const uint32_t qa = (DCB_ABL & 2) ? base_s + 4u * (org + (yi & 1u))
+                                                                      : base_s + 4u * (yi * bw + xi);
+                                    uint32_t a, b, c, d;
+                                    asm("ld.shared.b32 %0, [%1];" : "=r"(a) : "r"(qa));
+                                    if (DCB_ABL & 8) {
+                                        tapmax = max(tapmax, a ^ (uint32_t)__double2loint(tx) ^ (uint32_t)__double2loint(ty));
+                                        v[k] = __uint_as_float(a);
+                                        continue;
+                                    }
+                                    asm("ld.shared.b32 %0, [%1+4];" : "=r"(b) : "r"(qa));
+                                    asm("ld.shared.b32 %0, [%1+%2];" : "=r"(c) : "r"(qa), "n"(4 * kImgBoxW));
+                                    asm("ld.shared.b32 %0, [%1+%2];" : "=r"(d) : "r"(qa), "n"(4 * kImgBoxW + 4));
+                                    // a set sign bit, Inf or NaN among the taps: the exact row below
+                                    tapmax = __vimax3_u32(tapmax, a, b);
+                                    tapmax = __vimax3_u32(tapmax, c, d);
+                                    const double sd = lerp_fma(scaled_f64(a), scaled_f64(b), scaled_f64(c),
+                                                               scaled_f64(d), tx, ty);
+                                    // + half a float32 ulp; the low 29 bits of the sum are then the
+                                    // distance from the tie (mod 2^29): near 0 or 2^29 = not certified
+                                    const unsigned long long r =
+                                        (unsigned long long)__double_as_longlong(sd) + 0x10000000ull;
+                                    accb = min(accb, ((uint32_t)r << 3) + 8u * 32u);
+                                    v[k] = __uint_as_float((uint32_t)(r >> 29));
+                                    continue;
+                                }
                                 if (!WIDE && BLEND != DCB_BLEND_LERP32) {
                                     // fp64 blend from the raw float32 box: four conversions per pixel
                                     const double tx = __dsub_rn(__hiloint2double(__double2hiint(ux), (int)fx), Mx);
@@ -972,7 +1098,11 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                                                               p.yorg, p.ylast, p.rint);
                 }
                 }
-                if (FULL) {
+                if (DCB_ABL & 1) {
+#pragma unroll
+                    for (int k = 0; k < kCols; ++k)
+                        if (__float_as_uint(v[k]) == 0x7fc12345u) DCB_IMG_STORE(orow + 32 * k, v[k]);
+                } else if (FULL) {
 #pragma unroll
                     for (int k = 0; k < kCols; ++k) DCB_IMG_STORE(orow + 32 * k, v[k]);
                 } else {
@@ -993,7 +1123,22 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         // this warp is done with buffer i&1 (and with its plan record)
         __syncwarp();
         if (lane == 0) mbar_arrive(&data_empty[i & (NBUF - 1)]);
+        DCB_LOG(2 * i + 1);
+#ifdef DCB_IMG_TIMELINE
+        if (p.stats != nullptr && threadIdx.x == 0) dbg_t = global_ns();
+#endif
     }
+#ifdef DCB_IMG_TIMELINE
+    if (p.stats != nullptr && threadIdx.x == 0 && blockIdx.x < kTimelineCtas) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long *q = p.stats + 8 + 8 * blockIdx.x;
+        q[2] = global_ns();
+        q[3] = (unsigned long long)smid | ((unsigned long long)n << 32);
+        q[4] = dbg_wait;
+        q[5] = dbg_wmax;
+    }
+#endif
 }
 
 __device__ __forceinline__ bool widen_part(const ImageParams &p, unsigned char *smem, int buf,

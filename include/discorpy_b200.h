@@ -336,6 +336,15 @@ int dcb_plan_cache_clear(uint64_t *plans_built);
  * reserved.  reset != 0 clears the counters after reading. */
 int dcb_image_stats(int enable, uint64_t *out, int reset);
 
+/* Timeline of the LAST single-image launch made while dcb_image_stats counting was on: for CTA b
+ * (b < nctas <= 1024) out[8 b + 0..5] = %globaltimer (ns) at CTA start, when its first tile was
+ * ready to be sampled, when its first sampling warp finished its last tile,
+ * (SM id | tiles of this CTA << 32), the time that warp waited for later tiles in total and the
+ * longest such wait (ns); [6], [7] reserved.  nctas = -1: the per-warp event log of the first four
+ * CTAs instead (4 x 10 x 64 time stamps, -DDCB_IMG_TIMELINE builds).  Diagnostics behind
+ * profiles/r2/timeline_*.txt; an ordinary build reports zeros. */
+int dcb_image_timeline(uint64_t *out, int nctas);
+
 /* Device self-test of the custom fp64 square root used by the radial kernels
  * (probe points, Z-stack geometry) against IEEE sqrt on n pseudo-random inputs; *mismatch receives the number
  * of inputs whose result differs from the correctly rounded one. */
