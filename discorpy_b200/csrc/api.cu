@@ -315,7 +315,7 @@ static bool map_clips_at_border(const ImageParams &p, int map_kind) {
 // ---------------------------------------------------------------------------
 namespace {
 struct PlanKey {
-    int device, map_kind, th, H, W, row0, nrows, yorg, ylast, bw, bh, fast, n;
+    int device, map_kind, th, H, W, row0, nrows, yorg, ylast, bw, bh, fast, n, grid, nstatic;
     double xc, yc, a[DCB_MAX_TERMS], c[8];
 };
 struct PlanEntry {
@@ -331,20 +331,40 @@ uint64_t g_plan_clock = 0;
 size_t g_plan_bytes = 0;
 std::atomic<uint64_t> g_plan_builds{0};
 
-typedef void (*PlanKernel)(const ImageParams, void *, unsigned long long *);
-template <int MAP, int TH>
-void launch_plan_kernel(const ImageParams &p, void *out, unsigned long long *stats, cudaStream_t st) {
-    image_plan_kernel<MAP, TH><<<p.ntiles, kThreads, 0, st>>>(
-        p, reinterpret_cast<TilePlan<TH> *>(out), stats);
+// Plan memory: TilePlan<TH>[ntiles] | int2 boxes[ntiles] | int starts[grid + 1] | unsigned cost[ntiles]
+struct PlanLayout {
+    size_t boxes, starts, cost, bytes;
+};
+PlanLayout plan_layout(int th, int ntiles, int grid) {
+    PlanLayout l;
+    l.boxes = (size_t)ntiles * image_rec_bytes(th);
+    l.starts = l.boxes + (size_t)ntiles * sizeof(int2);
+    l.cost = (l.starts + (size_t)(grid + 1) * sizeof(int) + 15) / 16 * 16;
+    l.bytes = l.cost + (size_t)ntiles * sizeof(unsigned);
+    return l;
 }
-void launch_plan(int map_kind, int th, const ImageParams &p, void *out, unsigned long long *stats,
-                 cudaStream_t st) {
+template <int MAP, int TH>
+void launch_plan_kernel(const ImageParams &p, void *out, const PlanLayout &l,
+                        unsigned long long *stats, cudaStream_t st) {
+    char *base = reinterpret_cast<char *>(out);
+    image_plan_kernel<MAP, TH><<<p.ntiles, kThreads, 0, st>>>(
+        p, reinterpret_cast<TilePlan<TH> *>(out), reinterpret_cast<int2 *>(base + l.boxes),
+        reinterpret_cast<unsigned *>(base + l.cost), stats);
+}
+// builds the plan of launch p (p.ntiles tiles, `grid` CTAs, p.nstatic statically split tiles)
+void launch_plan(int map_kind, int th, const ImageParams &p, int grid, void *out,
+                 unsigned long long *stats, cudaStream_t st) {
+    const PlanLayout l = plan_layout(th, p.ntiles, grid);
     if (map_kind == MAP_RADIAL)
-        th == 32 ? launch_plan_kernel<MAP_RADIAL, 32>(p, out, stats, st)
-                 : launch_plan_kernel<MAP_RADIAL, 16>(p, out, stats, st);
+        th == 32 ? launch_plan_kernel<MAP_RADIAL, 32>(p, out, l, stats, st)
+                 : launch_plan_kernel<MAP_RADIAL, 16>(p, out, l, stats, st);
     else
-        th == 32 ? launch_plan_kernel<MAP_PERSP, 32>(p, out, stats, st)
-                 : launch_plan_kernel<MAP_PERSP, 16>(p, out, stats, st);
+        th == 32 ? launch_plan_kernel<MAP_PERSP, 32>(p, out, l, stats, st)
+                 : launch_plan_kernel<MAP_PERSP, 16>(p, out, l, stats, st);
+    char *base = reinterpret_cast<char *>(out);
+    image_plan_ranges_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const unsigned *>(base + l.cost),
+                                                 p.nstatic, grid,
+                                                 reinterpret_cast<int *>(base + l.starts));
 }
 size_t plan_cache_limit() {
     static size_t lim = [] {
@@ -365,19 +385,50 @@ bool plan_cache_enabled() {
 
 static unsigned long long *g_image_stats_fwd();
 
+// Counters of the single-image kernel's tile pool: each launch takes the next of 1024 slots of its
+// device (two words, zero when the launch starts; the last CTA of a launch zeroes them again), so
+// launches in flight on different streams never share one.
+static unsigned *g_sched_slots[64];
+static std::atomic<unsigned> g_sched_next{0};
+static std::mutex g_sched_mu;
+constexpr int kSchedSlots = 1024;
+static int image_sched_slot(unsigned **out) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(DCB_ERR_ARG, "device index %d out of range", dev);
+    {
+        std::lock_guard<std::mutex> lk(g_sched_mu);
+        if (g_sched_slots[dev] == nullptr) {
+            unsigned *d = nullptr;
+            CUDA_TRY(cudaMalloc((void **)&d, kSchedSlots * 2 * sizeof(unsigned)));
+            CUDA_TRY(cudaMemset(d, 0, kSchedSlots * 2 * sizeof(unsigned)));
+            g_sched_slots[dev] = d;
+        }
+    }
+    *out = g_sched_slots[dev] + 2 * (g_sched_next.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
+    return DCB_OK;
+}
+
 // Finds or builds the plan of this launch on `stream`; *transient receives a buffer the caller
 // must release with cudaFreeAsync after the launch (cache disabled), else NULL.
-static int get_image_plan(int map_kind, int th, ImageParams &p, cudaStream_t stream,
+static int get_image_plan(int map_kind, int th, ImageParams &p, int grid, cudaStream_t stream,
                           void **transient) {
     *transient = nullptr;
-    const size_t bytes = (size_t)p.ntiles * image_rec_bytes(th);
+    const PlanLayout lay = plan_layout(th, p.ntiles, grid);
+    const size_t bytes = lay.bytes;
+    p.plan_ready = 0;
+    auto bind = [&](void *d) {
+        p.plan = d;
+        p.plan_boxes = reinterpret_cast<const int2 *>(reinterpret_cast<char *>(d) + lay.boxes);
+        p.plan_starts = reinterpret_cast<const int *>(reinterpret_cast<char *>(d) + lay.starts);
+    };
     if (!plan_cache_enabled()) {
         void *d = nullptr;
         CUDA_TRY(cudaMallocAsync(&d, bytes, stream));
-        launch_plan(map_kind, th, p, d, g_image_stats_fwd(), stream);
+        launch_plan(map_kind, th, p, grid, d, g_image_stats_fwd(), stream);
         CUDA_TRY(cudaGetLastError());
         g_plan_builds.fetch_add(1, std::memory_order_relaxed);
-        p.plan = d;
+        bind(d);
         *transient = d;
         return DCB_OK;
     }
@@ -387,6 +438,7 @@ static int get_image_plan(int map_kind, int th, ImageParams &p, cudaStream_t str
     key.map_kind = map_kind, key.th = th, key.H = p.H, key.W = p.W, key.row0 = p.row0;
     key.nrows = p.nrows, key.yorg = p.yorg, key.ylast = p.ylast, key.bw = p.bw, key.bh = p.bh;
     key.fast = p.fast;
+    key.grid = grid, key.nstatic = p.nstatic;
     if (map_kind == MAP_RADIAL) {
         key.n = p.rad.n, key.xc = p.rad.xc, key.yc = p.rad.yc;
         memcpy(key.a, p.rad.a, sizeof(key.a));
@@ -415,7 +467,7 @@ static int get_image_plan(int map_kind, int th, ImageParams &p, cudaStream_t str
             cudaFree(e.dptr);
             return fail(DCB_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(ce));
         }
-        launch_plan(map_kind, th, p, e.dptr, g_image_stats_fwd(), stream);
+        launch_plan(map_kind, th, p, grid, e.dptr, g_image_stats_fwd(), stream);
         ce = cudaGetLastError();
         if (ce == cudaSuccess) ce = cudaEventRecord(e.ready, stream);
         if (ce != cudaSuccess) {
@@ -433,8 +485,10 @@ static int get_image_plan(int map_kind, int th, ImageParams &p, cudaStream_t str
         else
             CUDA_TRY(cudaStreamWaitEvent(stream, it->second.ready, 0));
     }
+    // complete before this launch is enqueued: the kernel may read it ahead of its grid dependency
+    p.plan_ready = it->second.ready_done ? 1 : 0;
     it->second.last_use = ++g_plan_clock;
-    p.plan = it->second.dptr;
+    bind(it->second.dptr);
     return DCB_OK;
 }
 
@@ -534,11 +588,31 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)sel.kern,
-                                                           kImgThreads, smem));
+                                                           image_threads(sel.wide), smem));
     if (occ < 1) return fail(DCB_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
-    const int grid = (int)std::min<long long>(ntiles, (long long)occ * props.sm_count);
+    // Tile scheduling (see remap_image_kernel): a static range per CTA for most of the tiles, a pool
+    // of 2.5 tiles per CTA claimed dynamically at the end, the last tile per CTA of it in halves.
+    // Uneven tiles (clipped regions, tiles that will not fit the box): everything is pooled.
+    const long long slots = (long long)occ * props.sm_count;
+    const int rpw = TH / kWarps;
+    // DCB_IMG_POOL="pool,halves,depth" (tenths of a tile per CTA, tenths, units) for A/B runs
+    static const struct PoolCfg { int pool10 = 25, halves10 = 10, depth = 3; } pc = [] {
+        PoolCfg c;
+        if (const char *e = getenv("DCB_IMG_POOL")) sscanf(e, "%d,%d,%d", &c.pool10, &c.halves10, &c.depth);
+        c.depth = std::max(1, std::min(kRawStages, c.depth));
+        return c;
+    }();
+    p.pool_depth = pc.depth;
+    long long pool = p.deal ? ntiles : std::min<long long>(ntiles, slots * pc.pool10 / 10);
+    const long long halves = std::min<long long>(pool, slots * pc.halves10 / 10);   // tiles claimed in two halves
+    p.nstatic = (int)(ntiles - pool);
+    p.npool_full = (int)(pool - halves);
+    p.npool_units = (int)(p.npool_full + halves * (rpw >= 2 ? 2 : 1));
+    const int grid = (int)std::min<long long>((long long)p.nstatic + p.npool_units, slots);
+    rc = image_sched_slot(&p.sched);
+    if (rc != DCB_OK) return rc;
     void *transient = nullptr;
-    rc = get_image_plan(map_kind, TH, p, stream, &transient);
+    rc = get_image_plan(map_kind, TH, p, grid, stream, &transient);
     if (rc != DCB_OK) return rc;
     {
         // programmatic stream serialization: see the griddepcontrol pair in remap_image_kernel
@@ -550,7 +624,7 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(kImgThreads);
+        cfg.blockDim = dim3(image_threads(sel.wide));
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -572,7 +646,7 @@ static ImageKernelSel pick_image_kernel_nt(int order, int blend) {
     if (order == 0) return {remap_image_kernel<MAP, 0, DCB_BLEND_EXACT, NT, TH, MINB>, false, TH};
     switch (blend) {
         case DCB_BLEND_LERP64:
-            return {remap_image_kernel<MAP, 1, DCB_BLEND_LERP64, NT, TH, MINB>, true, TH};
+            return {remap_image_kernel<MAP, 1, DCB_BLEND_LERP64, NT, TH, MINB>, false, TH};
         case DCB_BLEND_LERP32:
             return {remap_image_kernel<MAP, 1, DCB_BLEND_LERP32, NT, TH, MINB>, false, TH};
         default:

@@ -52,11 +52,19 @@ struct ImageParams {
     int bw, bh;        // staged box, bw % 4 == 0; bw == 0 => never stage
     unsigned box_bytes, stage_bytes;
     int dbg;           // A/B builds (-DDCB_AB): ablation switches, 0 otherwise
-    int deal;          // 0: each CTA a contiguous range of the tile order; 1: tiles dealt round-robin
+    int deal;          // 1: uneven tiles (clipped regions, fallback box): every tile comes from the pool
+    int nstatic;       // tiles [0, nstatic) are split into one contiguous range per CTA
+    int npool_full;    // pool: tiles [nstatic, nstatic + npool_full) are claimed whole,
+    int npool_units;   //       the rest in halves; npool_units claims in total
+    unsigned *sched;   // [0] next pool unit, [1] CTAs done (the last one resets both)
+    int pool_depth;    // units a producer keeps in flight while it claims from the pool (2..NBUF)
+    int plan_ready;    // 1: the plan was complete before this launch was enqueued (cache hit)
     int fast;          // 1: rows certified by the producer take the patch path (see RowPatch)
     int rint;          // 1: integer image, round half away from zero (finish_f64 in remap.cuh)
     unsigned long long *stats;   // diagnostics (dcb_image_stats), NULL normally
-    const void *plan;            // TilePlan<TH>[ntiles] (image_plan_kernel), device memory
+    const void *plan;            // TilePlan<TH>[ntiles] (image_plan_kernel), device memory; followed by
+    const int2 *plan_boxes;      //   {bx0, use ? by0 : ~by0} per tile, compact (what the producer reads)
+    const int *plan_starts;      //   first tile of every CTA's static range, gridDim.x + 1 entries
     RadialDev rad;
     PerspDev per;
 };
@@ -77,7 +85,7 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 #define DCB_IMG_LDS32 1
 #endif
 #ifndef DCB_IMG_EXACT_RAW
-#define DCB_IMG_EXACT_RAW 0
+#define DCB_IMG_EXACT_RAW 2   // 0: float64 tiles widened by the producers (round 1), 1: raw tiles + F2F, 2: raw tiles, scaled domain
 #endif
 // Ablations of the patch path for attribution runs (A/B builds only, results are WRONG):
 // 1 no stores, 2 every tap read from one address, 4 F = c0 (no Horner chain), 8 no blend (first tap)
@@ -218,19 +226,12 @@ struct MapEval;
 
 template <int NT>
 struct MapEval<MAP_RADIAL, NT> {
-    double xu[kCols], xu2[kCols];
+    // (only xu is kept per tile: with tiles claimed from a pool the column changes with every tile,
+    // and the verified rows of the patch path never need xu^2)
+    double xu[kCols];
     __device__ __forceinline__ void set_columns(const ImageParams &p, const int (&x)[kCols]) {
 #pragma unroll
-        for (int k = 0; k < kCols; ++k) {
-            xu[k] = (double)x[k] - p.rad.xc;
-            const double q = __dmul_rn(xu[k], xu[k]);
-            // r = 0 only at a pixel sitting exactly on the centre.  Keeping
-            // xu^2 >= 1e-300 gives r = 1e-150 there, hence the same F (= a0 after
-            // rounding) and the same coordinates (F * 0 + centre), and it leaves
-            // every other s = xu^2 + yu^2 bit-identical (1e-300 is far below half
-            // an ulp of any non-zero yu^2) -- so the hot loop needs no zero test.
-            xu2[k] = (q < 1e-300) ? 1e-300 : q;
-        }
+        for (int k = 0; k < kCols; ++k) xu[k] = (double)x[k] - p.rad.xc;
     }
     // yd: the row as a double
     __device__ __forceinline__ void row(const ImageParams &p, double yd, float (&xf)[kCols],
@@ -248,7 +249,17 @@ struct MapEval<MAP_RADIAL, NT> {
                                           double (&yq)[kCols]) const {
         const double yu = __dsub_rn(yd, p.rad.yc);
         const double yu2 = __dmul_rn(yu, yu);
-        double r[kCols], f[kCols];
+        double r[kCols], f[kCols], xu2[kCols];
+#pragma unroll
+        for (int k = 0; k < kCols; ++k) {
+            const double q = __dmul_rn(xu[k], xu[k]);
+            // r = 0 only at a pixel sitting exactly on the centre.  Keeping
+            // xu^2 >= 1e-300 gives r = 1e-150 there, hence the same F (= a0 after
+            // rounding) and the same coordinates (F * 0 + centre), and it leaves
+            // every other s = xu^2 + yu^2 bit-identical (1e-300 is far below half
+            // an ulp of any non-zero yu^2) -- so the chain below needs no zero test.
+            xu2[k] = (q < 1e-300) ? 1e-300 : q;
+        }
         if (NT > 2) {
             // F(r) = E(s) + r O(s), s = r^2 (the rounded sum the sqrt is taken of): the two short
             // Horner chains in s do not wait for the sqrt -- same number of operations as Horner in
@@ -397,8 +408,11 @@ __device__ __forceinline__ double dist_to_f32_boundary(double v) {
 template <int MAP, int TH>
 __global__ void __launch_bounds__(kThreads)
     image_plan_kernel(const __grid_constant__ ImageParams p, TilePlan<TH> *__restrict__ plan,
+                      int2 *__restrict__ boxes, unsigned *__restrict__ cost,
                       unsigned long long *__restrict__ stats) {
     __shared__ TileBox sbox;
+    __shared__ unsigned scost;
+    if (threadIdx.x == 0) scost = 0u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x;
     const int txi = t / p.tiles_y, tyi = t - txi * p.tiles_y;
@@ -422,6 +436,7 @@ __global__ void __launch_bounds__(kThreads)
         if (lane == 0) {
             sbox = bx;
             out.box = bx;
+            boxes[t] = make_int2(bx.bx0, bx.use ? bx.by0 : ~bx.by0);
         }
     }
     __syncthreads();
@@ -429,7 +444,7 @@ __global__ void __launch_bounds__(kThreads)
     const int lim_x = box.use ? min(p.bw - 1, wmax - box.bx0) : 0;
     const int lim_y = box.use ? min(p.bh - 1, p.ylast - box.by0) : 0;
     constexpr int RPW = TH / kWarps;
-    unsigned n_full = 0, n_part = 0, n_rows = 0;
+    unsigned n_full = 0, n_part = 0, n_rows = 0, n_genx = 0;
     for (int rr = 0; rr < RPW; ++rr) {
         const int r = warp * RPW + rr, y = y_lo + r;
         RowPatch rp;
@@ -510,6 +525,7 @@ __global__ void __launch_bounds__(kThreads)
             rp.mky = (1u << shy) - 1u;
             rp.e32y = (uint32_t)(150 - shy) << 23;
             n_full += (mask & 0xfu) == 0xfu || (mask & 0xf0u) == 0xf0u;
+            n_genx += (mask & 0xfu) != 0xfu && (mask & 0xf0u) == 0xf0u;
             n_part += !((mask & 0xfu) == 0xfu || (mask & 0xf0u) == 0xf0u) && mask != 0u;
         }
         n_rows += y < y_end;
@@ -520,6 +536,66 @@ __global__ void __launch_bounds__(kThreads)
         atomicAdd(stats + 6, (unsigned long long)n_part);
         atomicAdd(stats + 7, (unsigned long long)n_rows);
     }
+    // what the tile will cost the sampling warps, in quarters of a verified row: rows that take
+    // the per-pixel x binade a quarter more, rows on the exact path three times as much
+    // (profiles/r2/timeline_r2v.txt: the CTAs owning the columns through the distortion centre and
+    // the 2048 binade crossing finished 4 us after everyone else with equal tile counts)
+    if (lane == 0) atomicAdd(&scost, 4u * (n_full - n_genx) + 5u * n_genx + 12u * (n_rows - n_full));
+    __syncthreads();
+    if (threadIdx.x == 0) cost[t] = scost;
+}
+
+// Cuts the first nstatic tiles into `nranges` contiguous ranges of equal cost (tile i goes to the
+// range its cost midpoint falls into): starts[b] = first tile of range b, starts[nranges] = nstatic.
+// One CTA of 1024 threads; every thread owns a chunk of consecutive tiles.
+static __global__ void __launch_bounds__(1024)
+    image_plan_ranges_kernel(const unsigned *__restrict__ cost, int nstatic, int nranges,
+                             int *__restrict__ starts) {
+    __shared__ unsigned long long part[1024];
+    const int tid = threadIdx.x;
+    const int chunk = (nstatic + 1023) / 1024;
+    const int lo = min(tid * chunk, nstatic), hi = min(lo + chunk, nstatic);
+    unsigned long long sum = 0;
+    for (int i = lo; i < hi; ++i) sum += cost[i];
+    part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {   // exclusive scan of 1024 partial sums: a few microseconds, once per plan
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; ++i) {
+            const unsigned long long v = part[i];
+            part[i] = run;
+            run += v;
+        }
+        starts[0] = 0;
+        starts[nranges] = nstatic;
+    }
+    __syncthreads();
+    unsigned long long total = part[1023];
+    for (int i = min(1023 * chunk, nstatic); i < nstatic; ++i) total += cost[i];
+    if (total == 0) total = 1;
+    auto range_of = [&](unsigned long long before, unsigned c) -> int {
+        const unsigned long long mid = 2ull * before + c;   // twice the cost midpoint
+        return (int)min((unsigned long long)(nranges - 1), mid * (unsigned long long)nranges / (2ull * total));
+    };
+    unsigned long long before = part[tid];
+    // range of the tile just before this chunk (range 0 "before" tile 0)
+    int prev = 0;
+    if (lo > 0 && lo < nstatic) {
+        const unsigned cprev = cost[lo - 1];
+        prev = range_of(before - cprev, cprev);
+    }
+    for (int i = lo; i < hi; ++i) {
+        const unsigned c = cost[i];
+        const int b = range_of(before, c);
+        for (int r = prev + 1; r <= b; ++r) starts[r] = i;
+        prev = b;
+        before += c;
+    }
+    // ranges beyond the last tile's are empty
+    if (hi == nstatic && lo < hi)
+        for (int r = prev + 1; r < nranges; ++r) starts[r] = nstatic;
+    if (nstatic == 0 && tid == 0)
+        for (int r = 1; r < nranges; ++r) starts[r] = 0;
 }
 
 template <int ORDER, int BLEND>
@@ -530,8 +606,9 @@ struct ImageKernelTraits {
     // four taps per pixel itself -- no widening pass, no float64 tiles, four stages in flight.
     // Measured 54.4 us against 53.3 us with the float64 tiles (profiles/r2/ab_exact_raw_r2n.txt:
     // XU 40 % busy with 5 conversions per pixel, same 64 instructions per pixel), so off.)
-    static constexpr bool kWide = (ORDER == 1 && (BLEND == DCB_BLEND_LERP64 ||
-                                                  (BLEND == DCB_BLEND_EXACT && !DCB_IMG_EXACT_RAW)));
+    static constexpr bool kWide = (ORDER == 1 && DCB_IMG_EXACT_RAW == 0 &&
+                                   (BLEND == DCB_BLEND_LERP64 || BLEND == DCB_BLEND_EXACT));
+    static_assert(!kWide, "the float64-tile kernels were retired in round 2 (dynamic tile scheduling)");
 };
 
 // float32 box in raw stage 0 -> float64 tile `buf` (exact); producer warp `part`
@@ -548,8 +625,10 @@ __device__ __forceinline__ bool widen_part(const ImageParams &p, unsigned char *
 #endif
 constexpr int kRawStages = DCB_IMG_STAGES;   // !WIDE: raw float32 stages = tile buffers (2 or 4)
 constexpr int kRecRing = 3;       // WIDE: plan records in flight (tiles j-1, j being sampled, j+1 landing)
-constexpr int kImgProducers = 2;                             // producer warps
-constexpr int kImgThreads = kThreads + 32 * kImgProducers;   // 8 sampling warps + the producers
+constexpr int kImgProducers = 2;                             // producer warps of the float64-tile kernels
+// 8 sampling warps + the producers: two where the landed boxes are widened into float64 tiles, one
+// (copies only) where the samplers read the raw float32 stages
+__host__ __device__ constexpr int image_threads(bool wide) { return kThreads + (wide ? 32 * kImgProducers : 32); }
 
 // Shared-memory layout (host side must agree, see plan_and_launch_image in api.cu):
 //   WIDE : [raw][wide 0][wide 1][tail]      raw = stage_bytes, wide = 2 * stage_bytes
@@ -603,7 +682,7 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint
 // the tile loop and the XU-bound widening runs concurrently with the
 // fp64-bound sampling instead of in lock-step phases.
 template <int MAP, int ORDER, int BLEND, int NT, int TH, int MINB>
-__global__ void __launch_bounds__(kImgThreads, MINB)
+__global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>::kWide), MINB)
     remap_image_kernel(const __grid_constant__ ImageParams p,
                        const __grid_constant__ CUtensorMap tmap) {
     constexpr bool WIDE = ImageKernelTraits<ORDER, BLEND>::kWide;
@@ -632,34 +711,20 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     const int wmax = p.W - 1;
     const int y_end = p.row0 + p.nrows;
 
-    // This CTA's tiles.  deal == 0: a contiguous range of the column-major tile order, so that
-    // consecutive tiles sit below each other and share their column terms -- 3 % faster when every
-    // tile costs the same.  deal == 1 (the host sets it when part of the map is clipped at the
-    // image border or the staged box is only the fallback size, i.e. when some tiles take the slow
-    // row path): tiles dealt round-robin, otherwise whole CTAs own nothing but slow tiles -- the
-    // config-1 geometry (19.9 % clipped) took 166 us instead of 100, the config-3 perspective 93
-    // instead of 70 (profiles/r1/bench_tile_dealing.txt).
-    //
-    // The contiguous ranges are cut in units of one ROW GROUP (kWarps rows, one per sampling warp;
-    // RPW groups per tile), not of whole tiles: 4096 tiles over 296 CTAs are 13.84 tiles each, and
-    // with whole tiles the CTAs holding 13 sat idle for a tile's time (3.2 us of 53, the per-CTA
-    // timeline in profiles/r2/timeline_r2t.txt).  The first and the last tile of a range are
-    // sampled in part (row groups g_first.. and ..g_last); the neighbouring CTA stages the same box.
-    const int tstep = p.deal ? (int)gridDim.x : 1;
-    int t0, n, g_first = 0, g_last = RPW;
-    if (p.deal) {
-        t0 = (int)blockIdx.x;
-        n = (p.ntiles - t0 + tstep - 1) / tstep;
-    } else {
-        const long long units = (long long)p.ntiles * RPW;
-        const long long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
-        t0 = (int)(u0 / RPW);
-        g_first = (int)(u0 - (long long)t0 * RPW);
-        const int tl = (int)((u1 - 1) / RPW);
-        n = u1 > u0 ? tl - t0 + 1 : 0;
-        g_last = (int)(u1 - 1 - (long long)tl * RPW) + 1;
-    }
-    auto tile_of = [&](int k) -> int { return t0 + k * tstep; };   // local tile k -> tile index
+    // Tile scheduling (round 2).  Tiles are numbered column-major.  The first p.nstatic of them
+    // are split statically, one contiguous range per CTA, so that consecutive tiles sit below each
+    // other and share their column terms; the rest form a POOL that the producer warps claim from
+    // with an atomic counter once their range is exhausted -- whole tiles first, the last ones in
+    // halves (RPW / 2 row groups).  The per-CTA timeline of the purely static split
+    // (profiles/r2/timeline_r2t*.txt) showed CTAs finishing up to 11 us apart in a 53 us kernel:
+    // 13 against 14 tiles, the second CTA of an SM running 4-9 % behind the first (oldest-first
+    // warp scheduling), tiles with binade crossings.  While it claims from the pool a producer
+    // keeps only one unit in flight beyond the one being sampled: a unit claimed is a unit this
+    // CTA must do, and four claimed ahead would decide the balance 10 us before the end.
+    // p.deal (uneven tiles: clipped regions, fallback boxes) => nstatic == 0, everything is pooled.
+    // The static ranges are cut by estimated cost, not by tile count (image_plan_ranges_kernel).
+    uint32_t *unit_g = reinterpret_cast<uint32_t *>(tail + 80);   // [4] row groups of the unit in stage b
+    constexpr uint32_t kNoUnit = 0xffffffffu;
 
     if (threadIdx.x == 0) {
 #ifdef DCB_IMG_TIMELINE
@@ -669,98 +734,122 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             mbar_init(&raw_full[b], 1);
             mbar_init(&data_empty[b], kWarps);
         }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&data_full[b], 1);
-            odd[b] = 0;
-        }
         fence_mbar_init();
         if (staged) tma_prefetch_desc(&tmap);
     }
     __syncthreads();
     // Programmatic dependent launch (api.cu launches with programmatic stream serialization): the
     // CTAs of the next launch in the stream may take the SM slots this grid's CTAs free, and run
-    // everything above, before this grid has finished; nothing below -- no read of the plan or the
-    // source, no store -- happens before the preceding grid has completed and flushed.  Without
-    // the launch attribute both instructions do nothing.
+    // everything above, before this grid has finished; no read of the source and no store happens
+    // before the preceding grid has completed and flushed (griddepcontrol.wait below); the plan is
+    // read earlier only when it was complete before this launch was enqueued (p.plan_ready).
+    // Without the launch attribute both instructions do nothing.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    if (warp > kWarps) {
-        // ====================== second producer warp: widening only =====================
-        if (WIDE) {
-            uint32_t nraw = 0;
-            for (int j = 0; j < n; ++j) {
-                const int b = j & 1;
-                if (j >= 2) mbar_wait(&data_empty[b], (uint32_t)((j >> 1) - 1) & 1u);
-                DCB_LOG(3 * j);
-                asm volatile("bar.sync 1, 64;" ::: "memory");   // (A) buffer b is free
-                // tile j's record and box (if staged) have landed
-                mbar_wait(&raw_full[0], nraw & 1u);
-                ++nraw;
-                DCB_LOG(3 * j + 1);
-                if (rec[j % NREC].box.use) {
-                    const bool o = widen_part(p, smem, b, 1, lane);
-                    if (PATCH && __any_sync(0xffffffffu, o) && lane == 0) atomicOr(&odd[b], 1u);
-                }
-                DCB_LOG(3 * j + 2);
-                asm volatile("bar.sync 1, 64;" ::: "memory");   // (B) both halves written, raw free
-            }
-        }
-        return;
-    }
     if (warp == kWarps) {
         // =========================== producer warp ===================================
-        // lane 0: start the copies of local tile k -- its plan record into record slot `rs` and,
-        // when the tile is staged, its box into raw stage `st` -- both completing on raw_full[st]
-        auto issue = [&](int k, int st, int rs) {
-            const TilePlan<TH> *tp = plan + tile_of(k);
-            const int4 bx = __ldg(reinterpret_cast<const int4 *>(&tp->box));   // bx0, by0, use, shx
-            mbar_expect_tx(&raw_full[st], kRecBytes + (bx.z ? p.box_bytes : 0u));
-            bulk_load(&rec[rs], tp, kRecBytes, &raw_full[st]);
-            if (bx.z)
+        // lane 0 starts the copies of one tile in two steps: its plan record (and the read of its
+        // box origin, from a compact array: sixteen tiles share a cache line, so along a static
+        // range the read the TMA issue depends on is an L1 hit), then, when the tile is staged, its
+        // box into stage st -- both completing on raw_full[st]
+        auto issue_plan = [&](int tile, int st) -> int2 {
+            const TilePlan<TH> *tp = plan + tile;
+            const int2 bx = __ldg(p.plan_boxes + tile);   // bx0, use ? by0 : ~by0
+            mbar_expect_tx(&raw_full[st], kRecBytes + (bx.y >= 0 ? p.box_bytes : 0u));
+            bulk_load(&rec[st], tp, kRecBytes, &raw_full[st]);
+            return bx;
+        };
+        auto issue_box = [&](const int2 bx, int st) {
+            if (bx.y >= 0)
                 tma_load_3d(smem + (size_t)st * p.stage_bytes, &tmap, bx.x, bx.y - p.yorg, 0,
                             &raw_full[st]);
         };
-        if (WIDE) {
-            uint32_t nraw = 0;  // fills consumed from the single raw stage
-            if (n > 0 && lane == 0) issue(0, 0, 0);
-            for (int j = 0; j < n; ++j) {
-                const int b = j & 1;
-                if (j >= 2) mbar_wait(&data_empty[b], (uint32_t)((j >> 1) - 1) & 1u);
-                DCB_LOG(3 * j);
-                if (PATCH && lane == 0) odd[b] = 0u;   // buffer b is free: reset its flag
-                asm volatile("bar.sync 1, 64;" ::: "memory");   // (A)
-                mbar_wait(&raw_full[0], nraw & 1u);
-                ++nraw;
-                DCB_LOG(3 * j + 1);
-                if (rec[j % NREC].box.use) {
-                    const bool o = widen_part(p, smem, b, 0, lane);
-                    if (PATCH && __any_sync(0xffffffffu, o) && lane == 0) atomicOr(&odd[b], 1u);
-                }
-                DCB_LOG(3 * j + 2);
-                asm volatile("bar.sync 1, 64;" ::: "memory");   // (B) float64 tile complete, raw free
-                if (lane == 0) {
-                    // (the samplers have left tile j-2, whose record slot tile j+1 takes over)
-                    if (j + 1 < n) issue(j + 1, 0, (j + 1) % NREC);
-                    mbar_arrive(&data_full[b]);
+        // A plan that was complete before this launch was enqueued may be read while the preceding
+        // grid is still running: the static range and the plan half of its first NBUF tiles are
+        // under way before the grid dependency is waited for, only the source boxes come after.
+        int t0 = 0, n_static = 0, k0 = 0;
+        int2 bxs[NBUF];
+        auto read_range = [&]() {
+            if (lane == 0 && p.nstatic > 0) {
+                t0 = __ldg(p.plan_starts + blockIdx.x);
+                n_static = __ldg(p.plan_starts + blockIdx.x + 1) - t0;
+            }
+        };
+        if (p.plan_ready) {
+            read_range();
+            if (lane == 0) {
+                k0 = min(n_static, NBUF);
+#pragma unroll
+                for (int k = 0; k < NBUF; ++k) {
+                    if (k < k0) {
+                        unit_g[k] = (uint32_t)RPW << 8;
+                        bxs[k] = issue_plan(t0 + k, k);
+                    }
                 }
             }
-        } else {
-            // raw stage k % 4 doubles as the data buffer: the samplers wait on raw_full[k % 4];
-            // the producer runs at most four tiles ahead of the slowest sampling warp (with two
-            // stages the samplers waited 11 % of their time for copies issued only one tile
-            // earlier, profiles/r2/ncu_image_r2h_lerp32_two_stages.txt)
-            for (int k = 0; k < n; ++k) {
-                const int b = k & (NBUF - 1);
-                if (k >= NBUF) mbar_wait(&data_empty[b], (uint32_t)((k >> LOGB) - 1) & 1u);
-                DCB_LOG(k);
-                if (lane == 0) issue(k, b, b);
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (!p.plan_ready) read_range();
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NBUF; ++k)
+                if (k < k0) issue_box(bxs[k], k);
+        }
+        t0 = __shfl_sync(0xffffffffu, t0, 0);
+        n_static = __shfl_sync(0xffffffffu, n_static, 0);
+        k0 = __shfl_sync(0xffffffffu, k0, 0);
+        // raw stage k % NBUF is the data buffer of this CTA's k-th unit: the samplers wait on
+        // raw_full[k % NBUF]; the producer runs at most NBUF units ahead of the slowest sampling
+        // warp (with two stages the samplers waited 11 % of their time for copies issued only one
+        // tile earlier, profiles/r2/ncu_image_r2h_lerp32_two_stages.txt), p.pool_depth while it
+        // claims
+        for (int k = k0;; ++k) {
+            const int b = k & (NBUF - 1);
+            const int depth = k < n_static ? NBUF : p.pool_depth;
+            if (k >= depth) {
+                const int kd = k - depth;   // this unit must have been released by all samplers
+                mbar_wait_idle(&data_empty[kd & (NBUF - 1)], (uint32_t)(kd >> LOGB) & 1u);
+            }
+            DCB_LOG(k);
+            int more = 1;
+            if (lane == 0) {
+                if (k < n_static) {
+                    unit_g[b] = (uint32_t)RPW << 8;
+                    issue_box(issue_plan(t0 + k, b), b);
+                } else {
+                    const int v = (int)atomicAdd(&p.sched[0], 1u);
+                    if (v >= p.npool_units) {
+                        unit_g[b] = kNoUnit;   // tells the samplers to leave
+                        mbar_arrive(&raw_full[b]);
+                        more = 0;
+                    } else if (v < p.npool_full) {
+                        unit_g[b] = (uint32_t)RPW << 8;
+                        issue_box(issue_plan(p.nstatic + v, b), b);
+                    } else {
+                        constexpr int HG = RPW >= 2 ? RPW / 2 : 1;   // row groups of half a tile
+                        const int w = v - p.npool_full;
+                        const int ga = RPW >= 2 ? (w & 1) * HG : 0;
+                        unit_g[b] = (uint32_t)ga | ((uint32_t)(ga + HG) << 8);
+                        issue_box(issue_plan(p.nstatic + p.npool_full + (RPW >= 2 ? (w >> 1) : w), b), b);
+                    }
+                }
+            }
+            more = __shfl_sync(0xffffffffu, more, 0);
+            if (!more) break;
+        }
+        // the last CTA through here leaves the counters as it found them
+        if (lane == 0) {
+            const unsigned d = atomicAdd(&p.sched[1], 1u);
+            if (d == gridDim.x - 1) {
+                p.sched[0] = 0u;
+                p.sched[1] = 0u;
             }
         }
         return;
     }
 
     // ============================== sampling warps ====================================
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int txi = -1;   // tile column the per-thread column terms are set for
     MapEval<MAP, NT> ev;
     // patch path: the thread's four columns in the tile's variable tau = (x - x_tile - 63.5) / 64
@@ -776,9 +865,13 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
 #ifdef DCB_IMG_TIMELINE   // -DDCB_IMG_TIMELINE builds only (tools/timeline_probe.py)
     unsigned long long dbg_t = 0, dbg_wait = 0, dbg_wmax = 0;
 #endif
-    for (int i = 0; i < n; ++i) {
-        // tile i is ready: WIDE -> float64 tile i&1 written by the producer; !WIDE -> raw stage landed
-        mbar_wait(WIDE ? &data_full[i & 1] : &raw_full[i & (NBUF - 1)], (uint32_t)(i >> LOGB) & 1u);
+    int n = 0;   // units sampled (diagnostics)
+    for (int i = 0;; ++i) {
+        // unit i is ready: its record and box have landed in stage i % NBUF
+        mbar_wait(&raw_full[i & (NBUF - 1)], (uint32_t)(i >> LOGB) & 1u);
+        const uint32_t ug = unit_g[i & (NBUF - 1)];
+        if (ug == kNoUnit) break;
+        n = i + 1;
         DCB_LOG(2 * i);
 #ifdef DCB_IMG_TIMELINE
         if (p.stats != nullptr && threadIdx.x == 0 && blockIdx.x < kTimelineCtas) {
@@ -805,7 +898,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         {
             const int x_base = txi * kTileW + lane;
             // this warp's rows of the tile: warp + kWarps g for the row groups g of this CTA's share
-            const int ga = i == 0 ? g_first : 0, gb = i == n - 1 ? g_last : RPW;
+            const int ga = (int)(ug & 0xffu), gb = (int)(ug >> 8);
             const int y_base = p.row0 + tyi * TH + ga * kWarps + warp;
             const int rows_left = y_end - y_base;   // rows y_base + kWarps j exist for kWarps j < rows_left
             const int nrow = min(gb - ga, (rows_left + kWarps - 1) / kWarps);  // warp-uniform, may be <= 0
@@ -855,13 +948,21 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                 bool done = false;
                 if constexpr (PATCH) if (shx_t != 0) {
                     // ------------------- the patch path (see RowPatch) -------------------
-                    const uint4 inf = *reinterpret_cast<const uint4 *>(&prow->info);
+                    // (all four loads before the branch on the first: one shared-memory round trip
+                    // per row instead of two)
+                    uint4 inf;
+                    double2 c01, c23, c45;
+                    {
+                        const uint32_t pa = smem_u32(prow);
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+48];"
+                                     : "=r"(inf.x), "=r"(inf.y), "=r"(inf.z), "=r"(inf.w) : "r"(pa));
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c01.x), "=d"(c01.y) : "r"(pa));
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(c23.x), "=d"(c23.y) : "r"(pa));
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+32];" : "=d"(c45.x), "=d"(c45.y) : "r"(pa));
+                    }
                     // bits 0..3: verified with the tile's x binade; bits 4..7: verified with the
                     // x binade taken per pixel (rows crossing a power of two in x)
                     if ((inf.x & 0xfu) == 0xfu || (inf.x & 0xf0u) == 0xf0u) {
-                        const double2 c01 = *reinterpret_cast<const double2 *>(&prow->c[0]);
-                        const double2 c23 = *reinterpret_cast<const double2 *>(&prow->c[2]);
-                        const double2 c45 = *reinterpret_cast<const double2 *>(&prow->c[4]);
                         const double yu = __dsub_rn(yd, p.rad.yc);
                         double xq[kCols], yq[kCols];
 #pragma unroll
@@ -957,6 +1058,13 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                                     asm("ld.shared.f32 %0, [%1+%2];" : "=f"(d) : "r"(qa), "n"(4 * kImgBoxW + 4));
                                     // a set sign bit, Inf or NaN among the taps: not what lerp_fma is
                                     // certified for (largest bit pattern >= 0x7f800000)
+                                    if (BLEND == DCB_BLEND_LERP64) {   // three float64 lerps, no certificate needed
+                                        const double da = a, db = b, dc = c, dd = d;
+                                        const double top = fma(db - da, tx, da);
+                                        const double bot = fma(dd - dc, tx, dc);
+                                        v[k] = __double2float_rn(fma(bot - top, ty, top));
+                                        continue;
+                                    }
                                     tapmax = __vimax3_u32(tapmax, __float_as_uint(a), __float_as_uint(b));
                                     tapmax = __vimax3_u32(tapmax, __float_as_uint(c), __float_as_uint(d));
                                     const double sd = lerp_fma((double)a, (double)b, (double)c, (double)d, tx, ty);
@@ -1045,7 +1153,13 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                             const float *q = rawt + idx;
                             const double a = q[0], b = q[1];
                             const double c = q[bw], d = q[bw + 1];
-                            v[k] = finish_f64(blend_exact(a, b, c, d, (double)tx, (double)ty), p.rint);
+                            if (BLEND == DCB_BLEND_LERP64) {
+                                const double top = fma(b - a, (double)tx, a);
+                                const double bot = fma(d - c, (double)tx, c);
+                                v[k] = finish_f64(fma(bot - top, (double)ty, top), p.rint);
+                            } else {
+                                v[k] = finish_f64(blend_exact(a, b, c, d, (double)tx, (double)ty), p.rint);
+                            }
                         } else if (!WIDE) {
                             const float *q = rawt + idx;
                             const float a = q[0], b = q[1];
