@@ -273,7 +273,7 @@ static unsigned long long *g_image_stats_fwd() { return g_image_stats; }
 // Launch planning for the single-image kernel (remap_image.cuh).
 struct ImageKernelSel {
     ImageKernel kern;
-    bool wide;  // samples from the float64 tile (two of them + one raw stage)
+    bool wide;  // unused since round 2 (every kernel samples the raw float32 stages)
     int th;     // tile height the kernel was instantiated for
 };
 
@@ -528,9 +528,9 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
         bh = (int)need_h;
         // 5 stages (fp64 blends: one raw + two float64 tiles) or 4 raw stages + tail, x 2 CTAs
         // (each + 1 KB reserved) within the SM's 228 KB
-        const int nst = sel.wide ? 5 : kRawStages;
+        const int nst = kRawStages;
         const int max_stage =
-            TH >= 32 ? (int)((116736 - 1024 - image_tail_bytes(TH, sel.wide)) / nst / 128 * 128)
+            TH >= 32 ? (int)((116736 - 1024 - image_tail_bytes(TH)) / nst / 128 * 128)
                      : 14 * 1024;
         if (bw > 256 || bh > 256 || (long long)bw * bh * 4 > max_stage) {
             // strong magnification somewhere: stage a modest box, tiles whose
@@ -582,13 +582,13 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
     p.bh = bh;
     p.box_bytes = (unsigned)(bw * bh * 4);
     p.stage_bytes = (p.box_bytes + 127u) / 128u * 128u;
-    const size_t smem = (size_t)(sel.wide ? 5 : kRawStages) * p.stage_bytes + image_tail_bytes(TH, sel.wide);
+    const size_t smem = (size_t)kRawStages * p.stage_bytes + image_tail_bytes(TH);
     if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute((const void *)sel.kern,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)sel.kern,
-                                                           image_threads(sel.wide), smem));
+                                                           kImgThreads, smem));
     if (occ < 1) return fail(DCB_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
     // Tile scheduling (see remap_image_kernel): a static range per CTA for most of the tiles, a pool
     // of 2.5 tiles per CTA claimed dynamically at the end, the last tile per CTA of it in halves.
@@ -624,7 +624,7 @@ static int plan_and_launch_image(const ImageKernelSel &sel, ImageParams &p, doub
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(image_threads(sel.wide));
+        cfg.blockDim = dim3(kImgThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -650,8 +650,7 @@ static ImageKernelSel pick_image_kernel_nt(int order, int blend) {
         case DCB_BLEND_LERP32:
             return {remap_image_kernel<MAP, 1, DCB_BLEND_LERP32, NT, TH, MINB>, false, TH};
         default:
-            return {remap_image_kernel<MAP, 1, DCB_BLEND_EXACT, NT, TH, MINB>,
-                    ImageKernelTraits<1, DCB_BLEND_EXACT>::kWide, TH};
+            return {remap_image_kernel<MAP, 1, DCB_BLEND_EXACT, NT, TH, MINB>, false, TH};
     }
 }
 

@@ -1,34 +1,30 @@
-// remap_image.cuh -- the single-image backward-remap kernel (sm_100a), v4.
+// remap_image.cuh -- the single-image backward-remap kernel (sm_100a), v5 (round 2).
 //
 // Serves a1 `unwarp_image_backward` (postprocessing.py:111-148) and a4
 // `correct_perspective_image` (:444-492) for one float32 image, or a range of
 // its output rows.  Numerics are those of remap.cuh (same helpers); what is
-// different is the schedule, shaped by the ncu captures under profiles/r1:
-// at the 70 %-of-HBM target an SM must retire 2 output pixels per clock, i.e.
-// it has 64 issue slots, 32 fp64 slots and 8 XU (conversion / MUFU) slots per
-// pixel -- the kernel is bound by instruction issue, not by memory, so every
-// design decision below removes instructions from the per-pixel loop.
+// different is the schedule.  The kernel is bound by instruction issue, not by memory: at the
+// 70 %-of-HBM target an SM must retire 2 output pixels per clock, and on this part an fp64
+// instruction holds a sub-partition's issue port for its whole dispatch (2.1 cycles, 3.1 with three
+// distinct source registers) -- measured: every DFMA removed from the per-pixel loop saves its
+// pipe time in full, other instructions 1 cycle (profiles/r2/ablation_raw2_r2a1.txt).
 //
-//   * persistent CTAs walk output tiles of 128 x 32 pixels; while tile i is
-//     sampled, warp 0 estimates the source box of tile i+1 from 9 probe
-//     points and issues its TMA load, so the copy is hidden behind a full
-//     tile of fp64 work;
-//   * the box lands as float32 and is widened ONCE per source pixel into a
-//     float64 tile in shared memory (1.3 conversions per output pixel instead
-//     of 4 -- the 16-lane XU pipe is the scarcest resource);
-//   * coordinates are evaluated four pixels at a time right before they are
-//     used -- nothing stays live across a barrier except the per-thread column
-//     terms;
-//   * floor() of the fp32 coordinate uses a round-down add of 2^23 on the FP32
-//     pipe instead of F2I/I2F on the XU pipe;
-//   * the fast path does not clip: a coordinate outside the image fails the
-//     "2x2 footprint inside the staged box and strictly inside the image"
-//     test that every pixel makes anyway, and the (rare) rows that fail it --
-//     box estimate too small, last row/column, clipped regions -- take the
-//     generic clip + global gather of remap.cuh, so correctness never depends
-//     on the estimate;
-//   * the four fp64 bilinear weights come from one multiplication and four
-//     exact subtractions (see blend_exact below).
+//   * a PLAN per (model, geometry), built once and cached on the device (api.cu): per tile the
+//     source box, per tile row a verified degree-5 interpolant of the radial factor (RowPatch),
+//     per tile a cost estimate, per CTA a cost-balanced static range of tiles;
+//   * persistent CTAs (2 per SM): eight sampling warps and one producer warp that streams the
+//     tiles' boxes (TMA) and plan records (bulk copy) through four shared-memory stages;
+//   * tiles come from the CTA's static range first, then from a pool claimed with an atomic
+//     counter (whole tiles, halves at the very end) -- CTAs finish within about 1 us of each other;
+//   * programmatic dependent launch: the prologue, and the plan half of the first four tiles, run
+//     under the tail of the preceding launch in the stream;
+//   * verified rows ("patch path"): 7 DFMA per pixel for the coordinates, rounding to the
+//     float32 grid / floor / fraction by one magic addition each, taps from the raw float32
+//     stage, the exact blend as six certified FMAs in the scaled domain (scaled_f64: one integer
+//     multiply-wide per tap instead of a conversion), the float32 result by an integer shift;
+//   * every other row (image borders, the distortion centre, failed certificates, negative or
+//     non-finite pixels) takes the exact coordinate chain and SciPy's own sum, or the generic
+//     clip + global gather of remap.cuh, so no result depends on the plan's estimates.
 #pragma once
 #include "remap.cuh"
 
@@ -69,21 +65,6 @@ struct ImageParams {
     PerspDev per;
 };
 
-// One float64 tap of the widened tile through a 32-bit shared address with a compile-time byte
-// offset: the tile base is pinned in a register once per tile instead of being re-derived from the
-// generic pointer in every row (ptxas rematerialised S2UR / ULEA / LOP3 / LDC / IMAD per row under
-// the 96-register budget).  Together with the fixed box width: 237 -> 217 instructions per row of
-// 4 x 32 pixels; lerp64 55.3 -> 53.7 us, lerp32 45.1 -> 44.0, exact 57.5 -> 57.4 (not issue-bound).
-// -DDCB_IMG_LDS32=0 restores the generic-pointer loads for A/B builds.
-template <int OFF>
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-    double v;
-    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
-    return v;
-}
-#ifndef DCB_IMG_LDS32
-#define DCB_IMG_LDS32 1
-#endif
 #ifndef DCB_IMG_EXACT_RAW
 #define DCB_IMG_EXACT_RAW 2   // 0: float64 tiles widened by the producers (round 1), 1: raw tiles + F2F, 2: raw tiles, scaled domain
 #endif
@@ -598,48 +579,23 @@ static __global__ void __launch_bounds__(1024)
         for (int r = 1; r < nranges; ++r) starts[r] = 0;
 }
 
-template <int ORDER, int BLEND>
-struct ImageKernelTraits {
-    // bilinear in fp64: sample from the widened tile; otherwise from the raw
-    // float32 box (two stages, no widening pass)
-    // (-DDCB_IMG_EXACT_RAW=1: the exact blend also samples the raw float32 box and converts its
-    // four taps per pixel itself -- no widening pass, no float64 tiles, four stages in flight.
-    // Measured 54.4 us against 53.3 us with the float64 tiles (profiles/r2/ab_exact_raw_r2n.txt:
-    // XU 40 % busy with 5 conversions per pixel, same 64 instructions per pixel), so off.)
-    static constexpr bool kWide = (ORDER == 1 && DCB_IMG_EXACT_RAW == 0 &&
-                                   (BLEND == DCB_BLEND_LERP64 || BLEND == DCB_BLEND_EXACT));
-    static_assert(!kWide, "the float64-tile kernels were retired in round 2 (dynamic tile scheduling)");
-};
-
-// float32 box in raw stage 0 -> float64 tile `buf` (exact); producer warp `part`
-// of kImgProducers converts every kImgProducers-th group of 32 float4.  bw % 4 == 0.
-// Returns whether this part holds a value the certified blend (lerp_fma) does not cover: a set
-// sign bit, Inf / NaN, or a non-zero magnitude below 2^-80 (whose blend could be a float32
-// denormal, where the rounding boundaries are not those of the certificate).
-struct ImageParams;
-__device__ __forceinline__ bool widen_part(const ImageParams &p, unsigned char *smem, int buf,
-                                           int part, int lane);
-
 #ifndef DCB_IMG_STAGES
 #define DCB_IMG_STAGES 4
 #endif
-constexpr int kRawStages = DCB_IMG_STAGES;   // !WIDE: raw float32 stages = tile buffers (2 or 4)
-constexpr int kRecRing = 3;       // WIDE: plan records in flight (tiles j-1, j being sampled, j+1 landing)
-constexpr int kImgProducers = 2;                             // producer warps of the float64-tile kernels
-// 8 sampling warps + the producers: two where the landed boxes are widened into float64 tiles, one
-// (copies only) where the samplers read the raw float32 stages
-__host__ __device__ constexpr int image_threads(bool wide) { return kThreads + (wide ? 32 * kImgProducers : 32); }
+constexpr int kRawStages = DCB_IMG_STAGES;   // raw float32 stages = tile buffers in flight (2 or 4)
+// 8 sampling warps + one producer warp (copies only)
+constexpr int kImgThreads = kThreads + 32;
 
 // Shared-memory layout (host side must agree, see plan_and_launch_image in api.cu):
-//   WIDE : [raw][wide 0][wide 1][tail]      raw = stage_bytes, wide = 2 * stage_bytes
-//   !WIDE: [raw 0] .. [raw 3][tail]
-//   tail : uint64_t raw_full[4], data_empty[4], data_full[2]; uint32_t odd[4] (tile buffer holds
-//          values the certified blend does not cover); TilePlan<TH> rec[WIDE ? kRecRing : 4]
+//   [raw 0] .. [raw 3][tail]
+//   tail : uint64_t raw_full[4] (copy landed), data_empty[4] (stage released by the eight sampling
+//          warps); 16 bytes unused; uint32_t unit_g[4] (row groups of the unit in each stage);
+//          TilePlan<TH> rec[4]
 __host__ __device__ constexpr size_t image_rec_bytes(int th) {
     return sizeof(TileBox) + (size_t)th * sizeof(RowPatch);
 }
-__host__ __device__ constexpr size_t image_tail_bytes(int th, bool wide) {
-    return 96 + (wide ? kRecRing : kRawStages) * image_rec_bytes(th);
+__host__ __device__ constexpr size_t image_tail_bytes(int th) {
+    return 96 + kRawStages * image_rec_bytes(th);
 }
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -671,35 +627,29 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint
 // TH: tile height (16 or 32 rows); MINB: resident CTAs per SM the register
 // allocation is held to.
 //
-// Warp-specialised: warps 0..7 only evaluate coordinates and sample; warp 8 (the
-// producer) walks the plan: per tile one TMA load of the staged box and one bulk copy of the
-// tile's plan record, both completing on the same mbarrier, and -- for the fp64 blends,
-// together with warp 9 -- widens each landed float32 box into one of two
-// float64 tiles (one warp alone could not keep ahead of the samplers: with it
-// they spent 26 % of their time waiting, profiles/r1/ncu_summary_v6.txt).  The
-// hand-over is by mbarriers (data_full: producer -> samplers, data_empty: one
-// arrival per sampling warp -> producer), so there is no CTA-wide barrier in
-// the tile loop and the XU-bound widening runs concurrently with the
-// fp64-bound sampling instead of in lock-step phases.
+// Warp-specialised: warps 0..7 only evaluate coordinates and sample from the raw float32 stages;
+// warp 8 (the producer) walks this CTA's tiles: per tile one TMA load of the staged box and one
+// bulk copy of the tile's plan record, both completing on the stage's mbarrier (raw_full); the
+// sampling warps hand a stage back with one arrival each on data_empty.  There is no CTA-wide
+// barrier in the tile loop.  (Round 1 widened every landed box into float64 tiles with two
+// producer warps; the per-warp event log showed that widening -- 1.7 us per tile -- was as slow as
+// the sampling it fed, profiles/r2/timeline_r2t3_event_log.txt.  The exact blend now widens its
+// taps itself, in the scaled domain, see scaled_f64.)
 template <int MAP, int ORDER, int BLEND, int NT, int TH, int MINB>
-__global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>::kWide), MINB)
+__global__ void __launch_bounds__(kImgThreads, MINB)
     remap_image_kernel(const __grid_constant__ ImageParams p,
                        const __grid_constant__ CUtensorMap tmap) {
-    constexpr bool WIDE = ImageKernelTraits<ORDER, BLEND>::kWide;
     constexpr bool PATCH = (MAP == MAP_RADIAL) && kImgBoxW > 0;   // the patch path exists
     constexpr int RPW = TH / kWarps;  // rows per sampling warp and tile
-    constexpr int NBUF = WIDE ? 2 : kRawStages;   // tile buffers the samplers read from
-    constexpr int LOGB = (WIDE || kRawStages == 2) ? 1 : 2;
+    constexpr int NBUF = kRawStages;   // stages = tile buffers the samplers read from
+    constexpr int LOGB = kRawStages == 2 ? 1 : 2;
     static_assert((1 << LOGB) == NBUF, "buffer count");
-    constexpr int NREC = WIDE ? kRecRing : NBUF;
     constexpr uint32_t kRecBytes = (uint32_t)sizeof(TilePlan<TH>);
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *tail = smem + (WIDE ? 5 : kRawStages) * (size_t)p.stage_bytes;
+    unsigned char *tail = smem + kRawStages * (size_t)p.stage_bytes;
     uint64_t *raw_full = reinterpret_cast<uint64_t *>(tail);         // [4] TMA bytes landed
     uint64_t *data_empty = raw_full + 4;                             // [4] tile buffer released
-    uint64_t *data_full = raw_full + 8;                              // [2] WIDE: float64 tile ready
-    uint32_t *odd = reinterpret_cast<uint32_t *>(tail + 80);         // [2] see widen_part
-    TilePlan<TH> *rec = reinterpret_cast<TilePlan<TH> *>(tail + 96); // [NREC]
+    TilePlan<TH> *rec = reinterpret_cast<TilePlan<TH> *>(tail + 96); // [NBUF]
     const TilePlan<TH> *plan = reinterpret_cast<const TilePlan<TH> *>(p.plan);
 
     const int lane = threadIdx.x & 31;
@@ -790,9 +740,13 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
         }
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (!p.plan_ready) read_range();
-        if (lane == 0) {
+        if (lane == 0 && k0 > 0) {
+            // the first box alone, the prefetches once it has landed: all 296 CTAs start at the same
+            // moment, and four boxes each would queue the one everybody waits for behind 19 MB
+            issue_box(bxs[0], 0);
+            if (k0 > 1) mbar_wait(&raw_full[0], 0u);
 #pragma unroll
-            for (int k = 0; k < NBUF; ++k)
+            for (int k = 1; k < NBUF; ++k)
                 if (k < k0) issue_box(bxs[k], k);
         }
         t0 = __shfl_sync(0xffffffffu, t0, 0);
@@ -884,7 +838,7 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
             }
         }
 #endif
-        const TilePlan<TH> &trec = rec[i % NREC];
+        const TilePlan<TH> &trec = rec[i & (NBUF - 1)];
         const TileBox box = trec.box;
         const int tyi = box.pad[1];
         if (box.pad[0] != txi) {   // CTA-uniform: a new tile column
@@ -911,11 +865,6 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
             const int sb = i & (NBUF - 1);
             const float *rawt =
                 reinterpret_cast<const float *>(smem + (size_t)sb * p.stage_bytes);
-            const double *widet = reinterpret_cast<const double *>(
-                smem + (size_t)(1 + 2 * sb) * p.stage_bytes);
-            // (ordered after the mbarrier wait above: every tap address below depends on it)
-            uint32_t wide_s = smem_u32(widet);
-            asm volatile("" : "+r"(wide_s)::"memory");
             const bool full_w = __all_sync(0xffffffffu, txi * kTileW + kTileW - 1 <= wmax);  // CTA-uniform
             float *orow = p.dst + (long long)(y_base - p.row0) * p.dst_pitch + x_base;
             double yd = (double)y_base;
@@ -923,8 +872,7 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
             const int shx_t = box.shx;
             const uint32_t mkx_t = (1u << shx_t) - 1u, e32x_t = (uint32_t)(150 - shx_t) << 23;
             const uint32_t org = (uint32_t)(box.by0 * bw + box.bx0);
-            const uint32_t base_s = (WIDE ? wide_s : smem_u32(rawt)) - (WIDE ? 8u : 4u) * org;
-            const bool tile_odd = WIDE && BLEND == DCB_BLEND_EXACT && (odd[sb] != 0u);
+            const uint32_t base_s = smem_u32(rawt) - 4u * org;
             const RowPatch *prow = trec.rows + ga * kWarps + warp;
             unsigned n_bfail = 0;   // diagnostics, see p.stats
 #ifndef DCB_IMG_UNROLL
@@ -983,11 +931,9 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
                         const uint32_t mky = inf.z, e32y = inf.w;
                         const double My = __hiloint2double((int)inf.y, 0);
                         uint32_t accb = 0xffffffffu, tapmax = 0u;
-                        // ODD: the tile holds values lerp_fma is not certified for -> SciPy's sum
                         // GENX: the x binade (shift, rounding constant, masks) from each pixel's own
                         // exponent instead of the tile's: 8 more integer operations per pixel
-                        auto sample4 = [&](auto odd_tag, auto genx_tag) {
-                            constexpr bool ODD = decltype(odd_tag)::value;
+                        auto sample4 = [&](auto genx_tag) {
                             constexpr bool GENX = decltype(genx_tag)::value;
 #pragma unroll
                             for (int k = 0; k < kCols; ++k) {
@@ -1011,7 +957,7 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
                                 }
                                 const uint32_t xi = nx >> shx, yi = ny >> shy;
                                 const uint32_t fx = nx & mkx, fy = ny & mky;
-                                if (!WIDE && BLEND == DCB_BLEND_EXACT && DCB_IMG_EXACT_RAW == 2) {
+                                if (BLEND == DCB_BLEND_EXACT && DCB_IMG_EXACT_RAW == 2) {
                                     // The exact blend in the SCALED domain (see scaled_f64): taps are
                                     // widened by one integer multiply-wide each (no conversion, no
                                     // float64 tile), the certified FMA blend runs on v * 2^-896, and the
@@ -1019,6 +965,8 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
                                     // half-ulp added -- the certificate excludes ties, and the float32
                                     // rounding boundary sits at bit 28 of the low word whether the
                                     // result is a float32 normal or denormal.
+                                    // (fractions through I2F on the XU pipe plus an exponent step were
+                                    // measured: 46.0 us against 44.6, profiles/r2/ab_frac_i2f.txt)
                                     const double tx = __dsub_rn(__hiloint2double(__double2hiint(ux), (int)fx), Mx);
                                     const double ty = __dsub_rn(__hiloint2double(__double2hiint(uy), (int)fy), My);
                                     const uint32_t qa = (DCB_ABL & 2) ? base_s + 4u * (org + (yi & 1u))
@@ -1046,7 +994,7 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
                                     v[k] = __uint_as_float((uint32_t)(r >> 29));
                                     continue;
                                 }
-                                if (!WIDE && BLEND != DCB_BLEND_LERP32) {
+                                if (BLEND != DCB_BLEND_LERP32) {
                                     // fp64 blend from the raw float32 box: four conversions per pixel
                                     const double tx = __dsub_rn(__hiloint2double(__double2hiint(ux), (int)fx), Mx);
                                     const double ty = __dsub_rn(__hiloint2double(__double2hiint(uy), (int)fy), My);
@@ -1072,7 +1020,7 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
                                     v[k] = __double2float_rn(sd);
                                     continue;
                                 }
-                                if (!WIDE) {
+                                {
                                     // fraction as a float: exponent 150 - sh puts its ulp at 2^-sh
                                     const float tx = __uint_as_float(e32x | fx) - __uint_as_float(e32x);
                                     const float ty = __uint_as_float(e32y | fy) - __uint_as_float(e32y);
@@ -1085,40 +1033,13 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
                                     const float top = fmaf(b - a, tx, a);
                                     const float bot = fmaf(d - c, tx, c);
                                     v[k] = fmaf(bot - top, ty, top);
-                                    continue;
                                 }
-                                // fraction: the sum with its integer bits masked off, minus the rounding
-                                // constant (exact; the masked pair keeps the sum's own high word)
-                                const double tx = __dsub_rn(__hiloint2double(__double2hiint(ux), (int)fx), Mx);
-                                const double ty = __dsub_rn(__hiloint2double(__double2hiint(uy), (int)fy), My);
-                                const uint32_t qa = base_s + 8u * (yi * bw + xi);
-                                const double a = lds_f64<0>(qa), b = lds_f64<8>(qa);
-                                const double c = lds_f64<8 * kImgBoxW>(qa), d = lds_f64<8 * kImgBoxW + 8>(qa);
-                                double sd;
-                                if (BLEND == DCB_BLEND_LERP64) {
-                                    const double top = fma(b - a, tx, a);
-                                    const double bot = fma(d - c, tx, c);
-                                    sd = fma(bot - top, ty, top);
-                                } else if (ODD) {
-                                    sd = blend_exact(a, b, c, d, tx, ty);
-                                } else {
-                                    sd = lerp_fma(a, b, c, d, tx, ty);
-                                    accb = min(accb, cert_key(sd, kBlendCertAdd));
-                                }
-                                v[k] = __double2float_rn(sd);
                             }
                         };
-                        if ((inf.x & 0xfu) == 0xfu) {
-                            if (tile_odd)
-                                sample4(std::true_type{}, std::false_type{});
-                            else
-                                sample4(std::false_type{}, std::false_type{});
-                        } else {
-                            if (tile_odd)
-                                sample4(std::true_type{}, std::true_type{});
-                            else
-                                sample4(std::false_type{}, std::true_type{});
-                        }
+                        if ((inf.x & 0xfu) == 0xfu)
+                            sample4(std::false_type{});
+                        else
+                            sample4(std::true_type{});
                         // (a blend within 32 ulp64 of a rounding boundary: the exact row below)
                         done = !__any_sync(0xffffffffu, accb < kBlendCertLim || tapmax >= 0x7f800000u);
                         n_bfail += done ? 0u : 1u;
@@ -1140,7 +1061,6 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
                          ((unsigned)iy[k] < (unsigned)lim_y);
                 }
                 if (__all_sync(0xffffffffu, ok)) {
-                    double sd[WIDE ? kCols : 1];
 #pragma unroll
                     for (int k = 0; k < kCols; ++k) {
                         const float tx = xf[k] - (tfx[k] - 8388608.0f);  // exact
@@ -1149,7 +1069,7 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
                         if (ORDER == 0) {
                             const int sel = idx + (tx >= 0.5f ? 1 : 0) + (ty >= 0.5f ? bw : 0);
                             v[k] = rawt[sel];
-                        } else if (!WIDE && BLEND != DCB_BLEND_LERP32) {
+                        } else if (BLEND != DCB_BLEND_LERP32) {
                             const float *q = rawt + idx;
                             const double a = q[0], b = q[1];
                             const double c = q[bw], d = q[bw + 1];
@@ -1160,44 +1080,16 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
                             } else {
                                 v[k] = finish_f64(blend_exact(a, b, c, d, (double)tx, (double)ty), p.rint);
                             }
-                        } else if (!WIDE) {
+                        } else {
                             const float *q = rawt + idx;
                             const float a = q[0], b = q[1];
                             const float c = q[bw], d = q[bw + 1];
                             const float top = fmaf(b - a, tx, a);
                             const float bot = fmaf(d - c, tx, c);
                             v[k] = fmaf(bot - top, ty, top);
-                        } else {
-                            double a, b, c, d;
-                            if (DCB_IMG_LDS32 && kImgBoxW > 0) {
-                                const uint32_t qa = wide_s + 8u * (uint32_t)idx;
-                                a = lds_f64<0>(qa), b = lds_f64<8>(qa);
-                                c = lds_f64<8 * kImgBoxW>(qa), d = lds_f64<8 * kImgBoxW + 8>(qa);
-                            } else {
-                                const double *q = widet + idx;
-                                a = q[0], b = q[1];
-                                c = q[bw], d = q[bw + 1];
-                            }
-                            // (an integer-pipe widening of tx, ty -- one IMAD.WIDE + a select for
-                            // zero -- was measured: 64.7 us instead of 61.7 us; F2F stays)
-                            const double wx1 = (double)tx, wy1 = (double)ty;
-                            if (BLEND == DCB_BLEND_LERP64) {
-                                const double top = fma(b - a, wx1, a);
-                                const double bot = fma(d - c, wx1, c);
-                                sd[WIDE ? k : 0] = fma(bot - top, wy1, top);
-                            } else {
-                                sd[WIDE ? k : 0] = blend_exact(a, b, c, d, wx1, wy1);
-                            }
                         }
                     }
-                    if (WIDE) {
-                        if (p.rint) {  // integer image: SciPy's +-0.5 and truncate, still in fp64
-#pragma unroll
-                            for (int k = 0; k < kCols; ++k) sd[WIDE ? k : 0] = round_half_away(sd[WIDE ? k : 0]);
-                        }
-#pragma unroll
-                        for (int k = 0; k < kCols; ++k) v[k] = __double2float_rn(sd[WIDE ? k : 0]);
-                    } else if (ORDER == 1 && BLEND == DCB_BLEND_LERP32 && p.rint) {
+                    if (ORDER == 1 && BLEND == DCB_BLEND_LERP32 && p.rint) {                    } else if (ORDER == 1 && BLEND == DCB_BLEND_LERP32 && p.rint) {
 #pragma unroll
                         for (int k = 0; k < kCols; ++k) v[k] = finish_f32(v[k], 1);
                     }
@@ -1232,7 +1124,6 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
                 tile_rows(std::false_type{});
             if (n_bfail != 0 && p.stats != nullptr && lane == 0)
                 atomicAdd(p.stats + 3, (unsigned long long)n_bfail);
-            if (tile_odd && p.stats != nullptr && threadIdx.x == 0) atomicAdd(p.stats + 4, 1ull);
         }
         // this warp is done with buffer i&1 (and with its plan record)
         __syncwarp();
@@ -1253,39 +1144,6 @@ __global__ void __launch_bounds__(image_threads(ImageKernelTraits<ORDER, BLEND>:
         q[5] = dbg_wmax;
     }
 #endif
-}
-
-__device__ __forceinline__ bool widen_part(const ImageParams &p, unsigned char *smem, int buf,
-                                           int part, int lane) {
-    const uint4 *src4 = reinterpret_cast<const uint4 *>(smem);
-    double2 *dst2 = reinterpret_cast<double2 *>(smem + (size_t)(1 + 2 * buf) * p.stage_bytes);
-    const int n4 = (p.bw * p.bh) >> 2;
-    constexpr int kStep = 32 * kImgProducers;
-    // as unsigned integers: hi = largest bit pattern (sign bit or Inf / NaN => >= 0x7f800000),
-    // lo = smallest pattern - 1 (zero wraps to the top, so it is ignored)
-    uint32_t hi = 0u, lo = 0xffffffffu;
-    auto put = [&](int e, const uint4 &u) {
-        dst2[2 * e] = make_double2((double)__uint_as_float(u.x), (double)__uint_as_float(u.y));
-        dst2[2 * e + 1] = make_double2((double)__uint_as_float(u.z), (double)__uint_as_float(u.w));
-        hi = __vimax3_u32(hi, u.x, u.y);
-        hi = __vimax3_u32(hi, u.z, u.w);
-        lo = __vimin3_u32(lo, u.x - 1u, u.y - 1u);
-        lo = __vimin3_u32(lo, u.z - 1u, u.w - 1u);
-    };
-    int e = lane + 32 * part;
-    for (; e + 3 * kStep < n4; e += 4 * kStep) {
-        const uint4 u0 = src4[e], u1 = src4[e + kStep], u2 = src4[e + 2 * kStep],
-                    u3 = src4[e + 3 * kStep];
-        put(e, u0);
-        put(e + kStep, u1);
-        put(e + 2 * kStep, u2);
-        put(e + 3 * kStep, u3);
-    }
-    for (; e < n4; e += kStep) {
-        const uint4 u = src4[e];
-        put(e, u);
-    }
-    return hi >= 0x7f800000u || lo < 0x17800000u - 1u;
 }
 
 }  // namespace dcb
