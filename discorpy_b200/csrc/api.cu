@@ -148,17 +148,46 @@ static void persp_slopes(const dcb_persp &m, int H, int W, double *gmain, double
 }
 
 typedef void (*StackKernel)(const RemapParams, const CUtensorMap);
+static int image_sched_slot(unsigned **out);   // two self-resetting counters per launch, below
 
-// Launch planning for the Z-stack kernel (remap_stack.cuh).
-static int plan_and_launch_stack(StackKernel kern, bool widen, RemapParams &p, double gmain,
+// Launch planning for the Z-stack kernel (remap_stack.cuh).  kerns[0] is the 128 x 16 tile
+// instantiation, kerns[1] the 64 x 32 one.
+static int plan_and_launch_stack(const StackKernel (&kerns)[2], bool widen, RemapParams &p, double gmain,
                                  double gcross,
                                  int path_req, size_t src_pitch_bytes, size_t src_slice_bytes,
                                  cudaStream_t stream) {
     DevProps props;
     int rc = device_props(&props);
     if (rc != DCB_OK) return rc;
-    const int TH = kStkTileH;
-    p.tiles_x = (p.W + kTileW - 1) / kTileW;
+    if (!(gmain < 64.0) || !(gcross < 64.0)) gmain = gcross = 64.0;  // NaN / absurd
+    const int max_stage = 24 * 1024;
+    // footprint bound of a tw x th tile: +3 footprint slack, +3 because the box start is aligned
+    // down to 4 floats
+    auto bound = [&](int tw_, int th_, long long *w, long long *h) {
+        const double tw = std::min(tw_, p.W) - 1, th = std::min(th_, p.nrows) - 1;
+        *w = (long long)std::ceil(gmain * tw + gcross * th) + 3 + 3;
+        *h = (long long)std::ceil(gmain * th + gcross * tw) + 3;
+    };
+    // Tile shape: 128 x 16 whenever its footprint bound can be staged; otherwise the shape whose
+    // bound overshoots its largest stageable box the least (a sheared map stretches the source
+    // rows of a wide tile: config 5 needs up to 165 rows for 128 x 16 output pixels).
+    // DCB_STK_SHAPE=0/1 forces a shape (A/B runs).
+    int shape = 0;
+    {
+        long long wa, ha, wb, hb;
+        bound(kTileW, kStkTileH, &wa, &ha);
+        bound(64, 32, &wb, &hb);
+        const bool a_fits = wa <= 256 && ha <= 256 && wa * ha * 4 <= max_stage;
+        if (!a_fits) {
+            const double over_a = std::max(1.0, wa / 144.0) * std::max(1.0, ha / 42.0);
+            const double over_b = std::max(1.0, wb / 96.0) * std::max(1.0, hb / 64.0);
+            shape = over_b < over_a ? 1 : 0;
+        }
+        if (const char *env = getenv("DCB_STK_SHAPE")) shape = atoi(env) ? 1 : 0;
+    }
+    const StackKernel kern = kerns[shape];
+    const int TW = shape ? 64 : kTileW, TH = shape ? 32 : kStkTileH;
+    p.tiles_x = (p.W + TW - 1) / TW;
     p.tiles_y = (p.nrows + TH - 1) / TH;
     const long long tiles_xy = (long long)p.tiles_x * p.tiles_y;
 
@@ -175,21 +204,18 @@ static int plan_and_launch_stack(StackKernel kern, bool widen, RemapParams &p, d
     const int src_rows = p.ylast - p.yorg + 1;
     int bw = 0, bh = 0, nstage = 0;
     if (staged) {
-        if (!(gmain < 64.0) || !(gcross < 64.0)) gmain = gcross = 64.0;  // NaN / absurd
-        const double tw = std::min(kTileW, p.W) - 1, th = std::min(TH, p.nrows) - 1;
-        // +3 footprint slack, +3 because the box start is aligned down to 4 floats
-        long long need_w = (long long)std::ceil(gmain * tw + gcross * th) + 3 + 3;
-        long long need_h = (long long)std::ceil(gmain * th + gcross * tw) + 3;
+        long long need_w, need_h;
+        bound(TW, TH, &need_w, &need_h);
         need_w = std::min<long long>(need_w, (long long)p.W + 3);
         need_h = std::min<long long>(need_h, src_rows);
         bw = (int)((need_w + 3) / 4 * 4);
         bh = (int)need_h;
-        const int max_stage = 24 * 1024;
         if (bw > 256 || bh > 256 || (long long)bw * bh * 4 > max_stage) {
-            // footprint bound too large (strong magnification somewhere): stage a
-            // modest box; tiles that do not fit fall back to direct gathers.
-            bw = std::min(256, (std::min(kTileW + 16, (p.W + 3) / 4 * 4 + 4)));
-            bh = std::min(std::min(TH + 8, src_rows), max_stage / (bw * 4));
+            // footprint bound too large (strong magnification somewhere): stage the largest box
+            // a stage holds (144 x 42 / 96 x 64); tiles that do not fit it fall back to direct
+            // gathers.  (Round 1 staged only TH + 8 rows here: 15 % of config 4's tiles missed.)
+            bw = std::min(256, (std::min(TW + (shape ? 32 : 16), (p.W + 3) / 4 * 4 + 4)));
+            bh = std::min(src_rows, max_stage / (bw * 4));
         }
         if (const char *env = getenv("DCB_STK_BOX")) {   // diagnostics: "w,h" forces the staged box
             int ew = 0, eh = 0;
@@ -204,7 +230,7 @@ static int plan_and_launch_stack(StackKernel kern, bool widen, RemapParams &p, d
         const long long stage = ((long long)bw * bh * 4 + 127) / 128 * 128;
         // (the fp64 blends keep two float64 copies of a box = 4 stages' worth next to the ring)
         nstage = (int)std::max<long long>(
-            2, std::min<long long>(kStkMaxStages, (100 * 1024) / stage - (widen ? 4 : 0)));
+            2, std::min<long long>(kStkMaxStages, (DCB_STK_SMEM_KB * 1024) / stage - (widen ? 4 : 0)));
     }
     p.bw = bw;
     p.bh = bh;
@@ -259,6 +285,8 @@ static int plan_and_launch_stack(StackKernel kern, bool widen, RemapParams &p, d
     if (occ < 1) return fail(DCB_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
     const int grid = (int)std::min<long long>(nitems, (long long)occ * props.sm_count);
 
+    rc = image_sched_slot(&p.sched);
+    if (rc != DCB_OK) return rc;
     kern<<<grid, kThreads, smem, stream>>>(p, tmap);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -707,21 +735,30 @@ static int check_options(const dcb_options *opt, dcb_options *o) {
     return DCB_OK;
 }
 
+// the two tile shapes of the Z-stack kernel (remap_stack.cuh): [0] 128 x 16, [1] 64 x 32
+struct StackKernelPair {
+    StackKernel k[2];
+};
 template <bool ROUND32, bool RINT>
-static StackKernel pick_stack_kernel_r(int order, int blend) {
+static StackKernelPair pick_stack_kernel_r(int order, int blend) {
     // order 0 copies pixels: nothing to round
-    if (order == 0) return remap_stack_kernel<0, DCB_BLEND_EXACT, ROUND32, false>;
+    if (order == 0)
+        return {{remap_stack_kernel<0, DCB_BLEND_EXACT, ROUND32, false, 4>,
+                 remap_stack_kernel<0, DCB_BLEND_EXACT, ROUND32, false, 2>}};
     switch (blend) {
         case DCB_BLEND_LERP64:
-            return remap_stack_kernel<1, DCB_BLEND_LERP64, ROUND32, RINT>;
+            return {{remap_stack_kernel<1, DCB_BLEND_LERP64, ROUND32, RINT, 4>,
+                     remap_stack_kernel<1, DCB_BLEND_LERP64, ROUND32, RINT, 2>}};
         case DCB_BLEND_LERP32:
-            return remap_stack_kernel<1, DCB_BLEND_LERP32, ROUND32, RINT>;
+            return {{remap_stack_kernel<1, DCB_BLEND_LERP32, ROUND32, RINT, 4>,
+                     remap_stack_kernel<1, DCB_BLEND_LERP32, ROUND32, RINT, 2>}};
         default:
-            return remap_stack_kernel<1, DCB_BLEND_EXACT, ROUND32, RINT>;
+            return {{remap_stack_kernel<1, DCB_BLEND_EXACT, ROUND32, RINT, 4>,
+                     remap_stack_kernel<1, DCB_BLEND_EXACT, ROUND32, RINT, 2>}};
     }
 }
 template <bool ROUND32>
-static StackKernel pick_stack_kernel(int order, int blend, int rint) {
+static StackKernelPair pick_stack_kernel(int order, int blend, int rint) {
     return rint ? pick_stack_kernel_r<ROUND32, true>(order, blend)
                 : pick_stack_kernel_r<ROUND32, false>(order, blend);
 }
@@ -1101,9 +1138,9 @@ int dcb_unwarp_stack_backward_f32(const float *src, float *dst, int D, int H, in
     }
     const bool widen = false;  // no float64 copy of the staged box (see StackWeights)
     if (coord_round)
-        return plan_and_launch_stack(pick_stack_kernel<true>(o.order, o.blend, p.rint), widen, p, gm, gc,
+        return plan_and_launch_stack(pick_stack_kernel<true>(o.order, o.blend, p.rint).k, widen, p, gm, gc,
                                      o.path, src_pitch, src_slice_stride, (cudaStream_t)stream);
-    return plan_and_launch_stack(pick_stack_kernel<false>(1, o.blend, p.rint), widen, p, gm, gc, o.path,
+    return plan_and_launch_stack(pick_stack_kernel<false>(1, o.blend, p.rint).k, widen, p, gm, gc, o.path,
                                  src_pitch, src_slice_stride, (cudaStream_t)stream);
 }
 

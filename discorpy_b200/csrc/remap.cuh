@@ -41,6 +41,7 @@ struct RemapParams {
     int bw, bh, nstage;  // staged box; nstage == 0 => direct gathers only
     unsigned stage_bytes, box_bytes;
     int rint, pad;       // 1: integer image, round half away from zero (see finish_f64)
+    unsigned *sched;     // [0] next work item - gridDim.x, [1] CTAs done (the last one resets both)
     RadialDev rad;
     PerspDev per;
 };

@@ -34,9 +34,19 @@
 
 namespace dcb {
 
-constexpr int kStkTileH = 16;
-constexpr int kStkRows = kStkTileH / kWarps;  // 2 rows per warp
-constexpr int kStkPx = kStkRows * kCols;      // 8 pixels per thread
+#ifndef DCB_STK_MINB
+#define DCB_STK_MINB 2
+#endif
+#ifndef DCB_STK_SMEM_KB
+#define DCB_STK_SMEM_KB 100
+#endif
+// Output tile shapes (template parameter COLS = columns per thread): 128 x 16 (COLS 4, two rows per
+// warp) for ordinary maps, 64 x 32 (COLS 2, four rows per warp) for strongly sheared ones, whose
+// 128-pixel tile rows have source footprints too tall to stage (BASELINE config 5: median 24,
+// 90th percentile 67 source rows for 16 output rows; half its tiles missed the staged box and
+// gathered from global memory).  Every store instruction still writes one full 128-byte line.
+constexpr int kStkPx = 8;                     // pixels per thread
+constexpr int kStkTileH = 16;                 // the 128 x 16 shape (host side: plan_and_launch_stack)
 constexpr int kStkMaxStages = 8;
 
 // sqrt for the tile geometry: the 5-operation one-ulp form of remap_image.cuh (dsqrt_nz) with
@@ -49,6 +59,16 @@ __device__ __forceinline__ double dsqrt_fast0(double s) {
     const double q = fma(e, 0.375, 0.5) * e;
     const double r = fma(g, q, g);
     return (__double2hiint(s) < 0x00100000) ? 0.0 : r;
+}
+
+#ifndef DCB_STK_SCALED
+#define DCB_STK_SCALED 1
+#endif
+// see scaled_f64 (remap_image.cuh): the double v * 2^-896 of a non-negative finite float v
+__device__ __forceinline__ double scaled_tap(float f) {
+    unsigned long long w;
+    asm("mul.wide.u32 %0, %1, 536870912;" : "=l"(w) : "r"(__float_as_uint(f)));
+    return __longlong_as_double((long long)w);
 }
 
 // How the per-pixel sampling state is kept across the slices of a chunk.
@@ -71,13 +91,16 @@ struct StackWeights {
 // RINT: integer image, SciPy's round-half-away-from-zero on the fp64 sum (a
 // template parameter: as a run-time flag it cost a DSETP, three FSEL and an
 // XU-pipe FRND per pixel and slice, profiles/r1/ncu_stack_v7.txt).
-template <int ORDER, int BLEND, bool ROUND32, bool RINT_>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int ORDER, int BLEND, bool ROUND32, bool RINT_, int COLS>
+__global__ void __launch_bounds__(kThreads, DCB_STK_MINB)
     remap_stack_kernel(const __grid_constant__ RemapParams p,
                        const __grid_constant__ CUtensorMap tmap) {
     using CT = typename std::conditional<ROUND32, float, double>::type;
     using SW = StackWeights<ORDER, BLEND, ROUND32>;
     constexpr int RINT = RINT_ ? 1 : 0;
+    constexpr int ROWS = kStkPx / COLS;      // rows per warp
+    constexpr int TW = 32 * COLS;            // tile width
+    constexpr int TH = kWarps * ROWS;        // tile height
 
     extern __shared__ __align__(128) unsigned char smem[];
     // layout: [nstage raw boxes][full][empty][red]
@@ -89,13 +112,23 @@ __global__ void __launch_bounds__(kThreads, 2)
     const int warp = threadIdx.x >> 5;
     const bool staged = p.nstage > 0;
     const uint32_t S = (uint32_t)p.nstage;
-    if (staged && threadIdx.x == 0) {
-        for (int s = 0; s < p.nstage; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kWarps);
+    // Work items are CLAIMED from a counter, one ahead of the item being processed, instead of
+    // being dealt round-robin: the CTAs in flight then always hold the most recent consecutive
+    // items -- neighbouring tiles at the same slices, whose box halos are L2 hits -- however far
+    // their speeds have drifted apart.  (Dealt statically, a 2048-slice stack ran at 0.46 of the
+    // HBM peak where a 64-slice one reached 0.60 with the same tiles: after a few hundred items
+    // per CTA the neighbours were no longer concurrent and every halo came from DRAM.)
+    __shared__ int s_item[2];
+    if (threadIdx.x == 0) {
+        s_item[0] = (int)blockIdx.x;   // the first item needs no claim
+        if (staged) {
+            for (int s = 0; s < p.nstage; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], kWarps);
+            }
+            fence_mbar_init();
+            tma_prefetch_desc(&tmap);
         }
-        fence_mbar_init();
-        tma_prefetch_desc(&tmap);
     }
     __syncthreads();
 
@@ -103,16 +136,21 @@ __global__ void __launch_bounds__(kThreads, 2)
     int par = 0;
     const int wmax = p.W - 1;
     const int hmax = p.H - 1;
-    const int y_end = p.row0 + p.nrows;
     const int bw = p.bw;
+    const int y_end = p.row0 + p.nrows;
 
-    for (int item = blockIdx.x; item < p.ntiles; item += gridDim.x, par ^= 1) {
+    for (;; par ^= 1) {
+        const int item = s_item[par];
+        if (item >= p.ntiles) break;
+        // (read by the other threads after the barrier every item has: the bounding-box exchange
+        // of staged launches, the one at the end of the loop body otherwise)
+        if (threadIdx.x == 0) s_item[par ^ 1] = (int)gridDim.x + (int)atomicAdd(&p.sched[0], 1u);
         const int txi = item % p.tiles_x;
         const int rest = item / p.tiles_x;
         const int tyi = rest % p.tiles_y;
         const int zci = rest / p.tiles_y;
-        const int x_base = txi * kTileW + lane;
-        const int y_base = p.row0 + tyi * kStkTileH + warp * kStkRows;
+        const int x_base = txi * TW + lane;
+        const int y_base = p.row0 + tyi * TH + warp * ROWS;
         const int z0 = zci * p.zchunk;
         const int nz = min(p.zchunk, p.D - z0);
 
@@ -121,23 +159,23 @@ __global__ void __launch_bounds__(kThreads, 2)
         unsigned dxm = 0, dym = 0;             // bit i: second tap is one column right / one row down
         CT tx[kStkPx], ty[kStkPx];
         {
-            double xu[kCols], xu2[kCols];
+            double xu[COLS], xu2[COLS];
 #pragma unroll
-            for (int k = 0; k < kCols; ++k) {
+            for (int k = 0; k < COLS; ++k) {
                 xu[k] = (double)min(x_base + 32 * k, wmax) - p.rad.xc;  // :138 (edge lanes redo a valid pixel)
                 xu2[k] = __dmul_rn(xu[k], xu[k]);
             }
 #pragma unroll
-            for (int j = 0; j < kStkRows; ++j) {
+            for (int j = 0; j < ROWS; ++j) {
                 const double yu = (double)min(y_base + j, y_end - 1) - p.rad.yc;  // :139
                 const double yu2 = __dmul_rn(yu, yu);
-                double r[kCols], f[kCols];
+                double r[COLS], f[COLS];
 #pragma unroll
-                for (int k = 0; k < kCols; ++k) r[k] = dsqrt_fast0(__dadd_rn(xu2[k], yu2));  // :141
-                radial_factor<kCols>(p.rad.a, p.rad.n, r, f);                              // :142-143
+                for (int k = 0; k < COLS; ++k) r[k] = dsqrt_fast0(__dadd_rn(xu2[k], yu2));  // :141
+                radial_factor<COLS>(p.rad.a, p.rad.n, r, f);                              // :142-143
 #pragma unroll
-                for (int k = 0; k < kCols; ++k) {  // :144-145 (image, chunk) / :219-220 (slice)
-                    const int i = j * kCols + k;
+                for (int k = 0; k < COLS; ++k) {  // :144-145 (image, chunk) / :219-220 (slice)
+                    const int i = j * COLS + k;
                     const CT cx = clamp_coord<CT>(fma(f[k], xu[k], p.rad.xc), wmax);
                     const CT cy = clamp_coord<CT>(fma(f[k], yu, p.rad.yc), hmax);
                     // floor and fraction of a coordinate in [0, 2^23) without the XU pipe (F2I / I2F):
@@ -191,7 +229,8 @@ __global__ void __launch_bounds__(kThreads, 2)
                 rd[3 * kWarps + warp] = mxy;
             }
             // a pixel whose +1 tap was folded back needs the generic tap offsets
-            const bool mine = (ORDER == 1) && (dxm != 0xffu || dym != 0xffu);
+            constexpr unsigned kAllPx = (1u << kStkPx) - 1u;
+            const bool mine = (ORDER == 1) && (dxm != kAllPx || dym != kAllPx);
             edge = __syncthreads_or(mine ? 1 : 0) != 0;
             mnx = mny = INT_MAX;
             mxx = mxy = -1;
@@ -206,6 +245,10 @@ __global__ void __launch_bounds__(kThreads, 2)
             // multiple of 16 bytes, otherwise UTMALDG raises "illegal instruction"
             bx0 = mnx & ~3;
             by0 = mny;
+            // (A second, smaller box for the tiles whose footprint fits it -- two tensor maps,
+            // box pitch chosen per item -- was measured: the source bytes moved per output tile
+            // fall from 3x to 1.6x on configs 4 / 5 and nothing gets faster, the exact blends
+            // lose 4-8 % to the extra per-item state; profiles/r2/bench_stack_two_boxes_s4.jsonl.)
             fits = (mxx - bx0 + 1 <= bw) && (mxy - by0 + 1 <= p.bh);
         }
 
@@ -247,9 +290,9 @@ __global__ void __launch_bounds__(kThreads, 2)
             }
             float *orow = p.dst + (long long)z0 * p.dst_slice +
                           (long long)(y_base - p.row0) * p.dst_pitch + x_base;
-            bool colok[kCols];
+            bool colok[COLS];
 #pragma unroll
-            for (int k = 0; k < kCols; ++k) colok[k] = (x_base + 32 * k <= wmax);
+            for (int k = 0; k < COLS; ++k) colok[k] = (x_base + 32 * k <= wmax);
 
             // ONE slice loop for every tile.  (Measured, profiles/r1/stack_loop_ab.txt: as soon
             // as the loop exists in several specialised copies under CTA-uniform branches the
@@ -301,48 +344,93 @@ __global__ void __launch_bounds__(kThreads, 2)
                 if (lane == 0) mbar_arrive(&empty[st]);
                 // phase 2: the blend
                 float v[kStkPx];
+                if (ORDER == 0) {
 #pragma unroll
-                for (int i = 0; i < kStkPx; ++i) {
-                    if (ORDER == 0) {
-                        v[i] = fa[i];
-                        continue;
-                    }
-                    if (SW::kF32) {
+                    for (int i = 0; i < kStkPx; ++i) v[i] = fa[i];
+                } else if (SW::kF32) {
+#pragma unroll
+                    for (int i = 0; i < kStkPx; ++i) {
                         const float top = fmaf(fb[i] - fa[i], wf[i][0], fa[i]);
                         const float bot = fmaf(fd[i] - fc[i], wf[i][0], fc[i]);
                         v[i] = finish_f32(fmaf(bot - top, wf[i][1], top), RINT);
-                        continue;
                     }
-                    const double a = (double)fa[i], b = (double)fb[ORDER == 1 ? i : 0],
-                                 c = (double)fc[ORDER == 1 ? i : 0], d = (double)fd[ORDER == 1 ? i : 0];
-                    if (SW::kW4) {
-                        double s = __dmul_rn(a, wd[i][0]);
-                        s = __dadd_rn(s, __dmul_rn(b, wd[i][1]));
-                        s = __dadd_rn(s, __dmul_rn(c, wd[i][2]));
-                        s = __dadd_rn(s, __dmul_rn(d, wd[i][3]));
-                        v[i] = finish_f64(s, RINT);
-                    } else if (BLEND == DCB_BLEND_LERP64) {
-                        const double top = fma(b - a, wd[i][0], a);
-                        const double bot = fma(d - c, wd[i][0], c);
-                        v[i] = finish_f64(fma(bot - top, wd[i][1], top), RINT);
+                } else {
+                    // The float64 blends with the taps as doubles a, b, c, d; `post` undoes the
+                    // scale of the taps (1 for converted taps).  Every operation is SciPy's,
+                    // in SciPy's order.
+                    auto blend8 = [&](auto widen, const double post) {
+#pragma unroll
+                        for (int i = 0; i < kStkPx; ++i) {
+                            const double a = widen(fa[i]), b = widen(fb[ORDER == 1 ? i : 0]),
+                                         c = widen(fc[ORDER == 1 ? i : 0]), d = widen(fd[ORDER == 1 ? i : 0]);
+                            double s;
+                            if (SW::kW4) {
+                                s = __dmul_rn(a, wd[i][0]);
+                                s = __dadd_rn(s, __dmul_rn(b, wd[i][1]));
+                                s = __dadd_rn(s, __dmul_rn(c, wd[i][2]));
+                                s = __dadd_rn(s, __dmul_rn(d, wd[i][3]));
+                            } else if (BLEND == DCB_BLEND_LERP64) {
+                                const double top = fma(b - a, wd[i][0], a);
+                                const double bot = fma(d - c, wd[i][0], c);
+                                s = fma(bot - top, wd[i][1], top);
+                            } else {
+                                // float64 coordinates: SciPy's two-step products, every step rounded
+                                const double wx1 = wd[i][0], wy1 = wd[i][1];
+                                const double wx0 = __dsub_rn(1.0, wx1), wy0 = __dsub_rn(1.0, wy1);
+                                s = __dmul_rn(__dmul_rn(a, wy0), wx0);
+                                s = __dadd_rn(s, __dmul_rn(__dmul_rn(b, wy0), wx1));
+                                s = __dadd_rn(s, __dmul_rn(__dmul_rn(c, wy1), wx0));
+                                s = __dadd_rn(s, __dmul_rn(__dmul_rn(d, wy1), wx1));
+                            }
+                            if (post != 1.0) s = __dmul_rn(s, post);   // exact: a power of two, no underflow
+                            v[i] = finish_f64(s, RINT);
+                        }
+                    };
+#if DCB_STK_SCALED
+                    if (BLEND == DCB_BLEND_LERP64 || DCB_STK_SCALED == 2) {
+                    // Taps widened on the integer pipe in the scaled domain (scaled_f64 in
+                    // remap_image.cuh: u * 2^29 read as a double is v * 2^-896): the four
+                    // conversions per pixel and slice kept the 16-lane XU pipe busier than HBM
+                    // (5 XU operations per pixel; profiles/r1/ncu_stack_v14_exact_16x4096.txt).
+                    // A power-of-two scale commutes with every rounding as long as nothing becomes
+                    // a denormal double, which holds when every tap of the thread is a positive
+                    // normal float of at least 2^-78 (fp32-rounded coordinates: weights >= 2^-48)
+                    // or 2^-30 (float64 coordinates: each weight >= 2^-43): one min / max over the
+                    // 32 taps; otherwise (zeros, negative values, Inf / NaN, tiny values) the warp
+                    // converts this slice's taps the old way.
+                    uint32_t hi = 0u, lo = 0xffffffffu;
+#pragma unroll
+                    for (int i = 0; i < kStkPx; ++i) {
+                        const uint32_t ua = __float_as_uint(fa[i]), ub = __float_as_uint(fb[ORDER == 1 ? i : 0]);
+                        const uint32_t uc = __float_as_uint(fc[ORDER == 1 ? i : 0]), ud = __float_as_uint(fd[ORDER == 1 ? i : 0]);
+                        hi = __vimax3_u32(hi, ua, ub);
+                        hi = __vimax3_u32(hi, uc, ud);
+                        lo = __vimin3_u32(lo, ua, ub);
+                        lo = __vimin3_u32(lo, uc, ud);
+                    }
+                    constexpr uint32_t kTapMin = SW::kW4 ? 0x18800000u : 0x30800000u;
+                    if (__all_sync(0xffffffffu, lo >= kTapMin && hi < 0x7f800000u)) {
+                        blend8([](float f) { return scaled_tap(f); }, 0x1p896);
                     } else {
-                        // float64 coordinates: SciPy's two-step products, every step rounded
-                        const double wx1 = wd[i][0], wy1 = wd[i][1];
-                        const double wx0 = __dsub_rn(1.0, wx1), wy0 = __dsub_rn(1.0, wy1);
-                        double s = __dmul_rn(__dmul_rn(a, wy0), wx0);
-                        s = __dadd_rn(s, __dmul_rn(__dmul_rn(b, wy0), wx1));
-                        s = __dadd_rn(s, __dmul_rn(__dmul_rn(c, wy1), wx0));
-                        s = __dadd_rn(s, __dmul_rn(__dmul_rn(d, wy1), wx1));
-                        v[i] = finish_f64(s, RINT);
+                        blend8([](float f) { return (double)f; }, 1.0);
                     }
+                    } else {
+                        // (the exact blends: with their 4 + 4 weight registers per pixel the two
+                        // copies of the blend spill -- 39.0 against 36.3 us per 4096^2 slice,
+                        // profiles/r2/bench_stack_scaled_s1.jsonl)
+                        blend8([](float f) { return (double)f; }, 1.0);
+                    }
+#else
+                    blend8([](float f) { return (double)f; }, 1.0);
+#endif
                 }
 #pragma unroll
-                for (int j = 0; j < kStkRows; ++j) {
+                for (int j = 0; j < ROWS; ++j) {
                     if (y_base + j < y_end) {
                         float *o = orow + (long long)j * p.dst_pitch;
 #pragma unroll
-                        for (int k = 0; k < kCols; ++k)
-                            if (colok[k]) __stcs(o + 32 * k, v[j * kCols + k]);
+                        for (int k = 0; k < COLS; ++k)
+                            if (colok[k]) __stcs(o + 32 * k, v[j * COLS + k]);
                     }
                 }
                 if (threadIdx.x == 0 && iz + p.nstage - 1 < nz) {
@@ -429,15 +517,24 @@ __global__ void __launch_bounds__(kThreads, 2)
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < kStkRows; ++j) {
+                for (int j = 0; j < ROWS; ++j) {
                     if (y_base + j < y_end) {
                         float *o = orow + (long long)j * p.dst_pitch;
 #pragma unroll
-                        for (int k = 0; k < kCols; ++k)
-                            if (x_base + 32 * k <= wmax) __stcs(o + 32 * k, v[j * kCols + k]);
+                        for (int k = 0; k < COLS; ++k)
+                            if (x_base + 32 * k <= wmax) __stcs(o + 32 * k, v[j * COLS + k]);
                     }
                 }
             }
+        }
+        if (!staged) __syncthreads();
+    }
+    // the last CTA through here leaves the counters as it found them
+    if (threadIdx.x == 0) {
+        const unsigned d = atomicAdd(&p.sched[1], 1u);
+        if (d == gridDim.x - 1) {
+            p.sched[0] = 0u;
+            p.sched[1] = 0u;
         }
     }
 }

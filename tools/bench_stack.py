@@ -20,6 +20,7 @@ CASES = {
     "cfg2x16": (16, 4096, 4096, 2050.37, 2040.81, [COEF_DOT_05[i] / 3.0 ** i for i in range(5)], 1),
     "cfg2x64": (64, 4096, 4096, 2050.37, 2040.81, [COEF_DOT_05[i] / 3.0 ** i for i in range(5)], 1),
     "cfg4shard": (64, 2560, 2560, 1283.4, 1275.9, [1.0, -2e-5, 6e-8, -1e-10, 5e-14], 0),
+    "cfg4deep": (512, 2560, 2560, 1283.4, 1275.9, [1.0, -2e-5, 6e-8, -1e-10, 5e-14], 0),
     "cfg4chunk": (64, 2560, 2560, 1283.4, 1275.9, [1.0, -2e-5, 6e-8, -1e-10, 5e-14], 1),
     "cfg5shard": (8, 8192, 8192, 4100.3, 4090.8,
                   [1.0, -1e-5, 3e-8, -2e-11, 5e-15, -8e-19, 6e-23, -2e-27, 3e-32], 1),
@@ -29,7 +30,7 @@ CASES = {
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--cases", default=",".join(CASES))
+    ap.add_argument("--cases", default=",".join(c for c in CASES if c != "cfg4deep"))
     ap.add_argument("--blends", default="exact,lerp64,lerp32")
     ap.add_argument("--orders", default="1")
     args = ap.parse_args()
