@@ -335,6 +335,14 @@ def run_gpu_arm(args, rank, local_rank, world):
 
     # the very first launch of a (model, geometry) pair also builds its plan (remap_image.cuh):
     # time that cold call apart, it is not part of the steady-state metric
+    # (a 256 x 256 call first: the process's first launch also loads the kernels' modules and
+    # allocates the scheduler counters, which is not what a new calibration costs)
+    tiny_s, tiny_d = dcb.DeviceArray((256, 256)).fill(0.0), dcb.DeviceArray((256, 256))
+    t0 = time.perf_counter()
+    _cabi.check(fn(ctypes.c_void_p(tiny_s.ptr), ctypes.c_void_p(tiny_d.ptr), 256, 256, tiny_s.pitch,
+                   tiny_d.pitch, ctypes.byref(model), ctypes.byref(opt), sh))
+    dcb.synchronize()
+    first_call_us = (time.perf_counter() - t0) * 1e6
     dcb.plan_cache_clear()
     dcb.synchronize()
     t0 = time.perf_counter()
@@ -418,6 +426,7 @@ def run_gpu_arm(args, rank, local_rank, world):
             "exact": time_images(dcb.BLEND_EXACT), "lerp64": time_images(dcb.BLEND_LERP64),
             "lerp32": time_images(dcb.BLEND_LERP32), "order0": time_images(dcb.BLEND_EXACT, 0)}
         extras["single_image_cold_call_us"] = cold_call_us
+        extras["first_call_of_process_us"] = first_call_us
         # the same 4096^2 geometry as a Z-stack of slices sharing the model (a3, the path
         # unwarp_chunk_slices_backward takes): geometry evaluated once per tile
         depth = args.stack_depth
@@ -729,22 +738,29 @@ def bench_exchange(dcb, multigpu, post, comm, rank, world):
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant
 # kernel, from the committed `ncu --set full` capture (profiles/); None until
 # a capture exists for the current kernel.
-TRAFFIC_BYTES_PER_LAUNCH = 79762432 + 21441280
-TRAFFIC_SOURCE = ("profiles/r2/ncu_image_r2i_exact.txt: dram__bytes_read.sum 79.8 MB + "
-                  "dram__bytes_write.sum 21.4 MB of one launch (most of the 64 MiB output is "
+TRAFFIC_BYTES_PER_LAUNCH = 76521472 + 18578432
+TRAFFIC_SOURCE = ("profiles/r2/ncu_image_r2ac_exact.txt: dram__bytes_read.sum 76.5 MB + "
+                  "dram__bytes_write.sum 18.6 MB of one launch (most of the 64 MiB output is "
                   "still dirty in the 126 MB L2 when the profiled launch ends)")
 # What the SM side of one launch costs at 100 % of each pipe (us), from the instruction mix of
-# the committed capture (profiles/r2/ncu_image_r2i_exact.txt: thread instructions per pixel by
+# the committed capture (profiles/r2/ncu_image_r2ac_exact.txt: thread instructions per pixel by
 # pipe) and the pipe rates measured in round 1 (profiles/r1/microbench_*.txt: fp64 60.1 and XU
 # 15.6 thread-ops per clock per SM, issue 128): 16.78 Mpx / 148 SMs / 1.965 GHz x ops / rate.
+# issue_fp64_dispatch_us is the co-limit the ablation runs of round 2 point to
+# (profiles/r2/ablation_raw2_r2a1.txt): an fp64 instruction holds a sub-partition's issue port for
+# its whole dispatch -- 2.13 cycles, 3.07 with three distinct source registers -- so the 17.6 fp64
+# operations per pixel (8 of them three-register forms) cost 45 issue cycles, the other 44.8
+# instructions one each.
 def _colimit(ops_per_px, rate):
     return H * W / 148.0 / 1965.0 * ops_per_px / rate          # us
 
 
-COLIMIT = {"fp64_us": _colimit(17.8, 60.1), "xu_us": _colimit(2.4, 15.6),
-           "issue_us": _colimit(66.0, 128.0),
-           "source": "profiles/r2/ncu_image_r2i_exact.txt instruction mix; pipe rates "
-                     "profiles/r1/microbench_v1.txt"}
+COLIMIT = {"fp64_us": _colimit(17.6, 60.1), "xu_us": _colimit(0.2, 15.6),
+           "issue_us": _colimit(62.4, 128.0),
+           "issue_fp64_dispatch_us": _colimit(44.8 + 8 * 3.07 + 9.6 * 2.13, 128.0),
+           "source": "profiles/r2/ncu_image_r2ac_exact.txt instruction mix; pipe rates "
+                     "profiles/r1/microbench_v1.txt, microbench_fp64_operand_forms.txt; "
+                     "profiles/r2/ablation_raw2_r2a1.txt"}
 
 
 def main():
