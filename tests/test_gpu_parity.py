@@ -578,3 +578,58 @@ def test_unwarp_slice_backward_takes_any_numeric_index():
         assert np.max(np.abs(got - want)) <= 1e-5, index
         dev = post.unwarp_slice_backward(dcb.DeviceArray.from_host(stack), 101.3, 47.1, FACT5, index)
         assert np.array_equal(dev.to_host(), got)
+
+
+def test_dependent_launches_back_to_back():
+    """Programmatic dependent launch (csrc/remap_image.cuh: griddepcontrol): a launch whose source
+    is the output of the launch right before it in the stream must see all of it.  Three passes
+    chained on the device without a host synchronisation, twice (the second round reuses the
+    cached plans and reads them ahead of the grid dependency), each result against the oracle's
+    chain bit for bit; a model change in the middle builds a plan between two dependent launches."""
+    rng = np.random.default_rng(79)
+    mat = rng.random((1100, 1500), dtype=np.float32)
+    models = [(760.3, 540.9, FACT5), (700.1, 600.2, [1.0, 1e-5, -3e-9]), (760.3, 540.9, FACT5)]
+    want, stages = mat, []
+    for xc, yc, fact in models:
+        want = orc.unwarp_image_backward(want, xc, yc, fact)
+        stages.append(want)
+    for order_round in range(2):
+        cur = dcb.DeviceArray.from_host(mat)
+        outs = []
+        for xc, yc, fact in models:
+            cur = post.unwarp_image_backward(cur, xc, yc, fact)
+            outs.append(cur)
+        for k, (o, w) in enumerate(zip(outs, stages)):
+            assert np.array_equal(o.to_host(), w), (order_round, k)
+
+
+def test_launches_from_two_host_threads_share_no_scheduler_state():
+    """Every host thread has its own stream; the single-image and Z-stack kernels take their tile
+    counters from a ring of self-resetting slots (api.cu: image_sched_slot).  Two threads
+    launching at the same time must both get the oracle's bytes."""
+    import threading
+    rng = np.random.default_rng(80)
+    mats = [rng.random((900, 1300), dtype=np.float32) for _ in range(2)]
+    stack = rng.random((6, 200, 700), dtype=np.float32)
+    want_img = [orc.unwarp_image_backward(m, 640.2, 455.5, FACT5) for m in mats]
+    want_chunk = orc.unwarp_chunk_slices_backward(stack, 351.2, 99.5, FACT5, 0, 199)
+    errors = []
+
+    def worker(i):
+        try:
+            dcb.set_device(0)
+            dev = dcb.DeviceArray.from_host(mats[i])
+            for _ in range(12):
+                got = post.unwarp_image_backward(dev, 640.2, 455.5, FACT5).to_host()
+                if not np.array_equal(got, want_img[i]):
+                    errors.append(("image", i))
+                got = post.unwarp_chunk_slices_backward(stack, 351.2, 99.5, FACT5, 0, 199)
+                if not np.array_equal(got, want_chunk):
+                    errors.append(("chunk", i))
+        except Exception as exc:      # pragma: no cover
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors[:4]
