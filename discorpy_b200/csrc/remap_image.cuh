@@ -402,11 +402,18 @@ __global__ void __launch_bounds__(kThreads)
     TilePlan<TH> &out = plan[t];
     if (warp == 0) {
         TileBox bx = place_tile_box<MAP, TH>(p, x_lo, y_lo, lane);
-        if (MAP == MAP_RADIAL && p.fast && bx.use && x_lo + kTileW - 1 <= wmax) {
+        if (p.fast && bx.use && x_lo + kTileW - 1 <= wmax) {
             // x binade of the tile: the one of its centre pixel
-            const double xu = ((double)x_lo + 63.5) - p.rad.xc;
-            const double yu = ((double)y_lo + (TH - 1) * 0.5) - p.rad.yc;
-            const double xd = fma(radial_f(p.rad, xu, yu), xu, p.rad.xc);
+            double xd;
+            if (MAP == MAP_RADIAL) {
+                const double xu = ((double)x_lo + 63.5) - p.rad.xc;
+                const double yu = ((double)y_lo + (TH - 1) * 0.5) - p.rad.yc;
+                xd = fma(radial_f(p.rad, xu, yu), xu, p.rad.xc);
+            } else {
+                const double xm = (double)x_lo + 63.5, ym = (double)y_lo + (TH - 1) * 0.5;
+                const double den = p.per.c[6] * xm + p.per.c[7] * ym + 1.0;
+                xd = den > 0.0 ? (p.per.c[0] * xm + p.per.c[1] * ym + p.per.c[2]) / den : -1.0;
+            }
             const int ex = binade_of(xd);
             if (xd > 0.0 && ex >= 0 && ex <= 22) {
                 bx.shx = 23 - ex;
@@ -432,12 +439,23 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
         for (int i = 0; i < 6; ++i) rp.c[i] = 0.0;
         rp.info = 0, rp.mhi_y = 0, rp.mky = 0, rp.e32y = 0;
-        if (MAP == MAP_RADIAL && box.shx != 0 && y < y_end) {   // warp-uniform
+        if (box.shx != 0 && y < y_end) {   // warp-uniform
             const double yrow = (double)y;
             const double yu = __dsub_rn(yrow, p.rad.yc);
             const double xm = ((double)x_lo + 63.5) - p.rad.xc;   // xu at tau = 0
+            // projective map: what is interpolated along the row is w = 1 / (c6 x + c7 y + 1), the
+            // numerators are linear in x (MapEval<MAP_PERSP> holds c0 x and c3 x per column)
+            const double c8y = __dmul_rn(p.per.c[7], yrow);
+            const double a_row = fma(p.per.c[1], yrow, p.per.c[2]);   // c1 y + c2
+            const double e_row = fma(p.per.c[4], yrow, p.per.c[5]);   // c4 y + c5
             // node values on lanes 0..5, coefficient i on lane i, then broadcast
-            const double fn = radial_f(p.rad, fma(64.0, kPatchNodesX[lane % 6], xm), yu);
+            double fn;
+            if (MAP == MAP_RADIAL) {
+                fn = radial_f(p.rad, fma(64.0, kPatchNodesX[lane % 6], xm), yu);
+            } else {
+                const double xn = fma(64.0, kPatchNodesX[lane % 6], (double)x_lo + 63.5);
+                fn = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dmul_rn(p.per.c[6], xn), c8y), 1.0));
+            }
             double ci = 0.0;
 #pragma unroll
             for (int j = 0; j < 6; ++j)
@@ -446,7 +464,9 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
             for (int i = 0; i < 6; ++i) c[i] = __shfl_sync(0xffffffffu, ci, i);
             // y binade of the row: the one of its centre pixel (from the interpolant)
-            const double ydm = fma(c[0], yu, p.rad.yc);
+            const double ydm = MAP == MAP_RADIAL
+                                   ? fma(c[0], yu, p.rad.yc)
+                                   : __dmul_rn(c[0], fma(p.per.c[3], (double)x_lo + 63.5, e_row));
             const int ey = binade_of(ydm);
             const bool row_ok = ydm > 0.0 && ey >= 0 && ey <= 22;   // warp-uniform
             const int shx = box.shx, shy = 23 - (row_ok ? ey : 0);
@@ -464,16 +484,33 @@ __global__ void __launch_bounds__(kThreads)
                 f = fma(f, tau, c[2]);
                 f = fma(f, tau, c[1]);
                 f = fma(f, tau, c[0]);
-                const double xp = fma(f, xu, p.rad.xc), yp = fma(f, yu, p.rad.yc);
+                double xp, yp, xe, ye, mx, my;
+                if (MAP == MAP_RADIAL) {
+                    xp = fma(f, xu, p.rad.xc), yp = fma(f, yu, p.rad.yc);
+                    // the exact coordinates
+                    const double fe = radial_f(p.rad, xu, yu);
+                    xe = fma(fe, xu, p.rad.xc), ye = fma(fe, yu, p.rad.yc);
+                    // margin: the exact path's own variants (E/O split, one-ulp sqrt, Horner lengths
+                    // known at compile time) differ from this evaluation by a few ulp of F
+                    mx = 0x1p-48 * (fabs(xu) + fabs(xe)), my = 0x1p-48 * (fabs(yu) + fabs(ye));
+                } else {
+                    const double xdbl = (double)x;
+                    const double c1x = __dmul_rn(p.per.c[0], xdbl), c4x = __dmul_rn(p.per.c[3], xdbl);
+                    xp = __dmul_rn(f, __dadd_rn(c1x, a_row));
+                    yp = __dmul_rn(f, __dadd_rn(c4x, e_row));
+                    // the exact coordinates, MapEval<MAP_PERSP>'s operation order with IEEE divisions
+                    const double den = __dadd_rn(__dadd_rn(__dmul_rn(p.per.c[6], xdbl), c8y), 1.0);
+                    const double nxe = __dadd_rn(__dadd_rn(c1x, __dmul_rn(p.per.c[1], yrow)), p.per.c[2]);
+                    const double nye = __dadd_rn(__dadd_rn(c4x, __dmul_rn(p.per.c[4], yrow)), p.per.c[5]);
+                    const bool den_ok = den > 0x1p-900 && den < 0x1p900;
+                    xe = den_ok ? __ddiv_rn(nxe, den) : -1.0;
+                    ye = den_ok ? __ddiv_rn(nye, den) : -1.0;
+                    // margin: the kernel's reciprocal + Markstein quotients are within an ulp
+                    mx = 0x1p-48 * fabs(xe), my = 0x1p-48 * fabs(ye);
+                }
                 const uint32_t ny = (uint32_t)__double2loint(__dadd_rn(yp, My));
-                // the exact coordinates
-                const double fe = radial_f(p.rad, xu, yu);
-                const double xe = fma(fe, xu, p.rad.xc), ye = fma(fe, yu, p.rad.yc);
-                // margin: the exact path's own variants (E/O split, one-ulp sqrt, Horner lengths
-                // known at compile time) differ from this evaluation by a few ulp of F
                 bool oky = row_ok && xe > 0.0 && ye > 0.0 && xp > 0.0 &&
-                           dist_to_f32_boundary(xe) > 0x1p-48 * (fabs(xu) + fabs(xe)) &&
-                           dist_to_f32_boundary(ye) > 0x1p-48 * (fabs(yu) + fabs(ye));
+                           dist_to_f32_boundary(xe) > mx && dist_to_f32_boundary(ye) > my;
                 // same float32 value (this also pins the binade: a float32 of another binade is
                 // not a multiple of the grid or lies outside [2^23, 2^24] grid units)
                 oky = oky && (double)ny * gy == (double)__double2float_rn(ye) && ny >= (1u << 23) &&
@@ -639,7 +676,7 @@ template <int MAP, int ORDER, int BLEND, int NT, int TH, int MINB>
 __global__ void __launch_bounds__(kImgThreads, MINB)
     remap_image_kernel(const __grid_constant__ ImageParams p,
                        const __grid_constant__ CUtensorMap tmap) {
-    constexpr bool PATCH = (MAP == MAP_RADIAL) && kImgBoxW > 0;   // the patch path exists
+    constexpr bool PATCH = kImgBoxW > 0;   // the patch path exists
     constexpr int RPW = TH / kWarps;  // rows per sampling warp and tile
     constexpr int NBUF = kRawStages;   // stages = tile buffers the samplers read from
     constexpr int LOGB = kRawStages == 2 ? 1 : 2;
@@ -911,21 +948,34 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                     // bits 0..3: verified with the tile's x binade; bits 4..7: verified with the
                     // x binade taken per pixel (rows crossing a power of two in x)
                     if ((inf.x & 0xfu) == 0xfu || (inf.x & 0xf0u) == 0xf0u) {
-                        const double yu = __dsub_rn(yd, p.rad.yc);
                         double xq[kCols], yq[kCols];
-#pragma unroll
-                        for (int k = 0; k < kCols; ++k) {
-                            double f = fma(c45.y, tau[k], c45.x);
-                            if (DCB_ABL & 4) {
-                                f = c01.x + c45.y;
+                        {
+                            // per-row terms: radial yu; projective c1 y + c2 and c4 y + c5
+                            double ra, rb;
+                            if constexpr (MAP == MAP_RADIAL) {
+                                ra = __dsub_rn(yd, p.rad.yc), rb = 0.0;
                             } else {
-                            f = fma(f, tau[k], c23.y);
-                            f = fma(f, tau[k], c23.x);
-                            f = fma(f, tau[k], c01.y);
-                            f = fma(f, tau[k], c01.x);
+                                ra = fma(p.per.c[1], yd, p.per.c[2]), rb = fma(p.per.c[4], yd, p.per.c[5]);
                             }
-                            xq[k] = fma(f, ev.xu[k], p.rad.xc);
-                            yq[k] = fma(f, yu, p.rad.yc);
+#pragma unroll
+                            for (int k = 0; k < kCols; ++k) {
+                                double f = fma(c45.y, tau[k], c45.x);
+                                if (DCB_ABL & 4) {
+                                    f = c01.x + c45.y;
+                                } else {
+                                    f = fma(f, tau[k], c23.y);
+                                    f = fma(f, tau[k], c23.x);
+                                    f = fma(f, tau[k], c01.y);
+                                    f = fma(f, tau[k], c01.x);
+                                }
+                                if constexpr (MAP == MAP_RADIAL) {
+                                    xq[k] = fma(f, ev.xu[k], p.rad.xc);
+                                    yq[k] = fma(f, ra, p.rad.yc);
+                                } else {   // f interpolates 1 / (c6 x + c7 y + 1)
+                                    xq[k] = __dmul_rn(f, __dadd_rn(ev.c1x[k], ra));
+                                    yq[k] = __dmul_rn(f, __dadd_rn(ev.c4x[k], rb));
+                                }
+                            }
                         }
                         const int shy = (int)(inf.x >> 8) & 31;
                         const uint32_t mky = inf.z, e32y = inf.w;

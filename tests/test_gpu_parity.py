@@ -633,3 +633,30 @@ def test_launches_from_two_host_threads_share_no_scheduler_state():
     [t.start() for t in threads]
     [t.join() for t in threads]
     assert not errors, errors[:4]
+
+
+def test_projective_patch_path_equals_exact_path():
+    """correct_perspective_image on the patch path (verified row interpolants of 1 / denominator,
+    csrc/remap_image.cuh) gives the bytes of the exact division chain (DCB_IMG_FAST=0) and of
+    the oracle, for a mild and a strong keystone, orders 0 and 1."""
+    import os
+    rng = np.random.default_rng(81)
+    mat = rng.random((1200, 1664), dtype=np.float32) * 50.0
+    dev = dcb.DeviceArray.from_host(mat)
+    for coef in ([1.02, 0.01, -15.0, 0.005, 1.01, -8.0, 8e-6, -5e-6],
+                 [0.93, -0.04, 40.0, 0.02, 0.97, 25.0, -6e-5, 4e-5]):
+        for order in (1, 0):
+            dcb.plan_cache_clear()
+            dcb.image_stats(True, reset=True)
+            fast = post.correct_perspective_image(dev, coef, order=order).to_host()
+            st = dcb.image_stats(False, reset=True)
+            os.environ["DCB_IMG_FAST"] = "0"
+            try:
+                dcb.plan_cache_clear()
+                exact = post.correct_perspective_image(dev, coef, order=order).to_host()
+            finally:
+                del os.environ["DCB_IMG_FAST"]
+                dcb.plan_cache_clear()
+            assert np.array_equal(fast, exact), (coef, order)
+            assert np.array_equal(fast, orc.correct_perspective_image(mat, coef, order=order))
+            assert st["rows_patch"] > 0.5 * st["rows"], st
