@@ -2,6 +2,7 @@
 // argument validation, launch planning (tile grid, staged-box size, TMA
 // descriptor) and kernel dispatch.  Host side only; kernels are in remap.cuh.
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -394,6 +395,70 @@ void launch_plan(int map_kind, int th, const ImageParams &p, int grid, void *out
                                                  p.nstatic, grid,
                                                  reinterpret_cast<int *>(base + l.starts));
 }
+// Plan memory comes from slabs the library keeps (first fit, neighbours coalesced on release): a
+// cudaMalloc of 8.6 MB took 2-6 ms on the round's boxes -- ten times the plan kernels -- and a
+// caller trying calibrations pays it per model (tools/plan_probe.py).  Guarded by g_plans_mu.
+struct PlanSlab {
+    int device;
+    char *base;
+    size_t bytes;
+    std::map<size_t, size_t> free_;   // offset -> length
+};
+std::vector<PlanSlab> g_plan_slabs;
+constexpr size_t kPlanSlabBytes = (size_t)64 << 20;
+void *plan_alloc(int device, size_t bytes) {
+    bytes = (bytes + 255) / 256 * 256;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (auto &sl : g_plan_slabs) {
+            if (sl.device != device) continue;
+            for (auto it = sl.free_.begin(); it != sl.free_.end(); ++it) {
+                if (it->second < bytes) continue;
+                const size_t off = it->first, len = it->second;
+                sl.free_.erase(it);
+                if (len > bytes) sl.free_[off + bytes] = len - bytes;
+                return sl.base + off;
+            }
+        }
+        if (pass == 1) break;
+        PlanSlab sl;
+        sl.device = device;
+        sl.bytes = std::max(kPlanSlabBytes, bytes);
+        void *d = nullptr;
+        if (cudaMalloc(&d, sl.bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        sl.base = reinterpret_cast<char *>(d);
+        sl.free_[0] = sl.bytes;
+        g_plan_slabs.push_back(std::move(sl));
+    }
+    return nullptr;
+}
+// (the caller has made sure no kernel still reads the block: cudaDeviceSynchronize)
+void plan_release(void *ptr, size_t bytes) {
+    bytes = (bytes + 255) / 256 * 256;
+    char *q = reinterpret_cast<char *>(ptr);
+    for (auto &sl : g_plan_slabs) {
+        if (q < sl.base || q >= sl.base + sl.bytes) continue;
+        size_t off = (size_t)(q - sl.base), len = bytes;
+        auto next = sl.free_.lower_bound(off);
+        if (next != sl.free_.end() && off + len == next->first) {
+            len += next->second;
+            next = sl.free_.erase(next);
+        }
+        if (next != sl.free_.begin()) {
+            auto prev = std::prev(next);
+            if (prev->first + prev->second == off) {
+                off = prev->first;
+                len += prev->second;
+                sl.free_.erase(prev);
+            }
+        }
+        sl.free_[off] = len;
+        return;
+    }
+}
+
 size_t plan_cache_limit() {
     static size_t lim = [] {
         const char *e = getenv("DCB_PLAN_CACHE_MB");
@@ -482,27 +547,38 @@ static int get_image_plan(int map_kind, int th, ImageParams &p, int grid, cudaSt
             auto old = g_plans.begin();
             for (auto jt = g_plans.begin(); jt != g_plans.end(); ++jt)
                 if (jt->second.last_use < old->second.last_use) old = jt;
-            cudaFree(old->second.dptr);
+            cudaDeviceSynchronize();   // kernels on any stream may still read it
+            plan_release(old->second.dptr, old->second.bytes);
             cudaEventDestroy(old->second.ready);
             g_plan_bytes -= old->second.bytes;
             g_plans.erase(old);
         }
         PlanEntry e;
-        CUDA_TRY(cudaMalloc(&e.dptr, bytes));
+        const bool trace = getenv("DCB_TRACE_PLAN") != nullptr;
+        const auto tr0 = std::chrono::steady_clock::now();
+        e.dptr = plan_alloc(key.device, bytes);
+        if (e.dptr == nullptr) return fail(DCB_ERR_CUDA, "out of device memory for a plan of %zu bytes", bytes);
+        if (trace)
+            fprintf(stderr, "[dcb] plan memory (%zu bytes) %.0f us\n", bytes,
+                    std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr0).count());
         e.bytes = bytes;
         cudaError_t ce = cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming);
         if (ce != cudaSuccess) {
-            cudaFree(e.dptr);
+            plan_release(e.dptr, bytes);
             return fail(DCB_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(ce));
         }
         launch_plan(map_kind, th, p, grid, e.dptr, g_image_stats_fwd(), stream);
         ce = cudaGetLastError();
         if (ce == cudaSuccess) ce = cudaEventRecord(e.ready, stream);
         if (ce != cudaSuccess) {
-            cudaFree(e.dptr);
+            cudaDeviceSynchronize();
+            plan_release(e.dptr, bytes);
             cudaEventDestroy(e.ready);
             return fail(DCB_ERR_CUDA, "plan kernel launch failed: %s", cudaGetErrorString(ce));
         }
+        if (trace)
+            fprintf(stderr, "[dcb] plan build enqueued after %.0f us\n",
+                    std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr0).count());
         g_plan_builds.fetch_add(1, std::memory_order_relaxed);
         g_plan_bytes += bytes;
         it = g_plans.emplace(k, e).first;
@@ -1604,8 +1680,22 @@ int dcb_launch_count_reset(void) {
 }
 int dcb_plan_cache_clear(uint64_t *plans_built) {
     std::lock_guard<std::mutex> lk(g_plans_mu);
+    // (kernels on any stream of any device may still read the plans)
+    if (!g_plans.empty()) {
+        int cur = 0, ndev = 0;
+        cudaGetDevice(&cur);
+        cudaGetDeviceCount(&ndev);
+        std::vector<bool> seen((size_t)std::max(ndev, 1), false);
+        for (auto &sl : g_plan_slabs)
+            if (sl.device >= 0 && sl.device < ndev && !seen[(size_t)sl.device]) {
+                seen[(size_t)sl.device] = true;
+                cudaSetDevice(sl.device);
+                cudaDeviceSynchronize();
+            }
+        cudaSetDevice(cur);
+    }
     for (auto &kv : g_plans) {
-        cudaFree(kv.second.dptr);
+        plan_release(kv.second.dptr, kv.second.bytes);
         cudaEventDestroy(kv.second.ready);
     }
     g_plans.clear();

@@ -433,6 +433,7 @@ __global__ void __launch_bounds__(kThreads)
     const int lim_y = box.use ? min(p.bh - 1, p.ylast - box.by0) : 0;
     constexpr int RPW = TH / kWarps;
     unsigned n_full = 0, n_part = 0, n_rows = 0, n_genx = 0;
+    unsigned n_why[3] = {0, 0, 0};   // rows not verified: tile not eligible, row binade, pixels
     for (int rr = 0; rr < RPW; ++rr) {
         const int r = warp * RPW + rr, y = y_lo + r;
         RowPatch rp;
@@ -542,14 +543,18 @@ __global__ void __launch_bounds__(kThreads)
             rp.mhi_y = magic_hi(shy);
             rp.mky = (1u << shy) - 1u;
             rp.e32y = (uint32_t)(150 - shy) << 23;
+            n_why[1] += !row_ok;
+            n_why[2] += row_ok && mask == 0u;
             n_full += (mask & 0xfu) == 0xfu || (mask & 0xf0u) == 0xf0u;
             n_genx += (mask & 0xfu) != 0xfu && (mask & 0xf0u) == 0xf0u;
             n_part += !((mask & 0xfu) == 0xfu || (mask & 0xf0u) == 0xf0u) && mask != 0u;
         }
+        n_why[0] += box.shx == 0 && y < y_end;
         n_rows += y < y_end;
         if (lane == 0) out.rows[r] = rp;
     }
     if (stats != nullptr && lane == 0) {
+        for (int i = 0; i < 3; ++i) atomicAdd(stats + i, (unsigned long long)n_why[i]);
         atomicAdd(stats + 5, (unsigned long long)n_full);
         atomicAdd(stats + 6, (unsigned long long)n_part);
         atomicAdd(stats + 7, (unsigned long long)n_rows);

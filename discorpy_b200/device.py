@@ -413,7 +413,8 @@ def image_stats(enable=True, reset=False):
     out = (ctypes.c_uint64 * 8)()
     _cabi.call("dcb_image_stats", 1 if enable else 0, out, 1 if reset else 0)
     return {"rows_blend_redo": int(out[3]), "tiles_odd": int(out[4]), "rows_patch": int(out[5]),
-            "rows_partial": int(out[6]), "rows": int(out[7])}
+            "rows_partial": int(out[6]), "rows": int(out[7]), "rows_tile_not_eligible": int(out[0]),
+            "rows_binade": int(out[1]), "rows_no_segment_verified": int(out[2])}
 
 
 def plan_cache_clear():

@@ -332,8 +332,9 @@ int dcb_plan_cache_clear(uint64_t *plans_built);
  * with 0; out[0..7], when not NULL, receives since the last reset: [3] patch rows redone exactly
  * because of the blend certificate, [4] tiles holding values the certified blend does not cover,
  * and from the plans BUILT while counting was on: [5] tile rows verified for the patch path in
- * full, [6] rows verified in part (such rows take the exact path), [7] rows in total; 0..2
- * reserved.  reset != 0 clears the counters after reading. */
+ * full, [6] rows verified in part (such rows take the exact path), [7] rows in total; why rows
+ * were not verified: [0] their tile is not eligible (partial width, box not staged, centre outside
+ * the float32 binades), [1] the row's y binade, [2] no 32-pixel segment passed.  reset != 0 clears the counters after reading. */
 int dcb_image_stats(int enable, uint64_t *out, int reset);
 
 /* Timeline of the LAST single-image launch made while dcb_image_stats counting was on: for CTA b
