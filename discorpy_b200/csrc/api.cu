@@ -1242,6 +1242,41 @@ struct HostPipe {
     size_t stage_cap = 0;
     int device = -1;
     bool ok = false;
+    // Releases everything the pipe owns (a host thread that ends used to leave its
+    // buffers, three streams and 65 events behind).  Errors are ignored: at process exit the
+    // context may already be gone.
+    void release() {
+        if (!ok) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+            return;
+        }
+        if (up) cudaStreamSynchronize(up);
+        if (run) cudaStreamSynchronize(run);
+        if (down) cudaStreamSynchronize(down);
+        if (dsrc) cudaFree(dsrc);
+        if (ddst) cudaFree(ddst);
+        if (hstage) cudaFreeHost(hstage);
+        for (int i = 0; i < kMaxBands; ++i) {
+            if (ev_up[i]) cudaEventDestroy(ev_up[i]);
+            if (ev_run[i]) cudaEventDestroy(ev_run[i]);
+        }
+        if (ev_free) cudaEventDestroy(ev_free);
+        if (up) cudaStreamDestroy(up);
+        if (run) cudaStreamDestroy(run);
+        if (down) cudaStreamDestroy(down);
+        cudaGetLastError();
+        if (cur >= 0) cudaSetDevice(cur);
+        ok = false;
+    }
+    HostPipe() {
+        for (int i = 0; i < kMaxBands; ++i) ev_up[i] = ev_run[i] = nullptr;
+    }
+    HostPipe(const HostPipe &) = delete;
+    HostPipe &operator=(const HostPipe &) = delete;
+    ~HostPipe() { release(); }
 };
 thread_local HostPipe g_pipe;
 
@@ -1250,10 +1285,14 @@ int pipe_prepare(size_t src_bytes, size_t dst_bytes) {
     CUDA_TRY(cudaGetDevice(&dev));
     HostPipe &hp = g_pipe;
     if (hp.ok && hp.device != dev) {  // the thread moved to another GPU: start over
-        cudaFree(hp.dsrc);
-        cudaFree(hp.ddst);
-        if (hp.hstage) cudaFreeHost(hp.hstage);
-        hp = HostPipe();
+        hp.release();
+        hp.up = hp.run = hp.down = nullptr;
+        hp.ev_free = nullptr;
+        for (int i = 0; i < kMaxBands; ++i) hp.ev_up[i] = hp.ev_run[i] = nullptr;
+        hp.dsrc = hp.ddst = hp.hstage = nullptr;
+        hp.src_cap = hp.dst_cap = hp.stage_cap = 0;
+        hp.device = -1;
+        CUDA_TRY(cudaSetDevice(dev));
     }
     if (!hp.ok) {
         CUDA_TRY(cudaStreamCreateWithFlags(&hp.up, cudaStreamNonBlocking));

@@ -66,19 +66,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     __trap();
 }
 
-// The same for a warp with nothing else to do (the copy-only producer of the single-image kernel):
-// sleeps between polls, so its polling does not take issue slots from the sampling warps (6 % of
-// all issued instructions before, profiles/r2/ncu_img_raw2.txt).
-__device__ __forceinline__ void mbar_wait_idle(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-#pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
-        if (mbar_try(addr, parity)) return;
-        __nanosleep(400);
-    }
-    __trap();
-}
-
 // 3-D tiled TMA load global -> shared, completion signalled on an mbarrier.
 // Coordinates are in elements, innermost first; out-of-bounds elements are
 // zero-filled (they are never sampled: every tap index is clamped).

@@ -630,8 +630,8 @@ constexpr int kImgThreads = kThreads + 32;
 
 // Shared-memory layout (host side must agree, see plan_and_launch_image in api.cu):
 //   [raw 0] .. [raw 3][tail]
-//   tail : uint64_t raw_full[4] (copy landed), data_empty[4] (stage released by the eight sampling
-//          warps); 16 bytes unused; uint32_t unit_g[4] (row groups of the unit in each stage);
+//   tail : uint64_t raw_full[4] (copy landed); 48 bytes unused (stages come back through named
+//          barriers 1..4); uint32_t unit_g[4] (row groups of the unit in each stage);
 //          TilePlan<TH> rec[4]
 __host__ __device__ constexpr size_t image_rec_bytes(int th) {
     return sizeof(TileBox) + (size_t)th * sizeof(RowPatch);
@@ -672,7 +672,8 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint
 // Warp-specialised: warps 0..7 only evaluate coordinates and sample from the raw float32 stages;
 // warp 8 (the producer) walks this CTA's tiles: per tile one TMA load of the staged box and one
 // bulk copy of the tile's plan record, both completing on the stage's mbarrier (raw_full); the
-// sampling warps hand a stage back with one arrival each on data_empty.  There is no CTA-wide
+// sampling warps hand a stage back with a `bar.arrive` on the stage's named barrier, on which the
+// producer sleeps (`bar.sync`) instead of polling.  There is no CTA-wide
 // barrier in the tile loop.  (Round 1 widened every landed box into float64 tiles with two
 // producer warps; the per-warp event log showed that widening -- 1.7 us per tile -- was as slow as
 // the sampling it fed, profiles/r2/timeline_r2t3_event_log.txt.  The exact blend now widens its
@@ -690,7 +691,6 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *tail = smem + kRawStages * (size_t)p.stage_bytes;
     uint64_t *raw_full = reinterpret_cast<uint64_t *>(tail);         // [4] TMA bytes landed
-    uint64_t *data_empty = raw_full + 4;                             // [4] tile buffer released
     TilePlan<TH> *rec = reinterpret_cast<TilePlan<TH> *>(tail + 96); // [NBUF]
     const TilePlan<TH> *plan = reinterpret_cast<const TilePlan<TH> *>(p.plan);
 
@@ -724,7 +724,6 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
 #endif
         for (int b = 0; b < 4; ++b) {
             mbar_init(&raw_full[b], 1);
-            mbar_init(&data_empty[b], kWarps);
         }
         fence_mbar_init();
         if (staged) tma_prefetch_desc(&tmap);
@@ -799,12 +798,21 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         // warp (with two stages the samplers waited 11 % of their time for copies issued only one
         // tile earlier, profiles/r2/ncu_image_r2h_lerp32_two_stages.txt), p.pool_depth while it
         // claims
+        // Stages come back through NAMED BARRIERS 1..NBUF, not an mbarrier: the eight sampling
+        // warps `bar.arrive` on barrier 1 + stage when they are done with a unit, the producer
+        // `bar.sync`s on it and is descheduled until then.  (Polling data_empty with
+        // mbarrier.try_wait -- neither its suspend hint nor a nanosleep kept the warp asleep --
+        // was 4.7 of the kernel's 62 instructions per pixel, issued on the sub-partition it shares
+        // with two sampling warps: profiles/r2/ncu_image_r2ac_exact.txt, SASS lines 320-383.)
+        // Completions are consumed strictly in order, one per unit.
+        int released = 0;   // units 0 .. released-1 are known to have been handed back
         for (int k = k0;; ++k) {
             const int b = k & (NBUF - 1);
             const int depth = k < n_static ? NBUF : p.pool_depth;
-            if (k >= depth) {
-                const int kd = k - depth;   // this unit must have been released by all samplers
-                mbar_wait_idle(&data_empty[kd & (NBUF - 1)], (uint32_t)(kd >> LOGB) & 1u);
+            // unit k - depth must have been released by all samplers
+            while (released <= k - depth) {
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + (released & (NBUF - 1))), "n"(kImgThreads) : "memory");
+                ++released;
             }
             DCB_LOG(k);
             int more = 1;
@@ -1182,7 +1190,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
         }
         // this warp is done with buffer i&1 (and with its plan record)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&data_empty[i & (NBUF - 1)]);
+        asm volatile("bar.arrive %0, %1;" ::"r"(1 + (i & (NBUF - 1))), "n"(kImgThreads) : "memory");
         DCB_LOG(2 * i + 1);
 #ifdef DCB_IMG_TIMELINE
         if (p.stats != nullptr && threadIdx.x == 0) dbg_t = global_ns();
