@@ -661,3 +661,16 @@ def test_projective_patch_path_equals_exact_path():
             assert np.array_equal(fast, orc.correct_perspective_image(mat, coef, order=order))
             if abs(coef[6]) < 1e-5:     # (the strong keystone magnifies beyond the 144-wide staged box:
                 assert st["rows_patch"] > 0.5 * st["rows"], st      # most of its tiles stay exact)
+
+
+def test_plan_cache_eviction_and_slab_reuse():
+    """More calibrations than DCB_PLAN_CACHE_MB holds: plans are evicted, their slab memory reused
+    (api.cu: plan_alloc / plan_release), results stay the oracle's.  A subprocess, because the
+    cache limit is read once per process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, DCB_PLAN_CACHE_MB="16")
+    script = os.path.join(os.path.dirname(__file__), "plan_cache_eviction_check.py")
+    res = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
