@@ -1253,9 +1253,8 @@ struct HostPipe {
             ok = false;
             return;
         }
-        if (up) cudaStreamSynchronize(up);
-        if (run) cudaStreamSynchronize(run);
-        if (down) cudaStreamSynchronize(down);
+        for (cudaStream_t q : {up, run, down})
+            if (q) cudaStreamSynchronize(q);
         if (dsrc) cudaFree(dsrc);
         if (ddst) cudaFree(ddst);
         if (hstage) cudaFreeHost(hstage);
@@ -1264,9 +1263,8 @@ struct HostPipe {
             if (ev_run[i]) cudaEventDestroy(ev_run[i]);
         }
         if (ev_free) cudaEventDestroy(ev_free);
-        if (up) cudaStreamDestroy(up);
-        if (run) cudaStreamDestroy(run);
-        if (down) cudaStreamDestroy(down);
+        for (cudaStream_t q : {up, run, down})
+            if (q) cudaStreamDestroy(q);
         cudaGetLastError();
         if (cur >= 0) cudaSetDevice(cur);
         ok = false;
@@ -1379,11 +1377,61 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
     int rc = pipe_prepare(pitch * (size_t)H, pitch * (size_t)H);
     if (rc) return rc;
     HostPipe &hp = g_pipe;
-    if (nbands <= 0)  // one band per 8 MiB, at most 8 (a 4096^2 image: 8 bands of 512 rows)
-        nbands = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)W * 4 * (size_t)H) >> 23));
-    nbands = std::min(std::min(nbands, kMaxBands), H);
-    const int rows_per = (H + nbands - 1) / nbands;
-    nbands = (H + rows_per - 1) / rows_per;
+    // Row bands [edge[b], edge[b + 1]).  The call ends one upload band (the rows below an output
+    // band that it samples), one kernel and one download band after the last upload, and the first
+    // download starts two upload bands into the call: images of 32 MiB and more get bands of 2, 2
+    // and 4 MiB at both ends and ~6 MiB bands between them (a 4096^2 image: 128, 128, 256, 8 x 384,
+    // 256, 128, 128 rows -- 1.78 ms against 1.82 ms for eight equal bands; smaller bands throughout
+    // cost more in per-copy overhead than they save: tools/e2e_edges.py, profiles/r2/e2e_edges_*.txt);
+    // smaller images one band per 3.5 MiB, at most 8 (2160 x 2560: 0.73 ms in 6 bands against 0.87 ms
+    // in 2, profiles/r2/e2e_small_r2z9.txt).  nbands > 0 asks for that many equal bands;
+    // DCB_BAND_EDGES="n0,n1,..." (diagnostics) gives the band heights in 64ths of the image.
+    int edge[kMaxBands + 1];
+    {
+        const bool auto_bands = nbands <= 0;
+        const size_t img_bytes = (size_t)W * 4 * (size_t)H;
+        const int unit = (int)std::max<size_t>(1, ((size_t)2 << 20) / ((size_t)W * 4));   // rows per 2 MiB
+        if (auto_bands && img_bytes >= ((size_t)32 << 20) && H >= 16 * unit) {
+            const int mid = H - 8 * unit;
+            const int nmid = (int)std::max<size_t>(1, std::min<size_t>(kMaxBands - 6,
+                                                   ((size_t)mid * W * 4 + ((size_t)3 << 20)) / ((size_t)6 << 20)));
+            int n = 0;
+            edge[0] = 0;
+            for (int h : {unit, unit, 2 * unit}) edge[n + 1] = edge[n] + h, ++n;
+            for (int k = 1; k <= nmid; ++k) edge[++n] = 4 * unit + (int)((long long)mid * k / nmid);
+            for (int h : {2 * unit, unit, unit}) edge[n + 1] = edge[n] + h, ++n;
+            nbands = n;
+        } else {
+            if (auto_bands) nbands = (int)std::max<size_t>(1, std::min<size_t>(8, img_bytes / ((size_t)7 << 19)));
+            nbands = std::min(std::min(nbands, kMaxBands), H);
+            const int rows_per = (H + nbands - 1) / nbands;
+            nbands = (H + rows_per - 1) / rows_per;
+            for (int b = 0; b <= nbands; ++b) edge[b] = std::min(H, b * rows_per);
+        }
+        const char *env = auto_bands ? getenv("DCB_BAND_EDGES") : nullptr;
+        if (env != nullptr && env[0] != 0 && H >= 64) {
+            int n = 0, acc = 0;
+            edge[0] = 0;
+            for (const char *q = env; *q != 0 && n < kMaxBands;) {
+                char *e = nullptr;
+                const long v = strtol(q, &e, 10);
+                if (e == q || v <= 0) break;
+                acc += (int)v;
+                const int row = (int)std::min<long long>(H, (long long)H * acc / 64);
+                if (row > edge[n]) edge[++n] = row;
+                q = (*e == ',') ? e + 1 : e;
+            }
+            if (n == 0 || edge[n] < H) {
+                if (n < kMaxBands) edge[++n] = H; else edge[n] = H;
+            }
+            nbands = n;
+        }
+    }
+    auto band_of = [&](int row) -> int {   // the band holding source row `row`
+        int b = 0;
+        while (b < nbands - 1 && edge[b + 1] <= row) ++b;
+        return b;
+    };
     char *dsrc = (char *)hp.dsrc, *ddst = (char *)hp.ddst;
     // pageable source: bands go through a pinned staging buffer filled by the copy pool
     const bool stage = is_pageable(src_host);
@@ -1402,18 +1450,40 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
     for (int b = 0; b < nbands; ++b) need[b] = -1;
     auto need_of = [&](int k) -> int {
         if (need[k] < 0) {
-            const int q0 = k * rows_per, qn = std::min(rows_per, H - q0);
             int lo, hi;
-            radial_row_range(*model, H, W, q0, q0 + qn, &lo, &hi);
-            need[k] = std::min(nbands - 1, hi / rows_per);
+            radial_row_range(*model, H, W, edge[k], edge[k + 1], &lo, &hi);
+            need[k] = band_of(hi);
         }
         return need[k];
     };
+    // DCB_PIPE_TRACE=1 (diagnostics): device-side completion time of every band's upload, kernel
+    // and download, relative to the first upload's start, on stderr
+    const bool trace = getenv("DCB_PIPE_TRACE") != nullptr && getenv("DCB_PIPE_TRACE")[0] == '1';
+    cudaEvent_t tr0 = nullptr, tr[4][kMaxBands];
+    if (trace) {
+        CUDA_TRY(cudaEventCreate(&tr0));
+        for (int k = 0; k < 4; ++k)
+            for (int b = 0; b < nbands; ++b) CUDA_TRY(cudaEventCreate(&tr[k][b]));
+        CUDA_TRY(cudaEventRecord(tr0, hp.up));
+    }
     // uploads in row order; an output band is unwarped (second stream) as soon as the upload it
     // needs has been enqueued, and downloaded (third stream) behind its kernel
     int next = 0, waited = -1;
+    // DCB_PIPE_NOKERNEL (diagnostics): copies only -- what the two PCIe directions allow
+    const bool no_kernel = getenv("DCB_PIPE_NOKERNEL") != nullptr;
+    // DCB_PIPE_DIRECT=1: the band kernels store straight into the caller's page-locked destination
+    // (posted PCIe writes, one full 128-byte line per warp instruction) -- no device copy of the
+    // result, no download stream, no kernel -> copy hand-over per band
+    char *dst_dev = nullptr;
+    if (getenv("DCB_PIPE_DIRECT") != nullptr && getenv("DCB_PIPE_DIRECT")[0] == '1' && !is_pageable(dst_host)) {
+        void *q = nullptr;
+        if (cudaHostGetDevicePointer(&q, dst_host, 0) == cudaSuccess && q != nullptr)
+            dst_dev = (char *)q;
+        else
+            cudaGetLastError();
+    }
     for (int b = 0; b < nbands; ++b) {
-        const int r0 = b * rows_per, nr = std::min(rows_per, H - r0);
+        const int r0 = edge[b], nr = edge[b + 1] - r0;
         const char *from = (const char *)src_host + (size_t)r0 * src_pitch_host;
         size_t from_pitch = src_pitch_host;
         if (stage) {
@@ -1422,34 +1492,71 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
             from = to;
             from_pitch = wbytes;
         }
-        CUDA_TRY(cudaMemcpy2DAsync(dsrc + (size_t)r0 * pitch, pitch, from, from_pitch, wbytes, nr,
-                                   cudaMemcpyHostToDevice, hp.up));
+        // (rows that are contiguous on both sides go as ONE linear copy: a 2-D copy is a descriptor
+        // per row for the copy engine)
+        if (from_pitch == wbytes && pitch == wbytes)
+            CUDA_TRY(cudaMemcpyAsync(dsrc + (size_t)r0 * pitch, from, wbytes * (size_t)nr,
+                                     cudaMemcpyHostToDevice, hp.up));
+        else
+            CUDA_TRY(cudaMemcpy2DAsync(dsrc + (size_t)r0 * pitch, pitch, from, from_pitch, wbytes, nr,
+                                       cudaMemcpyHostToDevice, hp.up));
         CUDA_TRY(cudaEventRecord(hp.ev_up[b], hp.up));
+        if (trace) CUDA_TRY(cudaEventRecord(tr[0][b], hp.up));
         // (pinned source: every upload is enqueued before the first launch, as measured best)
         if (!stage && b < nbands - 1) continue;
         for (; next < nbands && (b == nbands - 1 || need_of(next) <= b); ++next) {
-            const int q0 = next * rows_per, qn = std::min(rows_per, H - q0);
+            const int q0 = edge[next], qn = edge[next + 1] - q0;
             if (need_of(next) > waited) {
                 CUDA_TRY(cudaStreamWaitEvent(hp.run, hp.ev_up[need_of(next)], 0));
                 waited = need_of(next);
             }
-            rc = dcb_unwarp_stack_backward_f32((const float *)dsrc, (float *)(ddst + (size_t)q0 * pitch),
-                                               1, H, W, 0, H, pitch, pitch * (size_t)H, pitch,
-                                               pitch * (size_t)qn, q0, qn, 1, model, opt, hp.run);
+            if (trace) CUDA_TRY(cudaEventRecord(tr[3][next], hp.run));
+            if (dst_dev != nullptr)
+                rc = dcb_unwarp_stack_backward_f32((const float *)dsrc,
+                                                   (float *)(dst_dev + (size_t)q0 * dst_pitch_host), 1, H, W, 0,
+                                                   H, pitch, pitch * (size_t)H, dst_pitch_host,
+                                                   dst_pitch_host * (size_t)qn, q0, qn, 1, model, opt, hp.run);
+            else if (!no_kernel)
+                rc = dcb_unwarp_stack_backward_f32((const float *)dsrc, (float *)(ddst + (size_t)q0 * pitch),
+                                                   1, H, W, 0, H, pitch, pitch * (size_t)H, pitch,
+                                                   pitch * (size_t)qn, q0, qn, 1, model, opt, hp.run);
             if (rc) {
                 cudaDeviceSynchronize();
                 return rc;
             }
+            if (trace) CUDA_TRY(cudaEventRecord(tr[1][next], hp.run));
+            if (dst_dev != nullptr) {
+                if (trace) CUDA_TRY(cudaEventRecord(tr[2][next], hp.run));
+                continue;
+            }
             CUDA_TRY(cudaEventRecord(hp.ev_run[next], hp.run));
             CUDA_TRY(cudaStreamWaitEvent(hp.down, hp.ev_run[next], 0));
-            CUDA_TRY(cudaMemcpy2DAsync((char *)dst_host + (size_t)q0 * dst_pitch_host, dst_pitch_host,
-                                       ddst + (size_t)q0 * pitch, pitch, wbytes, qn,
-                                       cudaMemcpyDeviceToHost, hp.down));
+            if (dst_pitch_host == wbytes && pitch == wbytes)
+                CUDA_TRY(cudaMemcpyAsync((char *)dst_host + (size_t)q0 * dst_pitch_host,
+                                         ddst + (size_t)q0 * pitch, wbytes * (size_t)qn,
+                                         cudaMemcpyDeviceToHost, hp.down));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync((char *)dst_host + (size_t)q0 * dst_pitch_host, dst_pitch_host,
+                                           ddst + (size_t)q0 * pitch, pitch, wbytes, qn,
+                                           cudaMemcpyDeviceToHost, hp.down));
+            if (trace) CUDA_TRY(cudaEventRecord(tr[2][next], hp.down));
         }
     }
     CUDA_TRY(cudaStreamSynchronize(hp.down));
     CUDA_TRY(cudaStreamSynchronize(hp.run));
     CUDA_TRY(cudaStreamSynchronize(hp.up));
+    if (trace) {
+        fprintf(stderr, "[dcb] pipe trace (%d bands; rows, needs, us: upload done / kernel start / kernel done / download done)\n", nbands);
+        for (int b = 0; b < nbands; ++b) {
+            float t[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tr0, tr[k][b]);
+            fprintf(stderr, "[dcb]   band %2d rows %5d need %2d  %8.1f %8.1f %8.1f %8.1f\n", b, edge[b + 1] - edge[b],
+                    need_of(b), t[0] * 1e3, t[3] * 1e3, t[1] * 1e3, t[2] * 1e3);
+        }
+        cudaEventDestroy(tr0);
+        for (int k = 0; k < 4; ++k)
+            for (int b = 0; b < nbands; ++b) cudaEventDestroy(tr[k][b]);
+    }
     return DCB_OK;
 }
 

@@ -78,6 +78,14 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// The same box into L2 only (no shared-memory destination, no completion to wait for).
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap *map, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

@@ -777,6 +777,13 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                         bxs[k] = issue_plan(t0 + k, k);
                     }
                 }
+                // ... and the first box is asked into L2 already.  A prefetch delivers nothing to
+                // this kernel -- the box is read after the grid dependency, through the same
+                // coherent L2 -- so it is harmless even if the preceding grid is still writing the
+                // source; when it is not, the DRAM latency of the box every sampling warp of this
+                // CTA waits for passes under that grid's tail.  (44.8 -> 43.4 us; all NBUF boxes:
+                // 44.2, they compete with the preceding grid's stores -- profiles/r2/ab2_l2pf*.txt)
+                if (k0 > 0 && bxs[0].y >= 0) tma_prefetch_l2_3d(&tmap, bxs[0].x, bxs[0].y - p.yorg, 0);
             }
         }
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1152,7 +1159,7 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                             v[k] = fmaf(bot - top, ty, top);
                         }
                     }
-                    if (ORDER == 1 && BLEND == DCB_BLEND_LERP32 && p.rint) {                    } else if (ORDER == 1 && BLEND == DCB_BLEND_LERP32 && p.rint) {
+                    if (ORDER == 1 && BLEND == DCB_BLEND_LERP32 && p.rint) {
 #pragma unroll
                         for (int k = 0; k < kCols; ++k) v[k] = finish_f32(v[k], 1);
                     }

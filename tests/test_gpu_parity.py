@@ -145,6 +145,28 @@ def test_fast_blends_within_tolerance(blend, rel):
         assert float(np.median(diff)) < 1e-7
 
 
+def test_integer_image_fast_blends_round_to_integers():
+    """Integer images with the float32 / float64 lerp blends: the result is rounded half away
+    from zero like SciPy's (never a truncated float), and differs from the oracle's exact
+    blend by at most one count where the blend lands within 1e-3 of a tie."""
+    rng = np.random.default_rng(19)
+    frame = rng.integers(0, 65536, (900, 1100), dtype=np.uint16)
+    want = orc.unwarp_image_backward(frame, 551.3, 447.9, FACT5, 1)
+    exactf = orc.unwarp_image_backward(frame.astype(np.float32), 551.3, 447.9, FACT5, 1).astype(np.float64)
+    for blend in (dcb.BLEND_LERP32, dcb.BLEND_LERP64):
+        post.config["blend"] = blend
+        got = post.unwarp_image_backward(frame, 551.3, 447.9, FACT5)
+        assert got.dtype == np.uint16
+        d = got.astype(np.int64) - want.astype(np.int64)
+        assert int(np.max(np.abs(d))) <= 1
+        # a differing pixel is one whose unrounded blend sits next to a tie
+        frac = np.abs(exactf - np.floor(exactf) - 0.5)
+        tol = 0.05 if blend == dcb.BLEND_LERP32 else 1e-6     # float32 blend of 16-bit counts
+        assert np.all(frac[d != 0] <= tol)
+        # and the rounding really happened: rounded (not truncated) float32 blends agree
+        assert abs(float(np.mean(got.astype(np.float64) - exactf))) < 5e-3
+
+
 def test_baseline_config2_full_size():
     """BASELINE config 2 at full size (4096 x 4096, 5 terms),
     full compare with the C oracle plus size-independent properties."""
