@@ -569,7 +569,26 @@ def bench_cfg3(dcb, _cabi, ctypes, stream, peak):
     want = oracle_c.correct_perspective_image(
         oracle_c.unwarp_image_backward(src0, 1030.2, 1019.6, FACT3, 1), PERS3, 1)
     bad = int(np.count_nonzero(dsts[0].to_host() != want))
+    # end to end: the public call on pinned host arrays (banded two-stage host pipeline)
+    import discorpy_b200.post.postprocessing as post
+    pins = []
+    for i in range(4):
+        a = dcb.pinned_empty((S, S), np.float32)
+        a[:] = src0 if i == 0 else srcs[i].to_host()
+        pins.append(a)
+    got = post.unwarp_image_backward_perspective(pins[0], 1030.2, 1019.6, FACT3, PERS3)
+    bad_e2e = int(np.count_nonzero(got != want))
+    for i in range(3):
+        post.unwarp_image_backward_perspective(pins[i], 1030.2, 1019.6, FACT3, PERS3)
+    t0 = time.perf_counter()
+    for i in range(16):
+        post.unwarp_image_backward_perspective(pins[i % 4], 1030.2, 1019.6, FACT3, PERS3)
+    e2e_ms = (time.perf_counter() - t0) / 16 * 1e3
     return {"workload": "configs[2]: perspective+radial combined unwarp, 2048x2048 fp32",
+            "e2e_ms_per_image": e2e_ms, "e2e_Mpixels_per_s": S * S / (e2e_ms * 1e3),
+            "e2e_api": "post.unwarp_image_backward_perspective(pinned ndarray): upload, both passes and "
+                       "download in row bands (dcb_unwarp_image_backward_perspective_host_f32)",
+            "e2e_parity_ok": bad_e2e == 0,
             "kernel_us_per_image": us, "Mpixels_per_s": S * S / us,
             "roofline_frac_vs_8B_per_px": ALGO_BYTES_PER_PX * S * S / (us * 1e-6) / 1e9 / peak,
             "launches_per_image": 2, "hbm_bytes_per_px_moved": 16,

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>
@@ -1273,8 +1274,8 @@ constexpr int kMaxBands = 32;
 struct HostPipe {
     cudaStream_t up = nullptr, run = nullptr, down = nullptr;
     cudaEvent_t ev_up[kMaxBands], ev_run[kMaxBands], ev_free = nullptr;
-    void *dsrc = nullptr, *ddst = nullptr;
-    size_t src_cap = 0, dst_cap = 0;
+    void *dsrc = nullptr, *ddst = nullptr, *dmid = nullptr;   // dmid: image between two stages
+    size_t src_cap = 0, dst_cap = 0, mid_cap = 0;
     void *hstage = nullptr;   // pinned staging copy of a pageable source image
     size_t stage_cap = 0;
     int device = -1;
@@ -1294,6 +1295,7 @@ struct HostPipe {
             if (q) cudaStreamSynchronize(q);
         if (dsrc) cudaFree(dsrc);
         if (ddst) cudaFree(ddst);
+        if (dmid) cudaFree(dmid);
         if (hstage) cudaFreeHost(hstage);
         for (int i = 0; i < kMaxBands; ++i) {
             if (ev_up[i]) cudaEventDestroy(ev_up[i]);
@@ -1315,7 +1317,7 @@ struct HostPipe {
 };
 thread_local HostPipe g_pipe;
 
-int pipe_prepare(size_t src_bytes, size_t dst_bytes) {
+int pipe_prepare(size_t src_bytes, size_t dst_bytes, size_t mid_bytes) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     HostPipe &hp = g_pipe;
@@ -1324,8 +1326,8 @@ int pipe_prepare(size_t src_bytes, size_t dst_bytes) {
         hp.up = hp.run = hp.down = nullptr;
         hp.ev_free = nullptr;
         for (int i = 0; i < kMaxBands; ++i) hp.ev_up[i] = hp.ev_run[i] = nullptr;
-        hp.dsrc = hp.ddst = hp.hstage = nullptr;
-        hp.src_cap = hp.dst_cap = hp.stage_cap = 0;
+        hp.dsrc = hp.ddst = hp.dmid = hp.hstage = nullptr;
+        hp.src_cap = hp.dst_cap = hp.mid_cap = hp.stage_cap = 0;
         hp.device = -1;
         CUDA_TRY(cudaSetDevice(dev));
     }
@@ -1353,6 +1355,13 @@ int pipe_prepare(size_t src_bytes, size_t dst_bytes) {
         hp.dst_cap = 0;
         CUDA_TRY(cudaMalloc(&hp.ddst, dst_bytes));
         hp.dst_cap = dst_bytes;
+    }
+    if (hp.mid_cap < mid_bytes) {
+        if (hp.dmid) CUDA_TRY(cudaFree(hp.dmid));
+        hp.dmid = nullptr;
+        hp.mid_cap = 0;
+        CUDA_TRY(cudaMalloc(&hp.dmid, mid_bytes));
+        hp.mid_cap = mid_bytes;
     }
     return DCB_OK;
 }
@@ -1401,17 +1410,61 @@ void radial_row_range(const dcb_radial &m, int H, int W, int r0, int r1, int *lo
     *hi = (int)std::max(0.0, std::min((double)(H - 1), std::ceil(vmax) + 2.0));
 }
 
+// The same for the projective map: along any line the source row (c3 x + c4 y + c5) / (c6 x + c7 y + 1)
+// is a Moebius function of the line parameter, monotone while the denominator keeps its sign, so
+// over a band (a rectangle) it takes its extremes at the four corners.  A denominator that
+// changes sign or vanishes over the band: the whole image.
+void persp_row_range(const dcb_persp &m, int H, int W, int r0, int r1, int *lo, int *hi) {
+    const double *c = m.c;
+    const double xs[2] = {0.0, (double)(W - 1)}, ys[2] = {(double)r0, (double)(r1 - 1)};
+    double vmin = 1e300, vmax = -1e300;
+    int sign = 0;
+    bool ok = true;
+    for (double y : ys)
+        for (double x : xs) {
+            const double den = c[6] * x + c[7] * y + 1.0;
+            const int sg = den > 0.0 ? 1 : (den < 0.0 ? -1 : 0);
+            if (sg == 0 || (sign != 0 && sg != sign)) ok = false;
+            sign = sg;
+            const double v = (c[3] * x + c[4] * y + c[5]) / den;
+            if (!(std::fabs(v) < 1e15)) ok = false;
+            vmin = std::min(vmin, v);
+            vmax = std::max(vmax, v);
+        }
+    if (!ok) {
+        *lo = 0;
+        *hi = H - 1;
+        return;
+    }
+    *lo = (int)std::max(0.0, std::min((double)(H - 1), std::floor(vmin) - 1.0));
+    *hi = (int)std::max(0.0, std::min((double)(H - 1), std::ceil(vmax) + 2.0));
+}
+
 }  // namespace
 
-int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, int H, int W,
-                                       size_t src_pitch_host, size_t dst_pitch_host,
-                                       const dcb_radial *model, const dcb_options *opt, int nbands) {
+// One stage of the host-buffer pipeline: a remap of the whole image, launched band by band.
+struct PipeStage {
+    // conservative range [lo, hi] of the INPUT rows that output rows [r0, r1) of this stage sample
+    std::function<void(int r0, int r1, int *lo, int *hi)> rows;
+    // output rows [q0, q0 + qn) of this stage: `in` is the stage's whole input image (device,
+    // `in_pitch` bytes per row), `out_band` the first of the qn output rows
+    std::function<int(const float *in, size_t in_pitch, float *out_band, size_t out_pitch, int q0, int qn,
+                      cudaStream_t stream)> launch;
+};
+
+// Host image -> nstages remaps (1: radial or projective, 2: radial then projective) -> host image,
+// as one pipeline over row bands on three streams: the image is uploaded band by band; a band of
+// stage-1 output rows is launched as soon as the last source row it can sample has been enqueued,
+// a band of stage-2 rows as soon as the last stage-1 row it can sample has been launched (both on
+// the one compute stream, so stream order is the dependency), and every finished band of the last
+// stage is downloaded behind its kernel.  Synchronous.
+static int host_pipeline(const float *src_host, float *dst_host, int H, int W, size_t src_pitch_host,
+                         size_t dst_pitch_host, int nbands, int nstages, const PipeStage *stages) {
     REQUIRE(src_host != nullptr && dst_host != nullptr, "null image pointer");
-    REQUIRE(model != nullptr, "radial model is NULL");
     REQUIRE(H >= 1 && W >= 1, "image must be at least 1x1 (got %dx%d)", H, W);
     REQUIRE(src_pitch_host >= (size_t)W * 4 && dst_pitch_host >= (size_t)W * 4, "bad host pitch");
     const size_t pitch = ((size_t)W * 4 + 15) / 16 * 16;  // device rows: 16-byte pitch for TMA
-    int rc = pipe_prepare(pitch * (size_t)H, pitch * (size_t)H);
+    int rc = pipe_prepare(pitch * (size_t)H, pitch * (size_t)H, nstages > 1 ? pitch * (size_t)H : 0);
     if (rc) return rc;
     HostPipe &hp = g_pipe;
     // Row bands [edge[b], edge[b + 1]).  The call ends one upload band (the rows below an output
@@ -1464,12 +1517,12 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
             nbands = n;
         }
     }
-    auto band_of = [&](int row) -> int {   // the band holding source row `row`
+    auto band_of = [&](int row) -> int {   // the band holding row `row`
         int b = 0;
         while (b < nbands - 1 && edge[b + 1] <= row) ++b;
         return b;
     };
-    char *dsrc = (char *)hp.dsrc, *ddst = (char *)hp.ddst;
+    char *dsrc = (char *)hp.dsrc, *ddst = (char *)hp.ddst, *dmid = (char *)hp.dmid;
     // pageable source: bands go through a pinned staging buffer filled by the copy pool
     const bool stage = is_pageable(src_host);
     const size_t wbytes = (size_t)W * 4;
@@ -1480,21 +1533,22 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
         CUDA_TRY(cudaHostAlloc(&hp.hstage, wbytes * (size_t)H, cudaHostAllocDefault));
         hp.stage_cap = wbytes * (size_t)H;
     }
-    // last upload band an output band needs (the last source row it can touch); evaluated on
+    // last input band an output band of stage s needs (the last row it can touch); evaluated on
     // first use, i.e. after the first uploads are already under way (8 x 2049 polynomial samples
     // cost the host ~50 us)
-    int need[kMaxBands];
-    for (int b = 0; b < nbands; ++b) need[b] = -1;
-    auto need_of = [&](int k) -> int {
-        if (need[k] < 0) {
-            int lo, hi;
-            radial_row_range(*model, H, W, edge[k], edge[k + 1], &lo, &hi);
-            need[k] = band_of(hi);
+    int need[2][kMaxBands];
+    for (int st = 0; st < 2; ++st)
+        for (int b = 0; b < nbands; ++b) need[st][b] = -1;
+    auto need_of = [&](int st, int k) -> int {
+        if (need[st][k] < 0) {
+            int lo = 0, hi = H - 1;
+            stages[st].rows(edge[k], edge[k + 1], &lo, &hi);
+            need[st][k] = band_of(std::max(0, std::min(H - 1, hi)));
         }
-        return need[k];
+        return need[st][k];
     };
-    // DCB_PIPE_TRACE=1 (diagnostics): device-side completion time of every band's upload, kernel
-    // and download, relative to the first upload's start, on stderr
+    // DCB_PIPE_TRACE=1 (diagnostics): device-side time of every band's upload, first-stage kernel
+    // start, last-stage kernel end and download, relative to the first upload's start, on stderr
     const bool trace = getenv("DCB_PIPE_TRACE") != nullptr && getenv("DCB_PIPE_TRACE")[0] == '1';
     cudaEvent_t tr0 = nullptr, tr[4][kMaxBands];
     if (trace) {
@@ -1503,14 +1557,13 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
             for (int b = 0; b < nbands; ++b) CUDA_TRY(cudaEventCreate(&tr[k][b]));
         CUDA_TRY(cudaEventRecord(tr0, hp.up));
     }
-    // uploads in row order; an output band is unwarped (second stream) as soon as the upload it
-    // needs has been enqueued, and downloaded (third stream) behind its kernel
-    int next = 0, waited = -1;
     // DCB_PIPE_NOKERNEL (diagnostics): copies only -- what the two PCIe directions allow
     const bool no_kernel = getenv("DCB_PIPE_NOKERNEL") != nullptr;
-    // DCB_PIPE_DIRECT=1: the band kernels store straight into the caller's page-locked destination
-    // (posted PCIe writes, one full 128-byte line per warp instruction) -- no device copy of the
-    // result, no download stream, no kernel -> copy hand-over per band
+    // DCB_PIPE_DIRECT=1: the last stage's kernels store straight into the caller's page-locked
+    // destination (posted PCIe writes, one full 128-byte line per warp instruction) -- no device
+    // copy of the result, no download stream, no kernel -> copy hand-over per band.  Measured on
+    // the round's boxes: 41-46 GB/s against the copy engine's 55, the call 1.76 ms against 1.78
+    // (profiles/r2/e2e_edges_r2z8.txt) -- opt-in.
     char *dst_dev = nullptr;
     if (getenv("DCB_PIPE_DIRECT") != nullptr && getenv("DCB_PIPE_DIRECT")[0] == '1' && !is_pageable(dst_host)) {
         void *q = nullptr;
@@ -1519,6 +1572,43 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
         else
             cudaGetLastError();
     }
+    const int last = nstages - 1;
+    int next[2] = {0, 0}, waited = -1;
+    // the final stage's output band `k`: kernel into the device result (or the caller's buffer),
+    // then its download
+    auto launch_band = [&](int st, int k) -> int {
+        const int q0 = edge[k], qn = edge[k + 1] - q0;
+        const char *in = st == 0 ? dsrc : dmid;
+        char *out = st < last ? dmid + (size_t)q0 * pitch
+                              : (dst_dev != nullptr ? dst_dev + (size_t)q0 * dst_pitch_host : ddst + (size_t)q0 * pitch);
+        const size_t out_pitch = (st == last && dst_dev != nullptr) ? dst_pitch_host : pitch;
+        if (trace && st == 0) CUDA_TRY(cudaEventRecord(tr[3][k], hp.run));
+        if (!no_kernel) {
+            const int r = stages[st].launch((const float *)in, pitch, (float *)out, out_pitch, q0, qn, hp.run);
+            if (r) {
+                cudaDeviceSynchronize();
+                return r;
+            }
+        }
+        if (st < last) return DCB_OK;
+        if (trace) CUDA_TRY(cudaEventRecord(tr[1][k], hp.run));
+        if (dst_dev != nullptr) {
+            if (trace) CUDA_TRY(cudaEventRecord(tr[2][k], hp.run));
+            return DCB_OK;
+        }
+        CUDA_TRY(cudaEventRecord(hp.ev_run[k], hp.run));
+        CUDA_TRY(cudaStreamWaitEvent(hp.down, hp.ev_run[k], 0));
+        if (dst_pitch_host == wbytes && pitch == wbytes)
+            CUDA_TRY(cudaMemcpyAsync((char *)dst_host + (size_t)q0 * dst_pitch_host, ddst + (size_t)q0 * pitch,
+                                     wbytes * (size_t)qn, cudaMemcpyDeviceToHost, hp.down));
+        else
+            CUDA_TRY(cudaMemcpy2DAsync((char *)dst_host + (size_t)q0 * dst_pitch_host, dst_pitch_host,
+                                       ddst + (size_t)q0 * pitch, pitch, wbytes, qn, cudaMemcpyDeviceToHost,
+                                       hp.down));
+        if (trace) CUDA_TRY(cudaEventRecord(tr[2][k], hp.down));
+        return DCB_OK;
+    };
+    // uploads in row order
     for (int b = 0; b < nbands; ++b) {
         const int r0 = edge[b], nr = edge[b + 1] - r0;
         const char *from = (const char *)src_host + (size_t)r0 * src_pitch_host;
@@ -1529,8 +1619,7 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
             from = to;
             from_pitch = wbytes;
         }
-        // (rows that are contiguous on both sides go as ONE linear copy: a 2-D copy is a descriptor
-        // per row for the copy engine)
+        // (rows that are contiguous on both sides go as ONE linear copy)
         if (from_pitch == wbytes && pitch == wbytes)
             CUDA_TRY(cudaMemcpyAsync(dsrc + (size_t)r0 * pitch, from, wbytes * (size_t)nr,
                                      cudaMemcpyHostToDevice, hp.up));
@@ -1541,54 +1630,33 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
         if (trace) CUDA_TRY(cudaEventRecord(tr[0][b], hp.up));
         // (pinned source: every upload is enqueued before the first launch, as measured best)
         if (!stage && b < nbands - 1) continue;
-        for (; next < nbands && (b == nbands - 1 || need_of(next) <= b); ++next) {
-            const int q0 = edge[next], qn = edge[next + 1] - q0;
-            if (need_of(next) > waited) {
-                CUDA_TRY(cudaStreamWaitEvent(hp.run, hp.ev_up[need_of(next)], 0));
-                waited = need_of(next);
+        const bool all_up = b == nbands - 1;
+        for (; next[0] < nbands && (all_up || need_of(0, next[0]) <= b); ++next[0]) {
+            const int nd = need_of(0, next[0]);
+            if (nd > waited) {
+                CUDA_TRY(cudaStreamWaitEvent(hp.run, hp.ev_up[nd], 0));
+                waited = nd;
             }
-            if (trace) CUDA_TRY(cudaEventRecord(tr[3][next], hp.run));
-            if (dst_dev != nullptr)
-                rc = dcb_unwarp_stack_backward_f32((const float *)dsrc,
-                                                   (float *)(dst_dev + (size_t)q0 * dst_pitch_host), 1, H, W, 0,
-                                                   H, pitch, pitch * (size_t)H, dst_pitch_host,
-                                                   dst_pitch_host * (size_t)qn, q0, qn, 1, model, opt, hp.run);
-            else if (!no_kernel)
-                rc = dcb_unwarp_stack_backward_f32((const float *)dsrc, (float *)(ddst + (size_t)q0 * pitch),
-                                                   1, H, W, 0, H, pitch, pitch * (size_t)H, pitch,
-                                                   pitch * (size_t)qn, q0, qn, 1, model, opt, hp.run);
-            if (rc) {
-                cudaDeviceSynchronize();
-                return rc;
+            rc = launch_band(0, next[0]);
+            if (rc) return rc;
+            // second stage: every band whose last input row has now been launched
+            for (; nstages > 1 && next[1] < nbands &&
+                   (next[0] == nbands - 1 || need_of(1, next[1]) <= next[0]); ++next[1]) {
+                rc = launch_band(1, next[1]);
+                if (rc) return rc;
             }
-            if (trace) CUDA_TRY(cudaEventRecord(tr[1][next], hp.run));
-            if (dst_dev != nullptr) {
-                if (trace) CUDA_TRY(cudaEventRecord(tr[2][next], hp.run));
-                continue;
-            }
-            CUDA_TRY(cudaEventRecord(hp.ev_run[next], hp.run));
-            CUDA_TRY(cudaStreamWaitEvent(hp.down, hp.ev_run[next], 0));
-            if (dst_pitch_host == wbytes && pitch == wbytes)
-                CUDA_TRY(cudaMemcpyAsync((char *)dst_host + (size_t)q0 * dst_pitch_host,
-                                         ddst + (size_t)q0 * pitch, wbytes * (size_t)qn,
-                                         cudaMemcpyDeviceToHost, hp.down));
-            else
-                CUDA_TRY(cudaMemcpy2DAsync((char *)dst_host + (size_t)q0 * dst_pitch_host, dst_pitch_host,
-                                           ddst + (size_t)q0 * pitch, pitch, wbytes, qn,
-                                           cudaMemcpyDeviceToHost, hp.down));
-            if (trace) CUDA_TRY(cudaEventRecord(tr[2][next], hp.down));
         }
     }
     CUDA_TRY(cudaStreamSynchronize(hp.down));
     CUDA_TRY(cudaStreamSynchronize(hp.run));
     CUDA_TRY(cudaStreamSynchronize(hp.up));
     if (trace) {
-        fprintf(stderr, "[dcb] pipe trace (%d bands; rows, needs, us: upload done / kernel start / kernel done / download done)\n", nbands);
+        fprintf(stderr, "[dcb] pipe trace (%d bands, %d stage(s); rows, needs, us: upload done / kernel start / kernel done / download done)\n", nbands, nstages);
         for (int b = 0; b < nbands; ++b) {
             float t[4] = {0, 0, 0, 0};
             for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tr0, tr[k][b]);
             fprintf(stderr, "[dcb]   band %2d rows %5d need %2d  %8.1f %8.1f %8.1f %8.1f\n", b, edge[b + 1] - edge[b],
-                    need_of(b), t[0] * 1e3, t[3] * 1e3, t[1] * 1e3, t[2] * 1e3);
+                    need_of(0, b), t[0] * 1e3, t[3] * 1e3, t[1] * 1e3, t[2] * 1e3);
         }
         cudaEventDestroy(tr0);
         for (int k = 0; k < 4; ++k)
@@ -1597,9 +1665,59 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
     return DCB_OK;
 }
 
-int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W, size_t src_pitch,
-                                      size_t dst_pitch, const dcb_persp *model,
-                                      const dcb_options *opt, void *stream) {
+static PipeStage radial_stage(const dcb_radial *model, const dcb_options *opt, int H, int W) {
+    PipeStage st;
+    st.rows = [=](int r0, int r1, int *lo, int *hi) { radial_row_range(*model, H, W, r0, r1, lo, hi); };
+    st.launch = [=](const float *in, size_t in_pitch, float *out, size_t out_pitch, int q0, int qn,
+                    cudaStream_t stream) {
+        return dcb_unwarp_stack_backward_f32(in, out, 1, H, W, 0, H, in_pitch, in_pitch * (size_t)H, out_pitch,
+                                             out_pitch * (size_t)qn, q0, qn, 1, model, opt, stream);
+    };
+    return st;
+}
+
+static int persp_rows_f32(const float *src, float *dst, int H, int W, size_t src_pitch, size_t dst_pitch,
+                          int row0, int nrows, const dcb_persp *model, const dcb_options *opt, void *stream);
+
+static PipeStage persp_stage(const dcb_persp *model, const dcb_options *opt, int H, int W) {
+    PipeStage st;
+    st.rows = [=](int r0, int r1, int *lo, int *hi) { persp_row_range(*model, H, W, r0, r1, lo, hi); };
+    st.launch = [=](const float *in, size_t in_pitch, float *out, size_t out_pitch, int q0, int qn,
+                    cudaStream_t stream) {
+        return persp_rows_f32(in, out, H, W, in_pitch, out_pitch, q0, qn, model, opt, stream);
+    };
+    return st;
+}
+
+int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, int H, int W,
+                                       size_t src_pitch_host, size_t dst_pitch_host,
+                                       const dcb_radial *model, const dcb_options *opt, int nbands) {
+    REQUIRE(model != nullptr, "radial model is NULL");
+    const PipeStage st = radial_stage(model, opt, H, W);
+    return host_pipeline(src_host, dst_host, H, W, src_pitch_host, dst_pitch_host, nbands, 1, &st);
+}
+
+int dcb_correct_perspective_image_host_f32(const float *src_host, float *dst_host, int H, int W,
+                                           size_t src_pitch_host, size_t dst_pitch_host,
+                                           const dcb_persp *model, const dcb_options *opt, int nbands) {
+    REQUIRE(model != nullptr, "perspective model is NULL");
+    const PipeStage st = persp_stage(model, opt, H, W);
+    return host_pipeline(src_host, dst_host, H, W, src_pitch_host, dst_pitch_host, nbands, 1, &st);
+}
+
+int dcb_unwarp_image_backward_perspective_host_f32(const float *src_host, float *dst_host, int H, int W,
+                                                   size_t src_pitch_host, size_t dst_pitch_host,
+                                                   const dcb_radial *radial, const dcb_persp *persp,
+                                                   const dcb_options *opt, int nbands) {
+    REQUIRE(radial != nullptr, "radial model is NULL");
+    REQUIRE(persp != nullptr, "perspective model is NULL");
+    const PipeStage st[2] = {radial_stage(radial, opt, H, W), persp_stage(persp, opt, H, W)};
+    return host_pipeline(src_host, dst_host, H, W, src_pitch_host, dst_pitch_host, nbands, 2, st);
+}
+
+// output rows [row0, row0 + nrows) of the projective remap; dst points at row row0
+static int persp_rows_f32(const float *src, float *dst, int H, int W, size_t src_pitch, size_t dst_pitch,
+                          int row0, int nrows, const dcb_persp *model, const dcb_options *opt, void *stream) {
     dcb_options o;
     int rc = check_options(opt, &o);
     if (rc) return rc;
@@ -1618,8 +1736,8 @@ int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W
     p.H = H;
     p.W = W;
     p.D = 1;
-    p.row0 = 0;
-    p.nrows = H;
+    p.row0 = row0;
+    p.nrows = nrows;
     p.yorg = 0;
     p.ylast = H - 1;
     double gm, gc;
@@ -1633,13 +1751,19 @@ int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W
     q.dst_pitch = p.dst_pitch;
     q.H = H;
     q.W = W;
-    q.row0 = 0;
-    q.nrows = H;
+    q.row0 = row0;
+    q.nrows = nrows;
     q.yorg = 0;
     q.ylast = H - 1;
     q.rint = (o.flags & DCB_FLAG_ROUND_INT) ? 1 : 0;
     const ImageKernelSel k = pick_image_kernel<MAP_PERSP>(o.order, o.blend, 0, o.flags);
     return plan_and_launch_image(k, q, gm, gc, o.path, src_pitch, (cudaStream_t)stream, MAP_PERSP);
+}
+
+int dcb_correct_perspective_image_f32(const float *src, float *dst, int H, int W, size_t src_pitch,
+                                      size_t dst_pitch, const dcb_persp *model,
+                                      const dcb_options *opt, void *stream) {
+    return persp_rows_f32(src, dst, H, W, src_pitch, dst_pitch, 0, H, model, opt, stream);
 }
 
 int dcb_unwarp_image_backward_perspective_f32(const float *src, float *dst, float *scratch, int H,

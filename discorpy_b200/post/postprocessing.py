@@ -584,6 +584,23 @@ _DTYPE_CODES = {np.dtype(np.float32): _cabi.DTYPE_F32,
                 np.dtype(np.int16): _cabi.DTYPE_I16}
 
 
+def _host_pipeline_f32(entry, mat, models, order):
+    """float32 host image -> pinned float32 host result through one of the banded
+    host-buffer entries (``dcb_*_host_f32``: upload, kernels and download overlap
+    in row bands; a pageable ``mat`` is staged band by band by the library)."""
+    (height, width) = mat.shape
+    src = mat if mat.flags.c_contiguous else np.ascontiguousarray(mat)
+    opt = _opts(order)
+    _dev.ensure_init()
+    out = _dev.pinned_empty((height, width), np.float32)
+    if src is mat:
+        _dev.maybe_register(src)      # a frame buffer seen before: page-lock it in place
+    args = [ctypes.byref(m) for m in models]
+    _cabi.call(entry, _vp(src.ctypes.data), _vp(out.ctypes.data), height, width,
+               width * 4, width * 4, *args, ctypes.byref(opt), config["bands"])
+    return out
+
+
 def _upload_native(arr, stream):
     """Host array (H, W) or (D, H, W) of a supported dtype -> (float32
     DeviceArray of the same shape, kernel flags, dtype to return or None).
@@ -726,6 +743,10 @@ def correct_perspective_image(mat, list_coef, order=1, mode="reflect",
     model = _cabi.make_persp(list_coef)
     if _wants_spline(mat, order):
         return _spline.remap(mat, order, mode, _cabi.MAP_PERSP, persp=model)[0]
+    if not on_device and mat.dtype == np.float32:
+        # host in, host out: banded upload / compute / download pipeline
+        return _host_pipeline_f32("dcb_correct_perspective_image_host_f32", mat,
+                                  (model,), order)
     stream = _dev.current_stream()
     flags, out_dtype = 0, None
     if on_device:
@@ -762,6 +783,10 @@ def unwarp_image_backward_perspective(mat, xcenter, ycenter, list_fact,
     if _wants_spline(mat, order):
         tmp = _spline.remap(mat, order, mode, _cabi.MAP_RADIAL, radial=radial)[0]
         return _spline.remap(tmp, order, mode, _cabi.MAP_PERSP, persp=persp)[0]
+    if not on_device and mat.dtype == np.float32:
+        # host in, host out: both passes band by band between the two PCIe directions
+        return _host_pipeline_f32("dcb_unwarp_image_backward_perspective_host_f32", mat,
+                                  (radial, persp), order)
     stream = _dev.current_stream()
     flags, out_dtype = 0, None
     if on_device:

@@ -159,6 +159,24 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
                                        const dcb_radial *model_host,
                                        const dcb_options *opt_host, int nbands);
 
+/* The projective remap (`correct_perspective_image`, postprocessing.py:462-492) and
+ * the radial remap followed by the projective one (demo_05.py:127,147) for HOST
+ * buffers, through the same banded pipeline: a band of projective output rows is
+ * launched as soon as the last row it can sample has been uploaded (or, in the
+ * two-stage form, has been produced by the radial stage; the intermediate image
+ * stays in HBM), and is downloaded behind its kernel.  Results equal those of
+ * dcb_correct_perspective_image_f32 / dcb_unwarp_image_backward_perspective_f32. */
+int dcb_correct_perspective_image_host_f32(const float *src_host, float *dst_host, int H, int W,
+                                           size_t src_pitch_host, size_t dst_pitch_host,
+                                           const dcb_persp *model_host,
+                                           const dcb_options *opt_host, int nbands);
+int dcb_unwarp_image_backward_perspective_host_f32(const float *src_host, float *dst_host, int H,
+                                                   int W, size_t src_pitch_host,
+                                                   size_t dst_pitch_host,
+                                                   const dcb_radial *radial_host,
+                                                   const dcb_persp *persp_host,
+                                                   const dcb_options *opt_host, int nbands);
+
 /* Replaces the per-slice Python loops of
  *   postprocessing.py:188-229 `unwarp_slice_backward`        (coord_round = 0,
  *       row0 = index, nrows = 1: float64 coordinates, never rounded), and

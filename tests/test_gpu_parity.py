@@ -657,6 +657,50 @@ def test_launches_from_two_host_threads_share_no_scheduler_state():
     assert not errors, errors[:4]
 
 
+def test_perspective_and_combined_host_pipelines():
+    """dcb_correct_perspective_image_host_f32 / dcb_unwarp_image_backward_perspective_host_f32
+    (host float32 in, host float32 out, banded): the bytes of the device-resident entries and of
+    the oracle, for every band count, pinned and pageable sources, a keystone whose bands reach far
+    across the image, a map that leaves the image, and a denominator that changes sign inside it
+    (every band then waits for the whole upload)."""
+    rng = np.random.default_rng(91)
+    fact = [1.0, -2e-5, 6e-8, -1e-10, 5e-14]
+    cases = [((1200, 1664), [1.02, 0.01, -15.0, 0.005, 1.01, -8.0, 8e-6, -5e-6]),
+             ((777, 1031), [0.93, -0.04, 40.0, 0.02, 0.97, 25.0, -6e-5, 4e-5]),
+             ((640, 512), [0.6, 0.5, -100.0, -0.5, 0.6, 300.0, 2e-4, -3e-4]),      # rotation + keystone
+             ((400, 600), [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, -4.03e-3, 1.3e-4])]      # denominator crosses 0 (never exactly)
+    for shape, coef in cases:
+        mat = rng.random(shape, dtype=np.float32) * 9.0
+        pinned = dcb.pinned_empty(shape, np.float32)
+        pinned[:] = mat
+        want = orc.correct_perspective_image(mat, coef)
+        dev = post.correct_perspective_image(dcb.DeviceArray.from_host(mat), coef).to_host()
+        assert np.array_equal(dev, want), (shape, coef)
+        xc, yc = shape[1] / 2 + 3.3, shape[0] / 2 - 2.2
+        want2 = orc.correct_perspective_image(orc.unwarp_image_backward(mat, xc, yc, fact), coef)
+        for bands in (0, 1, 2, 3, 7, 16, 32):
+            post.config["bands"] = bands
+            try:
+                src = mat if bands in (2, 7) else pinned
+                got = post.correct_perspective_image(src, coef)
+                got2 = post.unwarp_image_backward_perspective(src, xc, yc, fact, coef)
+                got0 = post.correct_perspective_image(src, coef, order=0)
+            finally:
+                post.config["bands"] = 0
+            assert np.array_equal(got, want), (shape, coef, bands)
+            assert np.array_equal(got2, want2), (shape, coef, bands)
+            assert np.array_equal(got0, orc.correct_perspective_image(mat, coef, order=0)), (shape, bands)
+    # a 48 MiB image: the unequal band schedule (2 / 2 / 4 MiB at both ends), both stages
+    big = rng.random((3072, 4096), dtype=np.float32)
+    coef = [1.02, 0.01, -15.0, 0.005, 1.01, -8.0, 8e-6, -5e-6]
+    got = post.unwarp_image_backward_perspective(big, 2050.4, 1500.6, FACT5, coef)
+    dev = post.unwarp_image_backward_perspective(dcb.DeviceArray.from_host(big), 2050.4, 1500.6,
+                                                 FACT5, coef)
+    assert np.array_equal(got, dev.to_host())
+    got = post.correct_perspective_image(big, coef)
+    assert np.array_equal(got, post.correct_perspective_image(dcb.DeviceArray.from_host(big), coef).to_host())
+
+
 def test_projective_patch_path_equals_exact_path():
     """correct_perspective_image on the patch path (verified row interpolants of 1 / denominator,
     csrc/remap_image.cuh) gives the bytes of the exact division chain (DCB_IMG_FAST=0) and of
