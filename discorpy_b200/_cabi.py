@@ -99,6 +99,7 @@ SIGNATURES = {
     "dcb_unwarp_image_backward_host_f32": [_vp, _vp, _i, _i, _sz, _sz,
                                            ctypes.POINTER(Radial),
                                            ctypes.POINTER(Options), _i],
+    "dcb_host_copy_2d": [_vp, _sz, _vp, _sz, _sz, _i],
     "dcb_correct_perspective_image_host_f32": [_vp, _vp, _i, _i, _sz, _sz,
                                                ctypes.POINTER(Persp),
                                                ctypes.POINTER(Options), _i],

@@ -1010,7 +1010,14 @@ private:
             seen = gen_;
             const Job j = job_;
             lk.unlock();
-            copy_rows(j, (int)((long long)j.rows * id / nth_), (int)((long long)j.rows * (id + 1) / nth_));
+            if (j.rows >= 2 * nth_) {   // many rows: a share of the rows each
+                copy_rows(j, (int)((long long)j.rows * id / nth_), (int)((long long)j.rows * (id + 1) / nth_));
+            } else {                    // a few long rows (slices of a stack): a share of every row's bytes
+                const size_t c0 = j.width_bytes * (size_t)id / (size_t)nth_ / 64 * 64;
+                const size_t c1 = id + 1 == nth_ ? j.width_bytes : j.width_bytes * (size_t)(id + 1) / (size_t)nth_ / 64 * 64;
+                for (int r = 0; r < j.rows && c1 > c0; ++r)
+                    stream_copy(j.dst + (size_t)r * j.dst_pitch + c0, j.src + (size_t)r * j.src_pitch + c0, c1 - c0);
+            }
             lk.lock();
             if (--pending_ == 0) cv_done_.notify_one();
         }
@@ -1687,6 +1694,15 @@ static PipeStage persp_stage(const dcb_persp *model, const dcb_options *opt, int
         return persp_rows_f32(in, out, H, W, in_pitch, out_pitch, q0, qn, model, opt, stream);
     };
     return st;
+}
+
+int dcb_host_copy_2d(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes,
+                     int rows) {
+    REQUIRE(dst != nullptr && src != nullptr, "null pointer");
+    REQUIRE(rows >= 0 && dst_pitch >= width_bytes && src_pitch >= width_bytes, "bad pitch");
+    if (rows == 0 || width_bytes == 0) return DCB_OK;
+    CopyPool::get().run({(const char *)src, (char *)dst, src_pitch, dst_pitch, width_bytes, rows});
+    return DCB_OK;
 }
 
 int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, int H, int W,

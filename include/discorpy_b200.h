@@ -159,6 +159,14 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
                                        const dcb_radial *model_host,
                                        const dcb_options *opt_host, int nbands);
 
+/* Host-to-host copy of `rows` rows of `width_bytes` bytes (pitches in bytes) by the
+ * library's pool of host threads with non-temporal stores -- what stages pageable
+ * (ordinary NumPy) data into page-locked buffers and results back out of them
+ * (post/streaming.py; one core copies ~4 GB/s, far less than the PCIe link).
+ * Synchronous; calls are serialised.  No reference counterpart (NumPy slicing). */
+int dcb_host_copy_2d(void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
+                     size_t width_bytes, int rows);
+
 /* The projective remap (`correct_perspective_image`, postprocessing.py:462-492) and
  * the radial remap followed by the projective one (demo_05.py:127,147) for HOST
  * buffers, through the same banded pipeline: a band of projective output rows is

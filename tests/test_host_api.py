@@ -199,3 +199,23 @@ def test_fold_coordinate_is_scipys_boundary_mapping():
                 assert np.array_equal(got, want), (trial, order, mode)
     with pytest.raises(NotImplementedError):
         post._explicit_coordinates(np.array([-2.0]), np.array([1.0]), 8, 8, 1, "grid-wrap")
+
+
+def test_host_copy_2d_matches_numpy():
+    """dcb_host_copy_2d (the copy pool with non-temporal stores that stages pageable data, no GPU
+    needed): any alignment, pitch and size, both ways of splitting the work over the threads."""
+    import ctypes
+    rng = np.random.default_rng(5)
+    cases = [(1, 1), (3, 63), (1, 70001), (5, 1 << 20), (40, 4097), (64, 300000), (2, (3 << 20) + 5),
+             (700, 16384), (9, 65536)]
+    for rows, width in cases:
+        for so, do in ((0, 0), (1, 3), (13, 64), (64, 7)):
+            sp, dp = width + int(rng.integers(0, 200)), width + int(rng.integers(0, 200))
+            src = rng.integers(0, 256, rows * sp + so + 64, dtype=np.uint8)
+            dst = np.full(rows * dp + do + 64, 0xA5, dtype=np.uint8)
+            want = dst.copy()
+            for r in range(rows):
+                want[do + r * dp: do + r * dp + width] = src[so + r * sp: so + r * sp + width]
+            _cabi.call("dcb_host_copy_2d", ctypes.c_void_p(dst.ctypes.data + do), dp,
+                       ctypes.c_void_p(src.ctypes.data + so), sp, width, rows)
+            assert np.array_equal(dst, want), (rows, width, so, do)
