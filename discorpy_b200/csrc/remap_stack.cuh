@@ -81,7 +81,14 @@ struct StackWeights {
     static constexpr bool kW4 = (ORDER == 1 && BLEND == DCB_BLEND_EXACT && ROUND32);
     // everything else keeps the two fractions as doubles
     static constexpr bool kT64 = (ORDER == 1 && !kF32 && !kW4);
-    static constexpr int kDoubles = kW4 ? 4 : (kT64 ? 2 : 0);
+    // float64 coordinates with the exact blend (unwarp_slice_backward): the complements 1 - tx and
+    // 1 - ty are kept too instead of being re-formed for every slice (2 of 13 fp64 operations per
+    // pixel and slice)
+#ifndef DCB_STK_T64W
+#define DCB_STK_T64W 1
+#endif
+    static constexpr bool kT64W = kT64 && BLEND == DCB_BLEND_EXACT && DCB_STK_T64W;
+    static constexpr int kDoubles = (kW4 || kT64W) ? 4 : (kT64 ? 2 : 0);
     // (Sampling the fp64 blends from a float64 copy of the staged box -- one
     // conversion per source pixel instead of one per tap -- was measured with a
     // CTA barrier per slice and rejected: 48 % vs 56 % of the HBM peak on
@@ -145,6 +152,10 @@ __global__ void __launch_bounds__(kThreads, DCB_STK_MINB)
         // (read by the other threads after the barrier every item has: the bounding-box exchange
         // of staged launches, the one at the end of the loop body otherwise)
         if (threadIdx.x == 0) s_item[par ^ 1] = (int)gridDim.x + (int)atomicAdd(&p.sched[0], 1u);
+        // (Claiming the items in strips of 4 / 8 / 16 tile columns, row by row inside a strip -- so that
+        // a tile and the one below it, whose boxes share most of their rows under a sheared map, read
+        // the same slice within a slice or two of each other -- changes nothing on any BASELINE shape:
+        // profiles/r2/ab_stack_strip.txt.)
         const int txi = item % p.tiles_x;
         const int rest = item / p.tiles_x;
         const int tyi = rest % p.tiles_y;
@@ -283,6 +294,10 @@ __global__ void __launch_bounds__(kThreads, DCB_STK_MINB)
                 } else if (SW::kT64) {
                     wd[i][0] = (double)tx[i];
                     wd[i][1] = (double)ty[i];
+                    if (SW::kT64W) {
+                        wd[i][SW::kT64W ? 2 : 0] = __dsub_rn(1.0, (double)tx[i]);
+                        wd[i][SW::kT64W ? 3 : 0] = __dsub_rn(1.0, (double)ty[i]);
+                    }
                 } else if (SW::kF32) {
                     wf[i][0] = (float)tx[i];
                     wf[i][1] = (float)ty[i];
@@ -376,7 +391,8 @@ __global__ void __launch_bounds__(kThreads, DCB_STK_MINB)
                             } else {
                                 // float64 coordinates: SciPy's two-step products, every step rounded
                                 const double wx1 = wd[i][0], wy1 = wd[i][1];
-                                const double wx0 = __dsub_rn(1.0, wx1), wy0 = __dsub_rn(1.0, wy1);
+                                const double wx0 = SW::kT64W ? wd[i][SW::kT64W ? 2 : 0] : __dsub_rn(1.0, wx1);
+                                const double wy0 = SW::kT64W ? wd[i][SW::kT64W ? 3 : 0] : __dsub_rn(1.0, wy1);
                                 s = __dmul_rn(__dmul_rn(a, wy0), wx0);
                                 s = __dadd_rn(s, __dmul_rn(__dmul_rn(b, wy0), wx1));
                                 s = __dadd_rn(s, __dmul_rn(__dmul_rn(c, wy1), wx0));
