@@ -42,6 +42,8 @@ def run(n, seed):
         kind = rng.choice(["radial", "radial", "persp", "chunk", "slice", "both", "color"])
         order = int(rng.choice([0, 1, 1, 1, 2, 3, 3, 4, 5]))
         mode = str(rng.choice(MODES))
+        # row bands of the host-buffer pipelines (float32 host images: radial, projective, both)
+        post.config["bands"] = int(rng.choice([0, 0, 1, 2, 3, 5, 9, 32]))
         try:
             if kind == "radial":
                 got = post.unwarp_image_backward(mat, xc, yc, fact, order=order, mode=mode)
@@ -102,6 +104,7 @@ def run(n, seed):
             nd = -1 if got is None or got.shape != want.shape else int(np.count_nonzero(got != want))
             print("MISMATCH case %d: %s %s %dx%d order %d mode %s nt %d xc %.3f yc %.3f: %d samples differ"
                   % (it, kind, dt, h, w, order, mode, nt, xc, yc, nd), flush=True)
+    post.config["bands"] = 0
     print("fuzz: %d cases, %d not bit-identical" % (n, bad))
     return bad
 
