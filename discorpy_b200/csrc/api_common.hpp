@@ -10,6 +10,10 @@ int fail(int code, const char *fmt, ...);
 void count_launches(int n);
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda), or NULL
 void *tma_encode_fn();
+// output rows [row0, row0 + nrows) of the projective remap, dst pointing at row row0 (api.cu; the
+// band launches of the host-buffer pipeline in hostpipe.cu)
+int persp_rows_f32(const float *src, float *dst, int H, int W, size_t src_pitch, size_t dst_pitch,
+                   int row0, int nrows, const dcb_persp *model, const dcb_options *opt, void *stream);
 }  // namespace dcb
 
 #define CUDA_TRY(expr)                                                                      \

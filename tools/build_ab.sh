@@ -6,5 +6,5 @@ cd "$(dirname "$0")/../discorpy_b200/csrc"
 name=$1; shift
 mkdir -p ../lib/ab
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I../../include \
-  -DDCB_NT_ONLY=5 "$@" -shared -o ../lib/ab/libdcb_$name.so api.cu diag.cu mg.cu -ldl
+  -DDCB_NT_ONLY=5 "$@" -shared -o ../lib/ab/libdcb_$name.so api.cu diag.cu mg.cu hostpipe.cu -ldl
 ls -la ../lib/ab/libdcb_$name.so
