@@ -601,6 +601,35 @@ def _host_pipeline_f32(entry, mat, models, order):
     return out
 
 
+_STAGE_CHUNK = 4 << 20
+
+
+def _h2d_raw(dptr, raw, stream):
+    """Bytes of the C-contiguous host array ``raw`` -> device address ``dptr`` on ``stream``.
+    Page-locked arrays are read by the DMA engine directly.  Pageable ones of 8 MiB and more
+    are copied chunk by chunk into a page-locked block by the library's copy pool
+    (non-temporal stores, ``dcb_host_copy_2d``) while the DMA engine moves the previous chunk
+    -- the driver's own staging of pageable memory runs on one thread (4096^2 uint16: 2.3 ms
+    of a 3 ms call).  Returns an object to keep alive until the stream has been synchronised
+    (or None)."""
+    n = raw.nbytes
+    if n < (8 << 20) or _dev.is_pinned(raw):
+        _cabi.call("dcb_h2d", _vp(dptr), _vp(raw.ctypes.data), n, _vp(stream.handle))
+        return None
+    bufs = [_dev.pinned_empty((_STAGE_CHUNK,), np.uint8) for _ in range(2)]
+    evs = [_dev.Event(), _dev.Event()]
+    for k, off in enumerate(range(0, n, _STAGE_CHUNK)):
+        b, m = k & 1, min(_STAGE_CHUNK, n - off)
+        if k >= 2:
+            evs[b].sync()          # the DMA that last read this block is done
+        _cabi.call("dcb_host_copy_2d", _vp(bufs[b].ctypes.data), m,
+                   _vp(raw.ctypes.data + off), m, m, 1)
+        _cabi.call("dcb_h2d", _vp(dptr + off), _vp(bufs[b].ctypes.data), m,
+                   _vp(stream.handle))
+        evs[b].record(stream)
+    return bufs
+
+
 def _upload_native(arr, stream):
     """Host array (H, W) or (D, H, W) of a supported dtype -> (float32
     DeviceArray of the same shape, kernel flags, dtype to return or None).
@@ -619,12 +648,12 @@ def _upload_native(arr, stream):
     rows = int(np.prod(raw.shape[:-1], dtype=np.int64))
     sh = _vp(stream.handle)
     with _dev.borrowed(max(raw.nbytes, 16)) as draw:
-        _cabi.call("dcb_h2d", _vp(draw.ptr), _vp(raw.ctypes.data), raw.nbytes,
-                   sh)
+        keep = _h2d_raw(draw.ptr, raw, stream)
         _cabi.call("dcb_unpack_hwc_to_planes_f32", _vp(draw.ptr),
                    _DTYPE_CODES[raw.dtype], _vp(dev.ptr), rows, raw.shape[-1],
                    1, dev.pitch, dev.pitch * rows, sh)
-        stream.sync()     # `raw` and the borrowed buffer are free again
+        stream.sync()     # `raw`, the staging block and the borrowed buffer are free again
+        del keep
     return dev, _cabi.FLAG_ROUND_INT, raw.dtype
 
 
@@ -668,9 +697,8 @@ def _unwarp_frame_hwc(frame, xcenter, ycenter, list_fact, order):
     dst = DeviceArray((chan, height, width))
     out = _dev.pinned_empty(raw.shape, raw.dtype)
     with _dev.borrowed(max(raw.nbytes, 16)) as draw:
-        _cabi.call("dcb_h2d", _vp(draw.ptr), _vp(raw.ctypes.data), raw.nbytes,
-                   sh)
-        if not _dev.is_pinned(raw):
+        keep = _h2d_raw(draw.ptr, raw, stream)
+        if keep is None and not _dev.is_pinned(raw):
             stream.sync()
         _cabi.call("dcb_unpack_hwc_to_planes_f32", _vp(draw.ptr), code,
                    _vp(planes.ptr), height, width, chan, planes.pitch,
@@ -683,6 +711,7 @@ def _unwarp_frame_hwc(frame, xcenter, ycenter, list_fact, order):
         _cabi.call("dcb_d2h", _vp(out.ctypes.data), _vp(draw.ptr), raw.nbytes,
                    sh)
         stream.sync()
+        del keep
     return out
 
 
