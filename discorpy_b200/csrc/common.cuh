@@ -78,6 +78,24 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// The same load with an L2 eviction-priority hint (createpolicy: 0 evict_first, 1 evict_last).
+__device__ __forceinline__ uint64_t l2_policy(int evict_last) {
+    uint64_t pol;
+    if (evict_last)
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_3d_hint(void *smem_dst, const CUtensorMap *map, int x, int y,
+                                                 int z, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
 // The same box into L2 only (no shared-memory destination, no completion to wait for).
 __device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap *map, int x, int y, int z) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
