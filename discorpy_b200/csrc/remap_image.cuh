@@ -65,6 +65,11 @@ struct ImageParams {
     PerspDev per;
 };
 
+// A/B builds: L2 eviction priority of the source boxes (1 evict_first, 2 evict_last, 0 no hint);
+// -1: the kernel's own choice (see issue_box)
+#ifndef DCB_IMG_L2HINT
+#define DCB_IMG_L2HINT (-1)
+#endif
 #ifndef DCB_IMG_EXACT_RAW
 #define DCB_IMG_EXACT_RAW 2   // 0: float64 tiles widened by the producers (round 1), 1: raw tiles + F2F, 2: raw tiles, scaled domain
 #endif
@@ -751,9 +756,20 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             return bx;
         };
         auto issue_box = [&](const int2 bx, int st) {
-            if (bx.y >= 0)
-                tma_load_3d(smem + (size_t)st * p.stage_bytes, &tmap, bx.x, bx.y - p.yorg, 0,
-                            &raw_full[st]);
+            if (bx.y >= 0) {
+                // L2 eviction priority of the source boxes: the bilinear kernels read them
+                // evict_first (a box is needed once, its lines make room for the output's write
+                // combining: exact 43.4 -> 43.0 us, float32 blend 32.1 -> 31.5), the nearest-neighbour
+                // kernel -- the one closest to the memory roofline, where halo hits count -- without
+                // a hint (26.5 us; 27.3 with evict_first).  profiles/r2/ab2_il2hint.txt
+                constexpr int kHint = DCB_IMG_L2HINT >= 0 ? DCB_IMG_L2HINT : (ORDER == 1 ? 1 : 0);
+                if constexpr (kHint != 0)
+                    tma_load_3d_hint(smem + (size_t)st * p.stage_bytes, &tmap, bx.x, bx.y - p.yorg, 0,
+                                     &raw_full[st], l2_policy(kHint - 1));
+                else
+                    tma_load_3d(smem + (size_t)st * p.stage_bytes, &tmap, bx.x, bx.y - p.yorg, 0,
+                                &raw_full[st]);
+            }
         };
         // A plan that was complete before this launch was enqueued may be read while the preceding
         // grid is still running: the static range and the plan half of its first NBUF tiles are
