@@ -661,12 +661,25 @@ constexpr int kLogCtas = 4, kLogEvents = 64;   // per-warp event log of the firs
 constexpr int kTimelineCtas = 1024;   // diagnostics: p.stats[8 + 8 b ..] = start, first tile, end, SM, waits of CTA b
 
 // 1-D bulk copy global -> shared, completion on an mbarrier (16-byte aligned, size % 16 == 0)
+// The plan records are loaded with the L2 evict_last hint (2; 1: evict_first, 0: none): the 8.6 MB plan of a
+// calibration is read again by every launch while 128 MB of image data pass through the L2 in between
+// (exact 43.00 -> 42.94 us, nearest 26.5 -> 26.3: profiles/r2/ab2_planhint.txt)
+#ifndef DCB_IMG_PLANHINT
+#define DCB_IMG_PLANHINT 2
+#endif
 __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes,
                                           uint64_t *bar) {
+#if DCB_IMG_PLANHINT
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(l2_policy(DCB_IMG_PLANHINT - 1))
+        : "memory");
+#else
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+#endif
 }
 
 // NT > 0: number of polynomial terms known at compile time (coefficients become
