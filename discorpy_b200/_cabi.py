@@ -100,6 +100,8 @@ SIGNATURES = {
                                            ctypes.POINTER(Radial),
                                            ctypes.POINTER(Options), _i],
     "dcb_host_copy_2d": [_vp, _sz, _vp, _sz, _sz, _i],
+    "dcb_host_band_edges": [_i, _i, _i, ctypes.POINTER(ctypes.c_int),
+                            ctypes.POINTER(ctypes.c_int)],
     "dcb_correct_perspective_image_host_f32": [_vp, _vp, _i, _i, _sz, _sz,
                                                ctypes.POINTER(Persp),
                                                ctypes.POINTER(Options), _i],

@@ -329,6 +329,66 @@ void persp_row_range(const dcb_persp &m, int H, int W, int r0, int r1, int *lo, 
 
 }  // namespace
 
+// Row bands [edge[b], edge[b + 1]) of an H x W float32 image; returns their number (<= kMaxBands).
+// The call ends one upload band (the rows below an output band that it samples), one kernel and one
+// download band after the last upload, and the first download starts two upload bands into the
+// call: images of 32 MiB and more get bands of 2, 2 and 4 MiB at both ends and ~6 MiB bands between
+// them (a 4096^2 image: 128, 128, 256, 8 x 384, 256, 128, 128 rows -- 1.78 ms against 1.82 ms for
+// eight equal bands; smaller bands throughout cost more in per-copy overhead than they save:
+// tools/e2e_edges.py, profiles/r2/e2e_edges_*.txt); smaller images one band per 3.5 MiB, at most 8
+// (2160 x 2560: 0.73 ms in 6 bands against 0.87 ms in 2, profiles/r2/e2e_small_r2z9.txt).
+// nbands > 0 asks for that many equal bands; DCB_BAND_EDGES="n0,n1,..." (diagnostics, only with
+// nbands <= 0) gives the band heights in 64ths of the image.
+static int band_edges(int H, int W, int nbands, int *edge) {
+    const bool auto_bands = nbands <= 0;
+    const size_t img_bytes = (size_t)W * 4 * (size_t)H;
+    const int unit = (int)std::max<size_t>(1, ((size_t)2 << 20) / ((size_t)W * 4));   // rows per 2 MiB
+    if (auto_bands && img_bytes >= ((size_t)32 << 20) && H >= 16 * unit) {
+        const int mid = H - 8 * unit;
+        const int nmid = (int)std::max<size_t>(
+            1, std::min<size_t>(std::min<size_t>(kMaxBands - 6, (size_t)mid),
+                                ((size_t)mid * W * 4 + ((size_t)3 << 20)) / ((size_t)6 << 20)));
+        int n = 0;
+        edge[0] = 0;
+        for (int h : {unit, unit, 2 * unit}) edge[n + 1] = edge[n] + h, ++n;
+        for (int k = 1; k <= nmid; ++k) edge[++n] = 4 * unit + (int)((long long)mid * k / nmid);
+        for (int h : {2 * unit, unit, unit}) edge[n + 1] = edge[n] + h, ++n;
+        nbands = n;
+    } else {
+        if (auto_bands) nbands = (int)std::max<size_t>(1, std::min<size_t>(8, img_bytes / ((size_t)7 << 19)));
+        nbands = std::min(std::min(nbands, kMaxBands), H);
+        const int rows_per = (H + nbands - 1) / nbands;
+        nbands = (H + rows_per - 1) / rows_per;
+        for (int b = 0; b <= nbands; ++b) edge[b] = std::min(H, b * rows_per);
+    }
+    const char *env = auto_bands ? getenv("DCB_BAND_EDGES") : nullptr;
+    if (env != nullptr && env[0] != 0 && H >= 64) {
+        int n = 0, acc = 0;
+        edge[0] = 0;
+        for (const char *q = env; *q != 0 && n < kMaxBands;) {
+            char *e = nullptr;
+            const long v = strtol(q, &e, 10);
+            if (e == q || v <= 0) break;
+            acc += (int)v;
+            const int row = (int)std::min<long long>(H, (long long)H * acc / 64);
+            if (row > edge[n]) edge[++n] = row;
+            q = (*e == ',') ? e + 1 : e;
+        }
+        if (n == 0 || edge[n] < H) {
+            if (n < kMaxBands) edge[++n] = H; else edge[n] = H;
+        }
+        nbands = n;
+    }
+    return nbands;
+}
+
+// The schedule alone (no GPU needed): what host_pipeline would use for an H x W image.
+int dcb_host_band_edges(int H, int W, int nbands, int *edges, int *count) {
+    REQUIRE(H >= 1 && W >= 1 && edges != nullptr && count != nullptr, "bad arguments");
+    *count = band_edges(H, W, nbands, edges);
+    return DCB_OK;
+}
+
 // One stage of the host-buffer pipeline: a remap of the whole image, launched band by band.
 struct PipeStage {
     // conservative range [lo, hi] of the INPUT rows that output rows [r0, r1) of this stage sample
@@ -354,56 +414,8 @@ static int host_pipeline(const float *src_host, float *dst_host, int H, int W, s
     int rc = pipe_prepare(pitch * (size_t)H, pitch * (size_t)H, nstages > 1 ? pitch * (size_t)H : 0);
     if (rc) return rc;
     HostPipe &hp = g_pipe;
-    // Row bands [edge[b], edge[b + 1]).  The call ends one upload band (the rows below an output
-    // band that it samples), one kernel and one download band after the last upload, and the first
-    // download starts two upload bands into the call: images of 32 MiB and more get bands of 2, 2
-    // and 4 MiB at both ends and ~6 MiB bands between them (a 4096^2 image: 128, 128, 256, 8 x 384,
-    // 256, 128, 128 rows -- 1.78 ms against 1.82 ms for eight equal bands; smaller bands throughout
-    // cost more in per-copy overhead than they save: tools/e2e_edges.py, profiles/r2/e2e_edges_*.txt);
-    // smaller images one band per 3.5 MiB, at most 8 (2160 x 2560: 0.73 ms in 6 bands against 0.87 ms
-    // in 2, profiles/r2/e2e_small_r2z9.txt).  nbands > 0 asks for that many equal bands;
-    // DCB_BAND_EDGES="n0,n1,..." (diagnostics) gives the band heights in 64ths of the image.
     int edge[kMaxBands + 1];
-    {
-        const bool auto_bands = nbands <= 0;
-        const size_t img_bytes = (size_t)W * 4 * (size_t)H;
-        const int unit = (int)std::max<size_t>(1, ((size_t)2 << 20) / ((size_t)W * 4));   // rows per 2 MiB
-        if (auto_bands && img_bytes >= ((size_t)32 << 20) && H >= 16 * unit) {
-            const int mid = H - 8 * unit;
-            const int nmid = (int)std::max<size_t>(1, std::min<size_t>(kMaxBands - 6,
-                                                   ((size_t)mid * W * 4 + ((size_t)3 << 20)) / ((size_t)6 << 20)));
-            int n = 0;
-            edge[0] = 0;
-            for (int h : {unit, unit, 2 * unit}) edge[n + 1] = edge[n] + h, ++n;
-            for (int k = 1; k <= nmid; ++k) edge[++n] = 4 * unit + (int)((long long)mid * k / nmid);
-            for (int h : {2 * unit, unit, unit}) edge[n + 1] = edge[n] + h, ++n;
-            nbands = n;
-        } else {
-            if (auto_bands) nbands = (int)std::max<size_t>(1, std::min<size_t>(8, img_bytes / ((size_t)7 << 19)));
-            nbands = std::min(std::min(nbands, kMaxBands), H);
-            const int rows_per = (H + nbands - 1) / nbands;
-            nbands = (H + rows_per - 1) / rows_per;
-            for (int b = 0; b <= nbands; ++b) edge[b] = std::min(H, b * rows_per);
-        }
-        const char *env = auto_bands ? getenv("DCB_BAND_EDGES") : nullptr;
-        if (env != nullptr && env[0] != 0 && H >= 64) {
-            int n = 0, acc = 0;
-            edge[0] = 0;
-            for (const char *q = env; *q != 0 && n < kMaxBands;) {
-                char *e = nullptr;
-                const long v = strtol(q, &e, 10);
-                if (e == q || v <= 0) break;
-                acc += (int)v;
-                const int row = (int)std::min<long long>(H, (long long)H * acc / 64);
-                if (row > edge[n]) edge[++n] = row;
-                q = (*e == ',') ? e + 1 : e;
-            }
-            if (n == 0 || edge[n] < H) {
-                if (n < kMaxBands) edge[++n] = H; else edge[n] = H;
-            }
-            nbands = n;
-        }
-    }
+    nbands = band_edges(H, W, nbands, edge);
     auto band_of = [&](int row) -> int {   // the band holding row `row`
         int b = 0;
         while (b < nbands - 1 && edge[b + 1] <= row) ++b;

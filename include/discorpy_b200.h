@@ -159,6 +159,12 @@ int dcb_unwarp_image_backward_host_f32(const float *src_host, float *dst_host, i
                                        const dcb_radial *model_host,
                                        const dcb_options *opt_host, int nbands);
 
+/* The row-band schedule the host-buffer entries use for an H x W float32 image
+ * (`nbands` as in those calls: 0 = library default): edges[0] = 0 < edges[1] < ...
+ * < edges[*count] = H, *count <= 32; `edges` holds 33 ints.  Diagnostics / tests;
+ * needs no GPU. */
+int dcb_host_band_edges(int H, int W, int nbands, int *edges, int *count);
+
 /* Host-to-host copy of `rows` rows of `width_bytes` bytes (pitches in bytes) by the
  * library's pool of host threads with non-temporal stores -- what stages pageable
  * (ordinary NumPy) data into page-locked buffers and results back out of them

@@ -219,3 +219,38 @@ def test_host_copy_2d_matches_numpy():
             _cabi.call("dcb_host_copy_2d", ctypes.c_void_p(dst.ctypes.data + do), dp,
                        ctypes.c_void_p(src.ctypes.data + so), sp, width, rows)
             assert np.array_equal(dst, want), (rows, width, so, do)
+
+
+def test_host_band_schedule():
+    """dcb_host_band_edges: the row bands of the host-buffer pipeline for any image shape --
+    strictly increasing from 0 to H, at most 32 bands, 2 / 2 / 4 MiB bands at both ends of large
+    images, the requested number of equal bands otherwise (no GPU needed)."""
+    import ctypes
+    import os
+
+    def edges(h, w, nb=0):
+        buf = (ctypes.c_int * 33)()
+        cnt = ctypes.c_int(0)
+        _cabi.call("dcb_host_band_edges", h, w, nb, buf, ctypes.byref(cnt))
+        return list(buf[:cnt.value + 1])
+
+    shapes = [(1, 1), (7, 3), (512, 640), (2048, 2048), (2160, 2560), (4096, 4096), (8192, 8192),
+              (3000, 5000), (16, 600000), (40, 2000000), (100000, 100), (8388607, 1), (33, 8388607)]
+    for (h, w) in shapes:
+        for nb in (0, 1, 2, 5, 8, 31, 32, 100):
+            e = edges(h, w, nb)
+            assert e[0] == 0 and e[-1] == h and 1 <= len(e) - 1 <= 32, (h, w, nb, e)
+            assert all(b > a for a, b in zip(e, e[1:])), (h, w, nb, e)
+            if nb > 0:
+                assert len(e) - 1 <= min(nb, h)
+    assert [b - a for a, b in zip(edges(4096, 4096), edges(4096, 4096)[1:])] == \
+        [128, 128, 256] + [384] * 8 + [256, 128, 128]
+    assert len(edges(2160, 2560)) - 1 == 6 and len(edges(1024, 1024)) - 1 == 1
+    os.environ["DCB_BAND_EDGES"] = "8,8,16,32"
+    try:
+        assert edges(4096, 4096) == [0, 512, 1024, 2048, 4096]
+        assert edges(4096, 4096, 4) == [0, 1024, 2048, 3072, 4096]      # explicit counts ignore it
+        os.environ["DCB_BAND_EDGES"] = "1,1"
+        assert edges(640, 640) == [0, 10, 20, 640]
+    finally:
+        del os.environ["DCB_BAND_EDGES"]
