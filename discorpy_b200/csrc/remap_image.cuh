@@ -65,6 +65,13 @@ struct ImageParams {
     PerspDev per;
 };
 
+// 1 (default): the exact path's window constants are formed inside its branch and the output row
+// address with one 32 x 32 -> 64 bit multiply -- 12 of the ~107 instructions of the tile prologue
+// (exact 42.9 -> 42.6 us, float32 blend 31.5 -> 30.8, lerp64 38.5 -> 39.2, nearest 26.3 -> 26.4:
+// profiles/r2/ab2_lazywin.txt); 0: in the prologue, for A/B builds
+#ifndef DCB_IMG_LAZYWIN
+#define DCB_IMG_LAZYWIN 1
+#endif
 // A/B builds: L2 eviction priority of the source boxes (1 evict_first, 2 evict_last, 0 no hint);
 // -1: the kernel's own choice (see issue_box)
 #ifndef DCB_IMG_L2HINT
@@ -942,17 +949,24 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             const int y_base = p.row0 + tyi * TH + ga * kWarps + warp;
             const int rows_left = y_end - y_base;   // rows y_base + kWarps j exist for kWarps j < rows_left
             const int nrow = min(gb - ga, (rows_left + kWarps - 1) / kWarps);  // warp-uniform, may be <= 0
+#if !DCB_IMG_LAZYWIN
             // bits(2^23 + n) - magic = n - box origin
             const int magic_x = 0x4B000000 + box.bx0, magic_y = 0x4B000000 + box.by0;
             // fast-path window: footprint inside the box and strictly inside the image
             const int lim_x = box.use ? min(p.bw - 1, wmax - box.bx0) : 0;
             const int lim_y = box.use ? min(p.bh - 1, p.ylast - box.by0) : 0;
+#endif
             const int bw = kImgBoxW > 0 ? kImgBoxW : p.bw;
             const int sb = i & (NBUF - 1);
             const float *rawt =
                 reinterpret_cast<const float *>(smem + (size_t)sb * p.stage_bytes);
             const bool full_w = __all_sync(0xffffffffu, txi * kTileW + kTileW - 1 <= wmax);  // CTA-uniform
+#if DCB_IMG_LAZYWIN
+            // (row pitches are below 2^31 elements: one 32 x 32 -> 64 bit multiply)
+            float *orow = p.dst + (long long)(y_base - p.row0) * (long long)(int)p.dst_pitch + x_base;
+#else
             float *orow = p.dst + (long long)(y_base - p.row0) * p.dst_pitch + x_base;
+#endif
             double yd = (double)y_base;
             // patch path, per tile: the x rounding constants and the tap address of image pixel (0, 0)
             const int shx_t = box.shx;
@@ -1145,6 +1159,16 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
                     }
                 }
                 if (!done) {
+#if DCB_IMG_LAZYWIN
+                // the exact path's window arithmetic, formed here and not in the tile prologue (the
+                // empty asm keeps the compiler from hoisting it back: every tile would pay for what
+                // 1 % of the rows use)
+                int wbx0 = box.bx0, wby0 = box.by0;
+                asm volatile("" : "+r"(wbx0), "+r"(wby0));
+                const int magic_x = 0x4B000000 + wbx0, magic_y = 0x4B000000 + wby0;
+                const int lim_x = box.use ? min(p.bw - 1, wmax - wbx0) : 0;
+                const int lim_y = box.use ? min(p.bh - 1, p.ylast - wby0) : 0;
+#endif
                 float xf[kCols], yf[kCols];
                 ev.row(p, yd, xf, yf);
                 float tfx[kCols], tfy[kCols];
