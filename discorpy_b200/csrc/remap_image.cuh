@@ -65,12 +65,16 @@ struct ImageParams {
     PerspDev per;
 };
 
-// 1 (default): the exact path's window constants are formed inside its branch and the output row
-// address with one 32 x 32 -> 64 bit multiply -- 12 of the ~107 instructions of the tile prologue
-// (exact 42.9 -> 42.6 us, float32 blend 31.5 -> 30.8, lerp64 38.5 -> 39.2, nearest 26.3 -> 26.4:
-// profiles/r2/ab2_lazywin.txt); 0: in the prologue, for A/B builds
+// The tile prologue (run by every thread for every tile, ~10 % of all instructions):
+// 1: the exact path's window constants are formed inside its branch and the output row address with
+//    one 32 x 32 -> 64 bit multiply -- 12 of ~107 instructions (exact 42.9 -> 42.6 us, float32 blend
+//    31.5 -> 30.8: profiles/r2/ab2_lazywin.txt);
+// 2 (default): the row address as one UNSIGNED multiply-add and the row count with a shift instead
+//    of a signed division -- 7 more (exact 42.7 -> 41.3 us: the register allocation of the exact
+//    kernel's row loop changes with it; profiles/r2/ab2_lazy2.txt);
+// 0: everything in the prologue, for A/B builds
 #ifndef DCB_IMG_LAZYWIN
-#define DCB_IMG_LAZYWIN 1
+#define DCB_IMG_LAZYWIN 2
 #endif
 // A/B builds: L2 eviction priority of the source boxes (1 evict_first, 2 evict_last, 0 no hint);
 // -1: the kernel's own choice (see issue_box)
@@ -948,7 +952,12 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             const int ga = (int)(ug & 0xffu), gb = (int)(ug >> 8);
             const int y_base = p.row0 + tyi * TH + ga * kWarps + warp;
             const int rows_left = y_end - y_base;   // rows y_base + kWarps j exist for kWarps j < rows_left
+#if DCB_IMG_LAZYWIN >= 2
+            const int nrow = min(gb - ga, (rows_left + kWarps - 1) >> 3);  // warp-uniform, may be <= 0
+            static_assert(kWarps == 8, "row groups of eight warps");
+#else
             const int nrow = min(gb - ga, (rows_left + kWarps - 1) / kWarps);  // warp-uniform, may be <= 0
+#endif
 #if !DCB_IMG_LAZYWIN
             // bits(2^23 + n) - magic = n - box origin
             const int magic_x = 0x4B000000 + box.bx0, magic_y = 0x4B000000 + box.by0;
@@ -963,7 +972,13 @@ __global__ void __launch_bounds__(kImgThreads, MINB)
             const bool full_w = __all_sync(0xffffffffu, txi * kTileW + kTileW - 1 <= wmax);  // CTA-uniform
 #if DCB_IMG_LAZYWIN
             // (row pitches are below 2^31 elements: one 32 x 32 -> 64 bit multiply)
+#if DCB_IMG_LAZYWIN >= 2
+            // (all three terms are non-negative and below 2^31: one unsigned multiply-add)
+            float *orow = p.dst + ((unsigned long long)(unsigned)(y_base - p.row0) * (unsigned)p.dst_pitch +
+                                   (unsigned)x_base);
+#else
             float *orow = p.dst + (long long)(y_base - p.row0) * (long long)(int)p.dst_pitch + x_base;
+#endif
 #else
             float *orow = p.dst + (long long)(y_base - p.row0) * p.dst_pitch + x_base;
 #endif
