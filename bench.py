@@ -757,27 +757,27 @@ def bench_exchange(dcb, multigpu, post, comm, rank, world):
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant
 # kernel, from the committed `ncu --set full` capture (profiles/); None until
 # a capture exists for the current kernel.
-TRAFFIC_BYTES_PER_LAUNCH = 76549632 + 17848064
-TRAFFIC_SOURCE = ("profiles/r2/ncu_image_r2zf_exact.txt: dram__bytes_read.sum 76.5 MB + "
-                  "dram__bytes_write.sum 17.8 MB of one launch (most of the 64 MiB output is "
+TRAFFIC_BYTES_PER_LAUNCH = 78657280 + 18953216
+TRAFFIC_SOURCE = ("profiles/r2/ncu_image_r2zp_exact.txt: dram__bytes_read.sum 78.7 MB + "
+                  "dram__bytes_write.sum 19.0 MB of one launch (most of the 64 MiB output is "
                   "still dirty in the 126 MB L2 when the profiled launch ends)")
 # What the SM side of one launch costs at 100 % of each pipe (us), from the instruction mix of
-# the committed capture (profiles/r2/ncu_image_r2zf_exact.txt: thread instructions per pixel by
+# the committed capture (profiles/r2/ncu_image_r2zp_exact.txt: thread instructions per pixel by
 # pipe) and the pipe rates measured in round 1 (profiles/r1/microbench_*.txt: fp64 60.1 and XU
 # 15.6 thread-ops per clock per SM, issue 128): 16.78 Mpx / 148 SMs / 1.965 GHz x ops / rate.
 # issue_fp64_dispatch_us is the co-limit the ablation runs of round 2 point to
 # (profiles/r2/ablation_raw2_r2a1.txt): an fp64 instruction holds a sub-partition's issue port for
 # its whole dispatch -- 2.13 cycles, 3.07 with three distinct source registers -- so the 17.6 fp64
-# operations per pixel (8 of them three-register forms) cost 45 issue cycles, the other 41.2
+# operations per pixel (8 of them three-register forms) cost 45 issue cycles, the other 38.8
 # instructions one each.
 def _colimit(ops_per_px, rate):
     return H * W / 148.0 / 1965.0 * ops_per_px / rate          # us
 
 
 COLIMIT = {"fp64_us": _colimit(17.6, 60.1), "xu_us": _colimit(0.2, 15.6),
-           "issue_us": _colimit(58.8, 128.0),
-           "issue_fp64_dispatch_us": _colimit(41.2 + 8 * 3.07 + 9.6 * 2.13, 128.0),
-           "source": "profiles/r2/ncu_image_r2zf_exact.txt instruction mix; pipe rates "
+           "issue_us": _colimit(56.4, 128.0),
+           "issue_fp64_dispatch_us": _colimit(38.8 + 8 * 3.07 + 9.6 * 2.13, 128.0),
+           "source": "profiles/r2/ncu_image_r2zp_exact.txt instruction mix; pipe rates "
                      "profiles/r1/microbench_v1.txt, microbench_fp64_operand_forms.txt; "
                      "profiles/r2/ablation_raw2_r2a1.txt"}
 
