@@ -848,6 +848,9 @@ static int check_image_args(const void *src, const void *dst, int H, int W, size
     REQUIRE(src_pitch >= (size_t)W * 4 && src_pitch % 4 == 0, "bad source pitch %zu", src_pitch);
     REQUIRE(dst_pitch >= (size_t)W * 4 && dst_pitch % 4 == 0, "bad destination pitch %zu",
             dst_pitch);
+    // (the kernels form row offsets with 32 x 32 -> 64 bit multiplies)
+    REQUIRE((src_pitch >> 2) < (1ull << 31) && (dst_pitch >> 2) < (1ull << 31),
+            "row pitch exceeds 2^31 elements");
     return DCB_OK;
 }
 
